@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — batched env-steps/sec of the fused CUDA step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one episode pass over the batch: every one of the B environments per GPU (default 65 536,
+BASELINE.json configs[2]: CliffordGym 8q all-to-all {H,S,CX}) is restored to its synthetic target and stepped
+T = max_depth = 128 times with a resident int32[T][B] action stream, i.e. T fused launches.  `value` is
+env-steps/sec over all GPUs with inputs resident in HBM; `e2e` is the same episode driven through the C-ABI
+call with HOST buffers (actions H2D, reward/done/success D2H every env-step, stream synchronised).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+# algorithmic bytes per env-step (fp32 obs, u8 mask, i32 action, f32 reward, u8 done,
+# packed state + metrics read and written once).
+ALGO_BYTES = {"C1_perm_grid3": 449, "C2_lf8_line": 375, "C3_clifford8_full": 1249, "C4_pauli10_line": 2377, "C5_perm27_heavyhex": 3225}
+METRIC = "batched env-steps/sec (CliffordGym 8q all-to-all {H,S,CX})"
+UNIT = "env-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3_clifford8_full")
+    ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
+    ap.add_argument("--episode-steps", type=int, default=128)
+    ap.add_argument("--add-inverts", type=int, default=0)
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="envs in the CPU baseline sample (0 = calibrate to ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from qiskit_gym_b200 import workloads as W
+    kind, n, gateset, kw = W.baseline_configs()[args.config]
+    return kind, n, gateset, dict(kw)
+
+
+def config_json(args, n_gpus, extra=None):
+    c = {
+        "workload": f"{args.config}: BASELINE.json config, {args.envs} envs per GPU x {args.episode_steps} env-steps per step "
+                    f"(set_state targets: identity scrambled by 256 random gates; uniform random actions; add_inverts={bool(args.add_inverts)}, "
+                    "add_perms=False, track_solution=True, default MetricsWeights)",
+        "envs_per_gpu": args.envs, "env_steps_per_step": args.episode_steps, "n_gpus": n_gpus,
+        "l2_policy": "observation tensor rotates over buffers totalling > 2x L2 (126 MB); every launch writes a slab larger than it can keep resident",
+    }
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline leg (the only places that execute oracle/)
+# ------------------------------------------------------------------------------------------------------
+def cpu_run(args, envs, steps=1, warmup=0, threads=None):
+    from oracle import oracle as orc
+    from qiskit_gym_b200 import workloads as W
+    kind, n, gateset, kw = workload(args)
+    threads = threads or (os.cpu_count() or 1)
+    pk = dict(kw)
+    if kind != W.PAULI:
+        pk["add_inverts"] = bool(args.add_inverts)
+    cfg = orc.make_config(kind, n, gateset, add_perms=False, **pk)
+    T = args.episode_steps
+    targets = W.random_targets(kind, n, gateset, envs, 20261017 + 3, scramble=256)
+    lens = W.payload_lengths(kind, n, targets)
+    rng = np.random.Generator(np.random.PCG64(20261017))
+    actions = W.random_actions(rng, T, envs, len(gateset))
+    coins = rng.integers(0, 2, size=(T, envs)).astype(np.uint8) if (args.add_inverts and kind != W.PAULI) else None
+    times = []
+    for i in range(warmup + steps):
+        sec, _ = orc.bench(cfg, targets, lens, actions, coins=coins, threads=threads)
+        if i >= warmup:
+            times.append(sec)
+    tot = sum(times)
+    return {"value": envs * T * steps / tot, "seconds": tot, "threads": threads, "envs": envs, "T": T}
+
+
+def calibrate_cpu_envs(args, target_seconds, threads):
+    probe = cpu_run(args, envs=max(64, 16 * threads), threads=threads)
+    rate = probe["value"]
+    envs = int(rate * target_seconds / args.episode_steps)
+    return max(256, min(envs // 64 * 64, 1 << 20))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    envs = args.cpu_sample_envs or calibrate_cpu_envs(args, 1.0, threads)   # ~1 s of CPU work per step
+    r = cpu_run(args, envs, steps=args.steps, warmup=args.warmup, threads=threads)
+    sample = f"{envs} envs x {args.episode_steps} env-steps per step, oracle C++ port of the Rust core (step+observe+masks+reward+is_final per env-step), {threads} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC if args.config == "C3_clifford8_full" else f"batched env-steps/sec ({args.config})",
+        "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 (byte-per-bit GF(2)) + f32 reward", "data": "synthetic",
+        "config": config_json(args, args.gpus, {"reference_sample": sample}),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from qiskit_gym_b200 import BatchedEnv
+    from qiskit_gym_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, n, gateset, kw = workload(args)
+    B, T, K, Wm = args.envs, args.episode_steps, args.steps, max(args.warmup, 0)
+    A = len(gateset)
+    pk = dict(kw)
+    if kind != W.PAULI:
+        pk["add_inverts"] = bool(args.add_inverts)
+    env = BatchedEnv(kind, n, gateset, B, device=local, max_depth=T, add_perms=False, **pk)
+    obs_size = int(np.prod(env.obs_shape()))
+    # synthetic inputs (seeded per global env id range so shards differ but are reproducible)
+    targets = W.random_targets(kind, n, gateset, B, 20261017 + 3 + 1000 * rank, scramble=256)
+    env.set_state(targets)
+    env.snapshot()
+    rng = np.random.Generator(np.random.PCG64(20261017 + rank))
+    actions_h = W.random_actions(rng, T, B, A)
+    actions = torch.from_numpy(actions_h).to(dev)
+    coins = None
+    if args.add_inverts and kind != W.PAULI:
+        coins = torch.from_numpy(rng.integers(0, 2, size=(T, B)).astype(np.uint8)).to(dev)
+    # rotating observation / mask buffers: > 2x L2 in total
+    obs_bytes = B * obs_size * 4
+    nbuf = max(2, int(np.ceil(2 * 126e6 / max(obs_bytes, 1))) + 1)
+    nbuf = min(nbuf, 64)
+    obs_bufs = [torch.empty((B, obs_size), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    mask_bufs = [torch.empty((B, A), dtype=torch.bool, device=dev) for _ in range(nbuf)]
+
+    def episode():
+        env.restore()
+        for t in range(T):
+            env.step(actions[t], coins=None if coins is None else coins[t], obs=obs_bufs[t % nbuf], mask=mask_bufs[t % nbuf])
+
+    # capture one episode (restore + T fused launches) in a CUDA graph: the inner loop is launch-bound from Python
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        episode()
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            episode()
+        for _ in range(Wm):
+            graph.replay()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
+        ev0.record(stream)
+        for _ in range(K):
+            graph.replay()
+        ev1.record(stream)
+        stream.synchronize()
+        t_wall1 = time.time()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    total_env_steps = world * B * T * K
+    value = total_env_steps / (ms * 1e-3)
+    errs = int(env.errors().max().item())
+
+    # ---- e2e: the same episode through the host-buffer C-ABI call (qg_step_host) -------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin_a = torch.from_numpy(actions_h).pin_memory()
+        a_np = pin_a.numpy()
+        rew = torch.empty(B, dtype=torch.float32).pin_memory(); don = torch.empty(B, dtype=torch.uint8).pin_memory(); suc = torch.empty(B, dtype=torch.uint8).pin_memory()
+        rew_np, don_np, suc_np = rew.numpy(), don.numpy(), suc.numpy()
+        Ke = max(1, min(K, 5))
+        with torch.cuda.stream(stream):
+            def episode_host():
+                env.restore()
+                acc = 0.0
+                for t in range(T):
+                    env.step_host(a_np[t], rew_np, don_np, suc_np, obs=obs_bufs[t % nbuf], mask=mask_bufs[t % nbuf])
+                    acc += float(rew_np[0])
+                return acc
+            episode_host()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(Ke):
+                episode_host()
+            e1.record(stream)
+            stream.synchronize()
+            ems = e0.elapsed_time(e1)
+        if world > 1:
+            t2 = torch.tensor([ems], dtype=torch.float64, device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            ems = float(t2.item())
+        e2e = {"value": world * B * T * Ke / (ems * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": T * B * 4, "d2h_bytes_per_step": T * B * 6,
+               "note": "per env-step: int32 actions pinned H2D, fused step (obs+mask stay on device for the policy), f32 reward + u8 done + u8 success D2H, stream sync",
+               "steps": Ke}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo = ALGO_BYTES.get(args.config)
+    launch_us = ms * 1e3 / (T * K)
+    roofline = None
+    if algo:
+        achieved = algo * B / (launch_us * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "kernel": "qg::k_step<CLIFFORD,64,STEP>", "algorithmic_bytes_per_env_step": algo, "avg_launch_us": launch_us}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        envs = args.cpu_sample_envs or calibrate_cpu_envs(args, 12.0, threads)
+        r = cpu_run(args, envs, threads=threads)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{envs} envs x {T} env-steps (same config, targets and action distribution), oracle C++ port of the Rust core, "
+                                  f"per env-step step+observe+masks+reward+is_final, {threads} host threads, {r['seconds']:.1f} s"}
+    line = {
+        "metric": METRIC if args.config == "C3_clifford8_full" else f"batched env-steps/sec ({args.config})",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (GF(2)) + f32 reward/obs", "data": "synthetic",
+        "config": config_json(args, world, {"obs_buffers": nbuf, "cuda_graph": True}),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": T * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "engine_error_flags": errs,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/* qg_engine.h — C ABI of the B200 batched synthesis-environment engine.
+ *
+ * This is the drop-in boundary for qiskit-gym's one data-parallel hot path: stepping many
+ * independent synthesis environments (Permutation, LinearFunction, Clifford, PauliNetwork)
+ * and the synth-time rollout search.  Every entry point replaces one method of the
+ * reference's `impl twisterl::rl::env::Env for X` blocks, batched over B environments.
+ * Reference paths are relative to /root/reference/rust/src.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; all functions return an int status
+ *    (QG_OK = 0, negative = error; message via qg_last_error()); nothing throws.
+ *  - pointers named *_dev are device pointers on the engine's GPU; *_host are host pointers.
+ *  - every device entry takes a CUDA stream (`qg_stream`, a cudaStream_t), is asynchronous on
+ *    that stream and allocates nothing; the *_host convenience calls synchronise the stream.
+ *  - one engine is bound to one GPU and is driven by one host thread at a time.
+ *  - the library fails (QG_ERR_CUDA) when no CUDA device is usable: there is no CPU fallback.
+ */
+#ifndef QG_ENGINE_H
+#define QG_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QG_API __attribute__((visibility("default")))
+
+typedef struct CUstream_st* qg_stream;   /* == cudaStream_t */
+typedef struct qg_engine qg_engine;
+typedef struct qg_twists qg_twists;
+
+/* status codes */
+enum {
+    QG_OK = 0,
+    QG_ERR_INVALID = -1,     /* bad argument / config (the reference raises ValueError/TypeError or panics) */
+    QG_ERR_CUDA = -2,        /* CUDA runtime failure or no device */
+    QG_ERR_UNSUPPORTED = -3, /* size outside the engine's limits (see qg_limits) */
+    QG_ERR_STATE = -4        /* malformed set_state payload */
+};
+
+/* envs (lib.rs:24-30) */
+enum { QG_ENV_PERMUTATION = 0, QG_ENV_LINEAR_FUNCTION = 1, QG_ENV_CLIFFORD = 2, QG_ENV_PAULI_NETWORK = 3 };
+
+/* gate kinds (envs/common.rs:19-29) */
+enum { QG_H = 0, QG_S = 1, QG_SDG = 2, QG_SX = 3, QG_SXDG = 4, QG_CX = 5, QG_CZ = 6, QG_SWAP = 7 };
+
+typedef struct qg_gate { int32_t kind; int32_t q0; int32_t q1; } qg_gate;   /* q1 unused for 1-qubit gates */
+
+/* Constructor arguments of the four pyo3 classes (permutation.rs:266-299,
+ * linear_function.rs:373-406, clifford.rs:390-423, pauli.rs:728-775); `None` defaults are
+ * resolved by the caller (qg_config_default does it). */
+typedef struct qg_config {
+    int32_t env_kind;
+    int32_t num_qubits;
+    int32_t difficulty;
+    int32_t depth_slope;
+    int32_t max_depth;
+    int32_t num_gates;
+    const qg_gate* gateset;
+    float w_n_cnots, w_n_layers_cnots, w_n_layers, w_n_gates;   /* MetricsWeights, metrics.rs:149-184 */
+    int32_t add_inverts;          /* ignored by PauliNetwork */
+    int32_t add_perms;
+    int32_t track_solution;
+    /* PauliNetwork only */
+    int32_t max_rotations;
+    int32_t pauli_diff_scale;
+    float num_qubits_decay;
+    int32_t final_pauli_layers;
+    float pauli_layer_reward;
+    /* engine extras */
+    int32_t solution_capacity;    /* entries kept per env; 0 = max_depth (+ rotations for Pauli) */
+} qg_config;
+
+/* error flag bits reported by qg_read_errors (situations where the reference panics) */
+enum {
+    QG_FLAG_SINGULAR = 1,        /* inverse of a singular matrix requested (linear_function.rs:131, clifford.rs:155) */
+    QG_FLAG_SOLUTION_OVERFLOW = 2,
+    QG_FLAG_LAYER_OVERFLOW = 4,  /* a layer counter passed 32767 */
+    QG_FLAG_BAD_ROTATION = 8,    /* zero-weight rotation met by the cleaner (pauli_network.rs:114 unwrap) */
+    QG_FLAG_BAD_ACTION = 16      /* negative action index */
+};
+
+/* ---- library / host-only helpers (usable without a GPU) ---------------------------------- */
+QG_API const char* qg_version(void);
+QG_API const char* qg_last_error(void);
+/* Fills every field with the reference defaults (metrics 0.01/0/0/0.0001, add_inverts=add_perms=
+ * track_solution=1, depth_slope=2, max_depth=128, difficulty=1, max_rotations=5, pauli_diff_scale=8,
+ * num_qubits_decay=0.5, final_pauli_layers=-1 (=> max_rotations+2), pauli_layer_reward=0.01). */
+QG_API void qg_config_default(qg_config* cfg, int32_t env_kind);
+/* Gate-name parser of common.rs:46-100 (trim, case-insensitive, arity check).
+ * Returns the gate kind, QG_ERR_INVALID for an unknown name, QG_ERR_STATE for a wrong arity. */
+QG_API int qg_gate_kind_from_name(const char* name, int32_t num_indices);
+/* Validates a config the way construction would (gate arity/indices, size limits). */
+QG_API int qg_config_validate(const qg_config* cfg);
+/* obs_shape() / num_actions() / set_state payload length (0 = variable, PauliNetwork) */
+QG_API int qg_config_obs_shape(const qg_config* cfg, int32_t out_shape[2]);
+QG_API int64_t qg_config_state_len(const qg_config* cfg);
+/* twists() (symmetry.rs:297-361): obs_perms/act_perms (or raw qubit perms for PauliNetwork). */
+QG_API int qg_twists_create(const qg_config* cfg, qg_twists** out);
+QG_API void qg_twists_destroy(qg_twists* t);
+QG_API int64_t qg_twists_count(const qg_twists* t);
+QG_API int64_t qg_twists_obs_len(const qg_twists* t);   /* entries per obs perm */
+QG_API int64_t qg_twists_act_len(const qg_twists* t);
+QG_API int qg_twists_copy(const qg_twists* t, int64_t* obs_perms_host, int64_t* act_perms_host);
+/* device memory an engine of this config and batch needs (bytes) */
+QG_API int64_t qg_workspace_bytes(const qg_config* cfg, int64_t batch);
+
+/* ---- engine lifetime ------------------------------------------------------------------- */
+/* workspace_dev: caller-owned device buffer of qg_workspace_bytes() bytes (256-byte aligned), or
+ * NULL to let the engine cudaMalloc it.  All envs start as the reference constructor leaves them
+ * (identity, depth 1, success, reward 1.0). */
+QG_API int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspace_dev, qg_engine** out);
+QG_API void qg_destroy(qg_engine* e);
+QG_API int64_t qg_batch(const qg_engine* e);
+QG_API int32_t qg_num_actions(const qg_engine* e);          /* Env::num_actions */
+QG_API int32_t qg_obs_size(const qg_engine* e);             /* prod(obs_shape()) */
+QG_API int qg_obs_shape(const qg_engine* e, int32_t out_shape[2]);   /* Env::obs_shape */
+QG_API int qg_set_difficulty(qg_engine* e, int32_t difficulty);      /* Env::set_difficulty */
+QG_API int32_t qg_get_difficulty(const qg_engine* e);                /* Env::get_difficulty */
+
+/* ---- state in ---------------------------------------------------------------------------- */
+/* Env::set_state (permutation.rs:168-173, linear_function.rs:279-283, clifford.rs:299-304,
+ * pauli.rs:517-552) for `count` envs starting at env `first`: states_host holds `count` payloads of
+ * exactly the reference's Vec<i64> encoding, payload i at states_host + i*stride (for PauliNetwork each
+ * payload is self-delimiting and `stride` is its allocated slot).  broadcast=1 loads payload 0 into all
+ * `count` envs (synth search).  depth := max_depth, internals reset. */
+QG_API int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride, int64_t first,
+                        int64_t count, int32_t broadcast, qg_stream stream);
+/* Env::reset for every env: identity scrambled by `difficulty` random gates drawn from
+ * Philox4x32-10(seed; env id, draw index) (permutation.rs:175-192, linear_function.rs:285-300,
+ * clifford.rs:306-319, pauli.rs:554-586).  env ids are first_env_id + local index so a sharded batch
+ * draws the same stream as an unsharded one. */
+QG_API int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream);
+
+/* `Clone` of the whole batch (the reference clones one prototype env per episode / rollout,
+ * permutation.rs:29, linear_function.rs:154, clifford.rs:179, pauli.rs:307-337): qg_snapshot keeps a
+ * device copy of every env record; qg_restore puts it back (solutions restart at the snapshot's length). */
+QG_API int qg_snapshot(qg_engine* e, qg_stream stream);
+QG_API int qg_restore(qg_engine* e, qg_stream stream);
+
+/* ---- the fused step ------------------------------------------------------------------- */
+/* Env::step + reward + is_final + success + observe + masks for all B envs in one launch.
+ *  actions_dev  int32[B]            action per env (>= num_actions: state no-op, depth still ticks)
+ *  coins_dev    uint8[B] or NULL    injected gen_bool(0.5) results for add_inverts; NULL = Philox
+ *  perm_raw_dev uint32[B] or NULL   PauliNetwork+add_perms: raw 32-bit draw for observe()'s perm pick
+ *                                   (index = mulhi(raw, n_perms)); NULL = Philox
+ *  obs_dev      float[B*obs_size] or NULL   dense 0/1 observation (row-major obs_shape per env)
+ *  mask_dev     uint8[B*num_actions] or NULL
+ *  reward_dev   float[B] or NULL;  done_dev uint8[B] or NULL (= is_final);  success_dev uint8[B] or NULL */
+QG_API int qg_step(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev,
+                   float* obs_dev, uint8_t* mask_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
+                   qg_stream stream);
+/* Same step with HOST buffers (pinned or pageable): copies actions (and coins) in, runs the step
+ * writing obs/mask to the given DEVICE tensors (may be NULL), copies reward/done/success out and
+ * synchronises.  This is the end-to-end call a host-side collector makes. */
+QG_API int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins_host,
+                        float* obs_dev, uint8_t* mask_dev,
+                        float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream);
+
+/* ---- stand-alone reads (no state change except the PauliNetwork perm pick) ----------------- */
+QG_API int qg_observe(qg_engine* e, const uint32_t* perm_raw_dev, float* obs_dev, qg_stream stream);  /* Env::observe, dense */
+QG_API int qg_masks(qg_engine* e, uint8_t* mask_dev, qg_stream stream);                                /* Env::masks */
+QG_API int qg_read_status(qg_engine* e, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
+                          int32_t* depth_dev, qg_stream stream);          /* reward/is_final/success/depth */
+QG_API int qg_read_metrics(qg_engine* e, uint32_t* counts_dev /*[B][4]: cnots, cnot layers, layers, gates*/, qg_stream stream);
+QG_API int qg_read_errors(qg_engine* e, uint32_t* flags_dev /*[B]*/, qg_stream stream);
+/* Raw state of one env in the reference's own byte-per-entry layout (perm: n bytes; LF: n*n;
+ * Clifford: 4n*n; PauliNetwork: 2n x (2n+R) row-major, R = rotations loaded), for parity tests. */
+QG_API int qg_get_state_host(qg_engine* e, int64_t env, uint8_t* out_host, int64_t cap, int64_t* len, qg_stream stream);
+/* Env::solution (solution ++ reverse(solution_inv); PauliNetwork rotation words as pauli.rs:685-719). */
+QG_API int qg_solution_host(qg_engine* e, int64_t env, uint32_t* out_host, int32_t cap, int32_t* len, qg_stream stream);
+
+/* ---- synth search (rollout driver pieces around the policy) ---------------------------- */
+/* Starts a search over the engine's B rollouts: zeroes the per-rollout return accumulators.
+ * The caller loads the target first (qg_set_state broadcast=1). */
+QG_API int qg_search_begin(qg_engine* e, uint64_t seed, int64_t first_rollout_id, qg_stream stream);
+/* One decision for every rollout that is not final yet: pick an action from the policy's
+ * non-negative action weights (weights_dev float[B*num_actions], e.g. softmax probabilities; masked by
+ * Env::masks), deterministic=1: first arg-max; 0: inverse-CDF sample with a Philox uniform and a
+ * sequential f32 cumulative sum; then the fused step; return += reward.  Final rollouts are left
+ * untouched.  chosen_dev int32[B] or NULL receives the action (-1 for rollouts already final). */
+QG_API int qg_search_step(qg_engine* e, const float* weights_dev, int32_t deterministic,
+                          float* obs_dev, uint8_t* mask_dev, int32_t* chosen_dev, int32_t* num_active_dev, qg_stream stream);
+/* On-GPU best-rollout reduction: key = success<<62 | orderable(return)<<30 | (2^30-1 - rollout id)
+ * (max wins: successful first, then highest return, then lowest id).  Writes the winning key to
+ * *best_key_host and the winner's local env index to *best_env_host (-1 if B == 0). */
+QG_API int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream);
+QG_API int qg_read_returns(qg_engine* e, float* returns_dev, qg_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QG_ENGINE_H */

@@ -1,0 +1,515 @@
+// qg_engine.cu — implementation of the C ABI declared in include/qg_engine.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "qg_host.hpp"
+#include "qg_kernels.cuh"
+
+using namespace qg;
+
+struct qg_twists { Twists t; };
+
+struct qg_engine {
+    qg_config cfg{};                 // gateset pointer re-targeted at `gates`
+    std::vector<qg_gate> gates;
+    Layout L;
+    DevCfg dc{};
+    int device = 0;
+    int64_t B = 0, Bpad = 0;
+    bool owns_ws = false;
+    uint8_t* ws = nullptr;
+    // workspace carve-outs
+    uint32_t* staged = nullptr;      // [Bpad][PW]
+    uint32_t* snap = nullptr;        // [W][Bpad] snapshot of the records
+    bool has_snap = false;
+    int32_t* io_actions = nullptr; uint8_t* io_coins = nullptr; float* io_reward = nullptr; uint8_t* io_done = nullptr; uint8_t* io_success = nullptr;
+    unsigned long long* best = nullptr;
+    // pinned host staging
+    uint32_t* h_staged = nullptr; int64_t h_staged_words = 0;
+    unsigned long long* h_best = nullptr;
+    int epc = 64; size_t smem_bytes = 0; int sm_scr = 0, sm_obs = 0, sm_aux = 0;
+    uint64_t magic_obs = 0, magic_A = 0;
+    int nperms = 0;
+};
+
+namespace {
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+            return QG_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+inline uint64_t magic40(uint32_t d) { return ((1ull << 40) + d - 1) / d; }
+
+struct WsPlan {
+    int64_t rec, snap, sol, ret, gates, ident, qperms, aperms, staged, io_actions, io_coins, io_reward, io_done, io_success, best, total;
+};
+WsPlan plan_ws(const Layout& L, int64_t B, int64_t nperms) {
+    const int64_t Bpad = align_up(std::max<int64_t>(B, 1), 32);
+    WsPlan p{}; int64_t o = 0;
+    auto take = [&](int64_t bytes) { const int64_t at = o; o = align_up(o + bytes, 256); return at; };
+    p.rec = take((int64_t)L.W * Bpad * 4);
+    p.snap = take((int64_t)L.W * Bpad * 4);
+    p.sol = take((int64_t)L.sol_cap * Bpad * 4);
+    p.ret = take(Bpad * 4);
+    p.gates = take((int64_t)L.A * 4);
+    p.ident = take((int64_t)L.SW * 4);
+    p.qperms = take(std::max<int64_t>(nperms * L.n, 1));
+    p.aperms = take(std::max<int64_t>(nperms * L.A * 2, 1));
+    p.staged = take((int64_t)L.PW * Bpad * 4);
+    p.io_actions = take(Bpad * 4); p.io_coins = take(Bpad); p.io_reward = take(Bpad * 4); p.io_done = take(Bpad); p.io_success = take(Bpad);
+    p.best = take(64);
+    p.total = o;
+    return p;
+}
+
+int pauli_perms(const qg_config* cfg, Twists& tw) {
+    if (cfg->env_kind != QG_ENV_PAULI_NETWORK || !cfg->add_perms) { tw = Twists(); return QG_OK; }
+    return compute_twists(cfg, true, tw);
+}
+
+template <int KIND, int EPC, int MODE>
+int launch_step_t(qg_engine* e, const StepArgs& a, cudaStream_t st) {
+    auto kern = k_step<KIND, EPC, MODE>;
+    const unsigned grid = (unsigned)((e->B + EPC - 1) / EPC);
+    kern<<<grid, kThreads, e->smem_bytes, st>>>(e->dc, a);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+template <int KIND, int EPC>
+int prepare_kernels_t(qg_engine* e) {   // opt in to > 48 KB dynamic shared memory once, outside any stream capture
+    if (e->smem_bytes <= 48 * 1024) return QG_OK;
+    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, EPC, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, EPC, MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, EPC, MODE_SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    return QG_OK;
+}
+template <int KIND>
+int prepare_kernels_k(qg_engine* e) { return e->epc == 64 ? prepare_kernels_t<KIND, 64>(e) : prepare_kernels_t<KIND, 32>(e); }
+int prepare_kernels(qg_engine* e) {
+    switch (e->L.kind) {
+        case QG_ENV_PERMUTATION: return prepare_kernels_k<QG_ENV_PERMUTATION>(e);
+        case QG_ENV_LINEAR_FUNCTION: return prepare_kernels_k<QG_ENV_LINEAR_FUNCTION>(e);
+        case QG_ENV_CLIFFORD: return prepare_kernels_k<QG_ENV_CLIFFORD>(e);
+        default: return prepare_kernels_k<QG_ENV_PAULI_NETWORK>(e);
+    }
+}
+template <int KIND, int MODE>
+int launch_step_k(qg_engine* e, const StepArgs& a, cudaStream_t st) {
+    return e->epc == 64 ? launch_step_t<KIND, 64, MODE>(e, a, st) : launch_step_t<KIND, 32, MODE>(e, a, st);
+}
+template <int MODE>
+int launch_step(qg_engine* e, StepArgs a, cudaStream_t st) {
+    if (e->B == 0) return QG_OK;
+    int cur = -1;
+    CUDA_OK(cudaGetDevice(&cur));
+    if (cur != e->device) CUDA_OK(cudaSetDevice(e->device));
+    a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.sm_aux = e->sm_aux; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
+    if (a.mask && (reinterpret_cast<uintptr_t>(a.mask) & 15)) { set_error("mask_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
+    switch (e->L.kind) {
+        case QG_ENV_PERMUTATION: return launch_step_k<QG_ENV_PERMUTATION, MODE>(e, a, st);
+        case QG_ENV_LINEAR_FUNCTION: return launch_step_k<QG_ENV_LINEAR_FUNCTION, MODE>(e, a, st);
+        case QG_ENV_CLIFFORD: return launch_step_k<QG_ENV_CLIFFORD, MODE>(e, a, st);
+        default: return launch_step_k<QG_ENV_PAULI_NETWORK, MODE>(e, a, st);
+    }
+}
+
+int launch_load(qg_engine* e, int64_t first, int64_t count, int broadcast, uint32_t depth_init, cudaStream_t st) {
+    if (count <= 0) return QG_OK;
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    switch (e->L.kind) {
+        case QG_ENV_PERMUTATION: k_load<QG_ENV_PERMUTATION><<<grid, 256, 0, st>>>(e->dc, e->staged, e->L.PW, first, count, broadcast, depth_init); break;
+        case QG_ENV_LINEAR_FUNCTION: k_load<QG_ENV_LINEAR_FUNCTION><<<grid, 256, 0, st>>>(e->dc, e->staged, e->L.PW, first, count, broadcast, depth_init); break;
+        case QG_ENV_CLIFFORD: k_load<QG_ENV_CLIFFORD><<<grid, 256, 0, st>>>(e->dc, e->staged, e->L.PW, first, count, broadcast, depth_init); break;
+        default: k_load<QG_ENV_PAULI_NETWORK><<<grid, 256, 0, st>>>(e->dc, e->staged, e->L.PW, first, count, broadcast, depth_init); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+int ensure_host_staging(qg_engine* e, int64_t words) {
+    if (e->h_staged_words >= words) return QG_OK;
+    if (e->h_staged) cudaFreeHost(e->h_staged);
+    e->h_staged = nullptr; e->h_staged_words = 0;
+    CUDA_OK(cudaMallocHost(&e->h_staged, (size_t)words * 4));
+    e->h_staged_words = words;
+    return QG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qg_version(void) { return "qiskit_gym_b200 0.1.0 (sm_100a)"; }
+const char* qg_last_error(void) { return get_error(); }
+
+void qg_config_default(qg_config* cfg, int32_t env_kind) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->env_kind = env_kind; cfg->difficulty = 1; cfg->depth_slope = 2; cfg->max_depth = 128;
+    cfg->w_n_cnots = 0.01f; cfg->w_n_layers_cnots = 0.0f; cfg->w_n_layers = 0.0f; cfg->w_n_gates = 0.0001f;   // metrics.rs:158-166
+    cfg->add_inverts = env_kind == QG_ENV_PAULI_NETWORK ? 0 : 1; cfg->add_perms = 1; cfg->track_solution = 1;
+    cfg->max_rotations = 5; cfg->pauli_diff_scale = 8; cfg->num_qubits_decay = 0.5f; cfg->final_pauli_layers = -1; cfg->pauli_layer_reward = 0.01f;
+}
+
+int qg_gate_kind_from_name(const char* name, int32_t num_indices) {   // common.rs:61-99
+    if (!name) return QG_ERR_INVALID;
+    std::string s(name);
+    const size_t a = s.find_first_not_of(" \t\r\n\f\v"), b = s.find_last_not_of(" \t\r\n\f\v");
+    s = (a == std::string::npos) ? std::string() : s.substr(a, b - a + 1);
+    for (char& ch : s) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+    static const struct { const char* nm; int kind; int arity; } table[] = {
+        {"h", QG_H, 1}, {"s", QG_S, 1}, {"sdg", QG_SDG, 1}, {"sx", QG_SX, 1}, {"sxdg", QG_SXDG, 1}, {"cx", QG_CX, 2}, {"cz", QG_CZ, 2}, {"swap", QG_SWAP, 2}};
+    for (const auto& t : table)
+        if (s == t.nm) return num_indices == t.arity ? t.kind : QG_ERR_STATE;
+    return QG_ERR_INVALID;
+}
+
+int qg_config_validate(const qg_config* cfg) { return validate_config(cfg); }
+
+int qg_config_obs_shape(const qg_config* cfg, int32_t out_shape[2]) {
+    Layout L; const int rc = make_layout(cfg, L);
+    if (rc != QG_OK) return rc;
+    out_shape[0] = L.obs_rows; out_shape[1] = L.obs_cols;
+    return QG_OK;
+}
+int64_t qg_config_state_len(const qg_config* cfg) {
+    Layout L; const int rc = make_layout(cfg, L);
+    return rc != QG_OK ? rc : L.state_len;
+}
+
+int qg_twists_create(const qg_config* cfg, qg_twists** out) {
+    if (!out) { set_error("null out"); return QG_ERR_INVALID; }
+    qg_twists* t = new (std::nothrow) qg_twists();
+    if (!t) { set_error("out of memory"); return QG_ERR_INVALID; }
+    const int rc = compute_twists(cfg, false, t->t);
+    if (rc != QG_OK) { delete t; return rc; }
+    *out = t; return QG_OK;
+}
+void qg_twists_destroy(qg_twists* t) { delete t; }
+int64_t qg_twists_count(const qg_twists* t) { return t ? (int64_t)t->t.obs_perms.size() : 0; }
+int64_t qg_twists_obs_len(const qg_twists* t) { return (t && !t->t.obs_perms.empty()) ? (int64_t)t->t.obs_perms[0].size() : 0; }
+int64_t qg_twists_act_len(const qg_twists* t) { return (t && !t->t.act_perms.empty()) ? (int64_t)t->t.act_perms[0].size() : 0; }
+int qg_twists_copy(const qg_twists* t, int64_t* obs, int64_t* act) {
+    if (!t) { set_error("null twists"); return QG_ERR_INVALID; }
+    for (const auto& p : t->t.obs_perms) { if (obs) { std::copy(p.begin(), p.end(), obs); obs += p.size(); } }
+    for (const auto& p : t->t.act_perms) { if (act) { std::copy(p.begin(), p.end(), act); act += p.size(); } }
+    return QG_OK;
+}
+
+int64_t qg_workspace_bytes(const qg_config* cfg, int64_t batch) {
+    Layout L; int rc = make_layout(cfg, L);
+    if (rc != QG_OK) return rc;
+    if (batch < 0) { set_error("batch must be >= 0"); return QG_ERR_INVALID; }
+    Twists tw; rc = pauli_perms(cfg, tw);
+    if (rc != QG_OK) return rc;
+    return plan_ws(L, batch, (int64_t)tw.act_perms.size()).total;
+}
+
+int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspace_dev, qg_engine** out) {
+    if (!out) { set_error("null out"); return QG_ERR_INVALID; }
+    *out = nullptr;
+    Layout L; int rc = make_layout(cfg, L);
+    if (rc != QG_OK) return rc;
+    if (batch < 0) { set_error("batch must be >= 0"); return QG_ERR_INVALID; }
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("no such CUDA device (the engine has no CPU fallback)"); return QG_ERR_CUDA; }
+    CUDA_OK(cudaSetDevice(device));
+    Twists tw; rc = pauli_perms(cfg, tw);
+    if (rc != QG_OK) return rc;
+    if (tw.act_perms.size() > 65535) { set_error("PauliNetwork: more than 65535 qubit permutations are not supported"); return QG_ERR_UNSUPPORTED; }
+
+    qg_engine* e = new (std::nothrow) qg_engine();
+    if (!e) { set_error("out of memory"); return QG_ERR_INVALID; }
+    e->cfg = *cfg; e->gates.assign(cfg->gateset, cfg->gateset + cfg->num_gates); e->cfg.gateset = e->gates.data();
+    e->L = L; e->device = device; e->B = batch; e->Bpad = align_up(std::max<int64_t>(batch, 1), 32);
+    e->nperms = (int)tw.act_perms.size();
+    const WsPlan p = plan_ws(L, batch, e->nperms);
+    auto fail = [&](int code) { qg_destroy(e); return code; };
+    if (workspace_dev) {
+        if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) { set_error("workspace must be 256-byte aligned"); return fail(QG_ERR_INVALID); }
+        e->ws = (uint8_t*)workspace_dev;
+    } else {
+        cudaError_t ce = cudaMalloc(&e->ws, (size_t)p.total);
+        if (ce != cudaSuccess) { set_error(std::string("cudaMalloc workspace: ") + cudaGetErrorString(ce)); e->ws = nullptr; return fail(QG_ERR_CUDA); }
+        e->owns_ws = true;
+    }
+    // shared-memory plan: [W | SCR | OW] words per env + one aux word
+    const int words = L.W + L.SCR + L.OW + 1;
+    e->epc = 64;
+    if ((size_t)words * 64 * 4 > 200 * 1024) e->epc = 32;
+    if ((size_t)words * e->epc * 4 > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
+    e->sm_scr = L.W * e->epc; e->sm_obs = (L.W + L.SCR) * e->epc; e->sm_aux = (L.W + L.SCR + L.OW) * e->epc;
+    e->smem_bytes = (size_t)words * e->epc * 4;
+    e->magic_obs = magic40((uint32_t)L.obs_size); e->magic_A = magic40((uint32_t)L.A);
+    rc = prepare_kernels(e);
+    if (rc != QG_OK) return fail(rc);
+
+    DevCfg& d = e->dc;
+    d.kind = L.kind; d.n = L.n; d.D = L.D; d.A = L.A; d.obs_size = L.obs_size; d.obs_cols = L.obs_cols;
+    d.SW = L.SW; d.MW = L.MW; d.W = L.W; d.off_lastg = L.off_lastg; d.off_lastcx = L.off_lastcx; d.off_state = L.off_state; d.off_extra = L.off_extra; d.OW = L.OW;
+    d.max_depth = cfg->max_depth; d.depth_slope = cfg->depth_slope; d.difficulty = cfg->difficulty;
+    d.add_inverts = (L.kind != QG_ENV_PAULI_NETWORK && cfg->add_inverts) ? 1 : 0; d.track = cfg->track_solution ? 1 : 0; d.sol_cap = cfg->track_solution ? L.sol_cap : 0;
+    d.max_rot = L.max_rot; d.Rtot = L.Rtot; d.CW = L.CW; d.nperms = e->nperms;
+    d.w0 = cfg->w_n_cnots; d.w1 = cfg->w_n_layers_cnots; d.w2 = cfg->w_n_layers; d.w3 = cfg->w_n_gates; d.plr = cfg->pauli_layer_reward;
+    d.B = batch; d.Bpad = e->Bpad;
+    d.rec = (uint32_t*)(e->ws + p.rec); d.sol = (uint32_t*)(e->ws + p.sol); d.ret = (float*)(e->ws + p.ret);
+    d.gates = (const uint32_t*)(e->ws + p.gates); d.ident = (const uint32_t*)(e->ws + p.ident);
+    d.qperms = (const uint8_t*)(e->ws + p.qperms); d.aperms = (const uint16_t*)(e->ws + p.aperms);
+    d.seed = 0; d.first_id = 0;
+    d.magic_n = (uint32_t)(((1ull << 32) + (uint32_t)L.n - 1) / (uint32_t)L.n);
+    e->staged = (uint32_t*)(e->ws + p.staged);
+    e->snap = (uint32_t*)(e->ws + p.snap);
+    e->io_actions = (int32_t*)(e->ws + p.io_actions); e->io_coins = e->ws + p.io_coins; e->io_reward = (float*)(e->ws + p.io_reward);
+    e->io_done = e->ws + p.io_done; e->io_success = e->ws + p.io_success; e->best = (unsigned long long*)(e->ws + p.best);
+
+    // constant tables
+    std::vector<uint32_t> gt((size_t)L.A);
+    for (int i = 0; i < L.A; ++i) gt[i] = (uint32_t)e->gates[i].kind | ((uint32_t)e->gates[i].q0 << 8) | ((uint32_t)(e->gates[i].kind >= QG_CX ? e->gates[i].q1 : 0) << 16);
+    std::vector<uint32_t> ident((size_t)L.PW, 0); pack_identity(L, ident.data());
+    cudaError_t ce = cudaMemcpy((void*)d.gates, gt.data(), gt.size() * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy((void*)d.ident, ident.data(), (size_t)L.SW * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && e->nperms > 0) {
+        std::vector<uint8_t> qp((size_t)e->nperms * L.n); std::vector<uint16_t> ap((size_t)e->nperms * L.A);
+        for (int k = 0; k < e->nperms; ++k) {
+            for (int q = 0; q < L.n; ++q) qp[(size_t)k * L.n + q] = (uint8_t)tw.obs_perms[k][q];
+            for (int g = 0; g < L.A; ++g) ap[(size_t)k * L.A + g] = (uint16_t)tw.act_perms[k][g];
+        }
+        ce = cudaMemcpy((void*)d.qperms, qp.data(), qp.size(), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy((void*)d.aperms, ap.data(), ap.size() * 2, cudaMemcpyHostToDevice);
+    }
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->h_best, 64);
+    if (ce != cudaSuccess) { set_error(std::string("engine table upload: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
+    // constructor state: identity, depth 1, success, reward 1.0 (permutation.rs:75-98, clifford.rs:205-236, pauli.rs:354-409)
+    ce = cudaMemcpy(e->staged, ident.data(), (size_t)L.PW * 4, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { set_error(std::string("engine init: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
+    rc = launch_load(e, 0, batch, 1, 1u, 0);
+    if (rc != QG_OK) return fail(rc);
+    ce = cudaStreamSynchronize(0);
+    if (ce != cudaSuccess) { set_error(std::string("engine init: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
+    *out = e;
+    return QG_OK;
+}
+
+void qg_destroy(qg_engine* e) {
+    if (!e) return;
+    if (e->h_staged) cudaFreeHost(e->h_staged);
+    if (e->h_best) cudaFreeHost(e->h_best);
+    if (e->owns_ws && e->ws) cudaFree(e->ws);
+    delete e;
+}
+
+int64_t qg_batch(const qg_engine* e) { return e ? e->B : 0; }
+int32_t qg_num_actions(const qg_engine* e) { return e ? e->L.A : 0; }
+int32_t qg_obs_size(const qg_engine* e) { return e ? e->L.obs_size : 0; }
+int qg_obs_shape(const qg_engine* e, int32_t out_shape[2]) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    out_shape[0] = e->L.obs_rows; out_shape[1] = e->L.obs_cols; return QG_OK;
+}
+int qg_set_difficulty(qg_engine* e, int32_t difficulty) {
+    if (!e || difficulty < 0) { set_error("bad difficulty"); return QG_ERR_INVALID; }
+    e->cfg.difficulty = difficulty; e->dc.difficulty = difficulty; return QG_OK;
+}
+int32_t qg_get_difficulty(const qg_engine* e) { return e ? e->cfg.difficulty : 0; }
+
+int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride, int64_t first, int64_t count, int32_t broadcast, qg_stream stream) {
+    if (!e || !states_host) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (first < 0 || count < 0 || first + count > e->B) { set_error("set_state: env range outside the batch"); return QG_ERR_INVALID; }
+    if (count == 0) return QG_OK;
+    CUDA_OK(cudaSetDevice(e->device));
+    const int64_t payloads = broadcast ? 1 : count;
+    int rc = ensure_host_staging(e, payloads * e->L.PW);
+    if (rc != QG_OK) return rc;
+    for (int64_t i = 0; i < payloads; ++i) {
+        int64_t used = 0;
+        rc = pack_state(&e->cfg, e->L, states_host + i * stride, stride, e->h_staged + i * e->L.PW, &used);
+        if (rc != QG_OK) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(e->staged, e->h_staged, (size_t)payloads * e->L.PW * 4, cudaMemcpyHostToDevice, st));
+    rc = launch_load(e, first, count, broadcast ? 1 : 0, (uint32_t)e->cfg.max_depth, st);
+    if (rc != QG_OK) return rc;
+    CUDA_OK(cudaStreamSynchronize(st));   // the pinned staging buffer is reused by the next call
+    return QG_OK;
+}
+
+int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    if (e->L.kind == QG_ENV_PAULI_NETWORK) { set_error("PauliNetwork reset runs on the host side of the binding (generator pauli.rs:115-271); use qg_set_state with generated targets"); return QG_ERR_UNSUPPORTED; }
+    CUDA_OK(cudaSetDevice(e->device));
+    e->dc.seed = seed; e->dc.first_id = first_env_id;
+    if (e->B == 0) return QG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((e->B + 63) / 64);
+    const size_t sm = (size_t)e->L.SW * 64 * 4;
+    switch (e->L.kind) {
+        case QG_ENV_PERMUTATION: k_reset<QG_ENV_PERMUTATION, 64><<<grid, 64, sm, st>>>(e->dc); break;
+        case QG_ENV_LINEAR_FUNCTION: k_reset<QG_ENV_LINEAR_FUNCTION, 64><<<grid, 64, sm, st>>>(e->dc); break;
+        default: k_reset<QG_ENV_CLIFFORD, 64><<<grid, 64, sm, st>>>(e->dc); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+int qg_snapshot(qg_engine* e, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    CUDA_OK(cudaMemcpyAsync(e->snap, e->dc.rec, (size_t)e->L.W * e->Bpad * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    e->has_snap = true;
+    return QG_OK;
+}
+int qg_restore(qg_engine* e, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    if (!e->has_snap) { set_error("qg_restore without a snapshot"); return QG_ERR_INVALID; }
+    CUDA_OK(cudaMemcpyAsync(e->dc.rec, e->snap, (size_t)e->L.W * e->Bpad * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return QG_OK;
+}
+
+int qg_step(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev, float* obs_dev, uint8_t* mask_dev,
+            float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !actions_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs = obs_dev; a.mask = mask_dev;
+    a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    return launch_step<MODE_STEP>(e, a, (cudaStream_t)stream);
+}
+
+int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
+                 float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream) {
+    if (!e || !actions_host) { set_error("null argument"); return QG_ERR_INVALID; }
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->B;
+    CUDA_OK(cudaMemcpyAsync(e->io_actions, actions_host, B * 4, cudaMemcpyHostToDevice, st));
+    if (coins_host) CUDA_OK(cudaMemcpyAsync(e->io_coins, coins_host, B, cudaMemcpyHostToDevice, st));
+    StepArgs a{}; a.actions = e->io_actions; a.coins = coins_host ? e->io_coins : nullptr; a.obs = obs_dev; a.mask = mask_dev;
+    a.reward = e->io_reward; a.done = e->io_done; a.success = e->io_success;
+    const int rc = launch_step<MODE_STEP>(e, a, st);
+    if (rc != QG_OK) return rc;
+    if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host, e->io_reward, B * 4, cudaMemcpyDeviceToHost, st));
+    if (done_host) CUDA_OK(cudaMemcpyAsync(done_host, e->io_done, B, cudaMemcpyDeviceToHost, st));
+    if (success_host) CUDA_OK(cudaMemcpyAsync(success_host, e->io_success, B, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return QG_OK;
+}
+
+int qg_observe(qg_engine* e, const uint32_t* perm_raw_dev, float* obs_dev, qg_stream stream) {
+    if (!e || !obs_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    StepArgs a{}; a.perm_raw = perm_raw_dev; a.obs = obs_dev;
+    return launch_step<MODE_OBSERVE>(e, a, (cudaStream_t)stream);
+}
+int qg_masks(qg_engine* e, uint8_t* mask_dev, qg_stream stream) {
+    if (!e || !mask_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    StepArgs a{}; a.mask = mask_dev;
+    return launch_step<MODE_OBSERVE>(e, a, (cudaStream_t)stream);
+}
+int qg_read_status(qg_engine* e, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, int32_t* depth_dev, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    if (e->B == 0) return QG_OK;
+    k_read_status<<<(unsigned)((e->B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->dc, reward_dev, done_dev, success_dev, depth_dev);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+int qg_read_metrics(qg_engine* e, uint32_t* counts_dev, qg_stream stream) {
+    if (!e || !counts_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (e->B == 0) return QG_OK;
+    k_read_metrics<<<(unsigned)((e->B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->dc, counts_dev);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+int qg_read_errors(qg_engine* e, uint32_t* flags_dev, qg_stream stream) {
+    if (!e || !flags_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (e->B == 0) return QG_OK;
+    k_read_errors<<<(unsigned)((e->B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->dc, flags_dev);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+int qg_get_state_host(qg_engine* e, int64_t env, uint8_t* out_host, int64_t cap, int64_t* len, qg_stream stream) {
+    if (!e || !out_host || !len) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (env < 0 || env >= e->B) { set_error("env index outside the batch"); return QG_ERR_INVALID; }
+    CUDA_OK(cudaSetDevice(e->device));
+    std::vector<uint32_t> col((size_t)e->L.W);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpy2DAsync(col.data(), 4, e->dc.rec + env, (size_t)e->Bpad * 4, 4, (size_t)e->L.W, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return unpack_state(e->L, col.data(), out_host, cap, len);
+}
+
+int qg_solution_host(qg_engine* e, int64_t env, uint32_t* out_host, int32_t cap, int32_t* len, qg_stream stream) {
+    if (!e || !len) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (env < 0 || env >= e->B) { set_error("env index outside the batch"); return QG_ERR_INVALID; }
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t flags = 0;
+    CUDA_OK(cudaMemcpyAsync(&flags, e->dc.rec + (size_t)HD_FLAGS * e->Bpad + env, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const int n = (int)(flags >> FL_LEN_SHIFT);
+    *len = n;
+    if (n == 0 || !out_host) return QG_OK;
+    if (cap < n) { set_error("solution buffer too small"); return QG_ERR_INVALID; }
+    std::vector<uint32_t> col((size_t)n);
+    CUDA_OK(cudaMemcpy2DAsync(col.data(), 4, e->dc.sol + env, (size_t)e->Bpad * 4, 4, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (e->L.kind == QG_ENV_PAULI_NETWORK) { std::copy(col.begin(), col.end(), out_host); return QG_OK; }
+    // solution ++ reverse(solution_inv) (clifford.rs:376-381); bit 31 marks entries logged while inverted
+    int k = 0;
+    for (int i = 0; i < n; ++i) if (!(col[i] & 0x80000000u)) out_host[k++] = col[i];
+    for (int i = n - 1; i >= 0; --i) if (col[i] & 0x80000000u) out_host[k++] = col[i] & 0x7FFFFFFFu;
+    return QG_OK;
+}
+
+int qg_search_begin(qg_engine* e, uint64_t seed, int64_t first_rollout_id, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    if (first_rollout_id < 0 || first_rollout_id + e->B > 0x3FFFFFFFll) { set_error("rollout ids must stay below 2^30"); return QG_ERR_INVALID; }
+    e->dc.seed = seed; e->dc.first_id = first_rollout_id;
+    if (e->B == 0) return QG_OK;
+    k_fill_f32<<<(unsigned)((e->B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->dc.ret, e->B, 0.0f);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+int qg_search_step(qg_engine* e, const float* weights_dev, int32_t deterministic, float* obs_dev, uint8_t* mask_dev, int32_t* chosen_dev,
+                   int32_t* num_active_dev, qg_stream stream) {
+    if (!e || !weights_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_active_dev) CUDA_OK(cudaMemsetAsync(num_active_dev, 0, 4, st));
+    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs = obs_dev; a.mask = mask_dev; a.chosen = chosen_dev; a.num_active = num_active_dev;
+    return launch_step<MODE_SEARCH>(e, a, st);
+}
+
+int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream) {
+    if (!e || !best_key_host || !best_env_host) { set_error("null argument"); return QG_ERR_INVALID; }
+    CUDA_OK(cudaSetDevice(e->device));
+    *best_key_host = 0; *best_env_host = -1;
+    if (e->B == 0) return QG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemsetAsync(e->best, 0, 8, st));
+    k_best<<<(unsigned)((e->B + 255) / 256), 256, 0, st>>>(e->dc, e->best);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(e->h_best, e->best, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const unsigned long long key = *e->h_best;
+    *best_key_host = (int64_t)key;
+    *best_env_host = (0x3FFFFFFFll - (int64_t)(key & 0x3FFFFFFFull)) - e->dc.first_id;
+    return QG_OK;
+}
+
+int qg_read_returns(qg_engine* e, float* returns_dev, qg_stream stream) {
+    if (!e || !returns_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (e->B == 0) return QG_OK;
+    k_copy_f32<<<(unsigned)((e->B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->dc.ret, returns_dev, e->B);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+}  // extern "C"

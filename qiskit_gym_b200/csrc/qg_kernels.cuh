@@ -1,0 +1,598 @@
+// qg_kernels.cuh — the fused environment kernels (sm_100a).
+//
+// One launch of k_step does, for every environment of the batch, what the reference does with five
+// trait calls per environment (step, reward, is_final, observe, masks — e.g. clifford.rs:321-368):
+//   phase 1 (one thread per environment, state staged in shared memory):
+//       gate lookup -> MetricsTracker update (metrics.rs:64-123) -> weighted penalty (metrics.rs:135-146)
+//       -> gate applied as row XOR / row swap on the packed GF(2) state -> solution log -> depth tick
+//       -> optional inverse (coin) -> solved() -> reward -> write-back;
+//   phase 2 (whole CTA): the CTA's contiguous slab of the dense float observation tensor and of the
+//       uint8 action-mask tensor is produced from the packed bits with 16-byte coalesced stores.
+#pragma once
+#include "qg_common.cuh"
+
+namespace qg {
+
+struct StepArgs {
+    const int32_t* actions;      // [B]            (MODE_STEP)
+    const uint8_t* coins;        // [B] or null
+    const uint32_t* perm_raw;    // [B] or null
+    const float* weights;        // [B][A]         (MODE_SEARCH)
+    int32_t deterministic;
+    float* obs;                  // [B][obs_size] or null
+    uint8_t* mask;               // [B][A] or null
+    float* reward; uint8_t* done; uint8_t* success;   // [B] or null
+    int32_t* chosen;             // [B] or null    (MODE_SEARCH)
+    int32_t* num_active;         // [1] or null    (MODE_SEARCH)
+    int32_t sm_scr, sm_obs, sm_aux;   // shared-memory region offsets in words
+    uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)
+};
+
+enum { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_SEARCH = 2 };
+
+__device__ __forceinline__ uint32_t fastdiv40(uint32_t x, uint64_t magic) { return (uint32_t)(((uint64_t)x * magic) >> 40); }
+
+struct Counts { uint32_t nc, ng, nl, nlc; };
+
+// metrics.rs:84-96
+template <class Wd>
+__device__ __forceinline__ void met_single(const Wd& lg, int n, int t, Counts& c, uint32_t& err) {
+    if ((unsigned)t >= (unsigned)n) return;
+    c.ng += 1;
+    int L = get16(lg, t) + 1;
+    if (L > 32767) { L = 32767; err |= QG_FLAG_LAYER_OVERFLOW; }
+    set16(lg, t, L);
+    c.nl = max(c.nl, (uint32_t)(L + 1));   // layers is always {0..max} so len() == max+1
+}
+// metrics.rs:98-123
+template <class Wd>
+__device__ __forceinline__ void met_cx(const Wd& lg, const Wd& lc, int n, int ctl, int tgt, Counts& c, uint32_t& err) {
+    if (ctl == tgt || (unsigned)ctl >= (unsigned)n || (unsigned)tgt >= (unsigned)n) return;
+    c.nc += 1; c.ng += 1;
+    int L = max(get16(lg, ctl), get16(lg, tgt)) + 1;
+    if (L > 32767) { L = 32767; err |= QG_FLAG_LAYER_OVERFLOW; }
+    set16(lg, ctl, L); set16(lg, tgt, L);
+    c.nl = max(c.nl, (uint32_t)(L + 1));
+    int Lc = max(get16(lc, ctl), get16(lc, tgt)) + 1;
+    if (Lc > 32767) { Lc = 32767; err |= QG_FLAG_LAYER_OVERFLOW; }
+    set16(lc, ctl, Lc); set16(lc, tgt, Lc);
+    c.nlc = max(c.nlc, (uint32_t)(Lc + 1));
+}
+// metrics.rs:64-82
+template <class Wd>
+__device__ __forceinline__ void met_gate(const Wd& lg, const Wd& lc, int n, int kind, int q0, int q1, Counts& c, uint32_t& err) {
+    if (kind == QG_CX) met_cx(lg, lc, n, q0, q1, c, err);
+    else if (kind == QG_SWAP) { met_cx(lg, lc, n, q0, q1, c, err); met_cx(lg, lc, n, q1, q0, c, err); met_cx(lg, lc, n, q0, q1, c, err); }
+    else if (kind == QG_CZ) { met_single(lg, n, q1, c, err); met_cx(lg, lc, n, q0, q1, c, err); met_single(lg, n, q1, c, err); }
+    else met_single(lg, n, q0, c, err);
+}
+// metrics.rs:135-146: ((w0*dc + w1*dlc) + w2*dl) + w3*dg, every product and sum rounded on its own.
+__device__ __forceinline__ float weighted_delta(const DevCfg& c, const Counts& now, const Counts& prev) {
+    const float dc = (float)(now.nc - prev.nc), dlc = (float)(now.nlc - prev.nlc);
+    const float dl = (float)(now.nl - prev.nl), dg = (float)(now.ng - prev.ng);
+    float s = __fadd_rn(__fmul_rn(c.w0, dc), __fmul_rn(c.w1, dlc));
+    s = __fadd_rn(s, __fmul_rn(c.w2, dl));
+    s = __fadd_rn(s, __fmul_rn(c.w3, dg));
+    return s;
+}
+
+// ---- state transitions ---------------------------------------------------------------------------
+// permutation.rs:205-208 | linear_function.rs:237-243 + 62-83 | clifford.rs:249-260 + 89-133
+template <int KIND, class Wd>
+__device__ __forceinline__ void apply_gate_state(const DevCfg& c, const Wd& S, int kind, int q0, int q1) {
+    if (KIND == QG_ENV_PERMUTATION) {
+        if (kind == QG_SWAP) { const uint32_t a = get8(S, q0), b = get8(S, q1); set8(S, q0, b); set8(S, q1, a); }
+    } else if (KIND == QG_ENV_LINEAR_FUNCTION) {
+        if (q0 == q1) return;
+        if (kind == QG_CX) row_xor(S, c.D, q1, q0);
+        else if (kind == QG_SWAP) row_swap(S, c.D, q0, q1);
+    } else if (KIND == QG_ENV_CLIFFORD) {
+        const int n = c.n, D = c.D;
+        switch (kind) {
+            case QG_H: row_swap(S, D, q0, n + q0); break;
+            case QG_S: case QG_SDG: row_xor(S, D, n + q0, q0); break;
+            case QG_SX: case QG_SXDG: row_xor(S, D, q0, n + q0); break;
+            case QG_CX: if (q0 != q1) { row_xor(S, D, q1, q0); row_xor(S, D, n + q0, n + q1); } break;
+            case QG_CZ: if (q0 != q1) { row_xor(S, D, n + q0, q1); row_xor(S, D, n + q1, q0); } break;
+            case QG_SWAP: if (q0 != q1) { row_swap(S, D, q0, q1); row_swap(S, D, n + q0, n + q1); } break;
+        }
+    }
+}
+
+// solved(): permutation.rs:122-128 | linear_function.rs:91-100 | clifford.rs:136-145
+template <int KIND, class Wd>
+__device__ __forceinline__ bool solved_state(const DevCfg& c, const Wd& S) {
+    if (KIND == QG_ENV_PERMUTATION) {
+        for (int i = 0; i < c.n; ++i) if (get8(S, i) != (uint32_t)i) return false;
+        return true;
+    } else {
+        uint32_t diff = 0;
+        for (int w = 0; w < c.SW; ++w) diff |= S[w] ^ __ldg(c.ident + w);
+        return diff == 0;
+    }
+}
+
+// Gauss-Jordan inverse over GF(2) (linear_function.rs:124-146, clifford.rs:147-170); M, I: scratch bit streams.
+template <class Wd>
+__device__ bool invert_matrix(const DevCfg& c, const Wd& S, const Wd& M, const Wd& I) {
+    const int D = c.D;
+    for (int w = 0; w < c.SW; ++w) { M[w] = S[w]; I[w] = __ldg(c.ident + w); }
+    for (int col = 0; col < D; ++col) {
+        if (!get_bit(M, col * D + col)) {
+            int pivot = -1;
+            for (int r = col + 1; r < D; ++r) if (get_bit(M, r * D + col)) { pivot = r; break; }
+            if (pivot < 0) return false;
+            row_swap(M, D, col, pivot); row_swap(I, D, col, pivot);
+        }
+        for (int r = 0; r < D; ++r)
+            if (r != col && get_bit(M, r * D + col)) { row_xor(M, D, r, col); row_xor(I, D, r, col); }
+    }
+    for (int w = 0; w < c.SW; ++w) S[w] = I[w];
+    return true;
+}
+// permutation.rs:101-107
+template <class Wd>
+__device__ void invert_perm(const DevCfg& c, const Wd& S, const Wd& T) {
+    for (int w = 0; w < c.SW; ++w) T[w] = 0;
+    for (int i = 0; i < c.n; ++i) set8(T, (int)get8(S, i), (uint32_t)i);
+    for (int w = 0; w < c.SW; ++w) S[w] = T[w];
+}
+
+// ---- PauliNetwork ----------------------------------------------------------------------------------
+struct PauliRegs { uint32_t plo, phi, alive, ord0, ord1, misc; };
+__device__ __forceinline__ uint32_t ord_get(const PauliRegs& p, int i) { return ((i < 8 ? p.ord0 : p.ord1) >> ((i & 7) * 4)) & 0xFu; }
+__device__ __forceinline__ void ord_set(PauliRegs& p, int i, uint32_t v) {
+    const int s = (i & 7) * 4;
+    if (i < 8) p.ord0 = (p.ord0 & ~(0xFu << s)) | (v << s); else p.ord1 = (p.ord1 & ~(0xFu << s)) | (v << s);
+}
+__device__ __forceinline__ void phase_add(PauliRegs& p, uint32_t m) { const uint32_t carry = p.plo & m; p.plo ^= m; p.phi ^= carry; }
+template <class Wd>
+__device__ __forceinline__ uint32_t rot_bits(const DevCfg& c, const Wd& S, int row) { return get_bits(S, row * c.CW + 2 * c.n, c.Rtot); }
+
+// pauli_network.rs:189-194 (+ pauli.rs:83-90)
+template <class Wd>
+__device__ __forceinline__ void pn_h(const DevCfg& c, const Wd& S, PauliRegs& p, int i) {
+    p.phi ^= rot_bits(c, S, i) & rot_bits(c, S, c.n + i);
+    row_swap(S, c.CW, i, c.n + i);
+}
+// pauli_network.rs:209-215 (+ pauli.rs:92-97); times = 1 (S) or 3 (Sdg = S^3, pauli_network.rs:229-233)
+template <class Wd>
+__device__ __forceinline__ void pn_s(const DevCfg& c, const Wd& S, PauliRegs& p, int i, bool thrice) {
+    const uint32_t x = rot_bits(c, S, i);
+    phase_add(p, x); if (thrice) p.phi ^= x;          // +x or +3x (mod 4)
+    row_xor(S, c.CW, c.n + i, i);                      // xor applied once or three times is the same matrix
+}
+// pauli_network.rs:217-223 (+ pauli.rs:105-110: H,S,H adds 2xz + z + 2z(1-x) = 3z); SXdg = SX^3 adds 9z = z
+template <class Wd>
+__device__ __forceinline__ void pn_sx(const DevCfg& c, const Wd& S, PauliRegs& p, int i, bool thrice) {
+    const uint32_t z = rot_bits(c, S, c.n + i);
+    phase_add(p, z); if (!thrice) p.phi ^= z;
+    row_xor(S, c.CW, i, c.n + i);
+}
+// pauli_network.rs:139-165 with the petgraph 0.6.5 retain_nodes/swap-remove node order.
+// Harvested (axis, qubit, idx) triples are appended to hv[] as axis<<21 | qubit<<11 | idx<<1.
+template <class Wd>
+__device__ void pn_clean(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p, const Wd& hv, int& nh, uint32_t& err) {
+    const int n = c.n;
+    for (;;) {
+        int m = (int)(p.misc >> 24);
+        if (m == 0) return;
+        uint32_t ones = 0, ge2 = 0;                 // per-rotation weight of (x|z): bit-sliced saturating count
+        for (int q = 0; q < n; ++q) { const uint32_t mk = rot_bits(c, S, q) | rot_bits(c, S, n + q); ge2 |= ones & mk; ones |= mk; }
+        const uint32_t alive0 = p.alive;
+        uint32_t marked = 0;                        // node positions to remove
+        for (int pos = 0; pos < m; ++pos) {
+            const uint32_t r = ord_get(p, pos);
+            const uint32_t anti = (X[PX_ANTI + (r >> 1)] >> ((r & 1) * 16)) & 0xFFFFu;   // earlier rotations that anticommute
+            if ((anti & alive0) != 0) continue;     // has an outgoing edge: not in the front layer (pauli_dag.rs:47-57)
+            if ((ge2 >> r) & 1u) continue;          // weight >= 2: not trivial (pauli_network.rs:83-97)
+            marked |= 1u << pos;
+            p.alive &= ~(1u << r);                  // set_column(zeros) (pauli_network.rs:153-156)
+            if (!((ones >> r) & 1u)) { err |= QG_FLAG_BAD_ROTATION; continue; }   // which_qubit().unwrap() panic in the reference
+            int q = 0; uint32_t x = 0, z = 0;
+            for (; q < n; ++q) { x = (rot_bits(c, S, q) >> r) & 1u; z = (rot_bits(c, S, n + q) >> r) & 1u; if (x | z) break; }
+            const uint32_t axis = x ? (z ? 1u : 0u) : 2u;   // which_axis (121-137)
+            hv[nh++] = (axis << 21) | ((uint32_t)q << 11) | (r << 1);
+        }
+        if (!marked) return;
+        for (int pos = m - 1; pos >= 0; --pos)      // retain_nodes: high -> low, swap-remove
+            if ((marked >> pos) & 1u) { ord_set(p, pos, ord_get(p, m - 1)); --m; }
+        p.misc = (p.misc & 0x00FFFFFFu) | ((uint32_t)m << 24);
+    }
+}
+// pauli_network.rs:196-207
+template <class Wd>
+__device__ __forceinline__ void pn_cnot(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p, int i, int j, const Wd& hv, int& nh, uint32_t& err) {
+    row_xor(S, c.CW, i, j);
+    row_xor(S, c.CW, c.n + j, c.n + i);
+    pn_clean(c, S, X, p, hv, nh, err);
+}
+// pauli_network.rs:225-260
+template <class Wd>
+__device__ void pn_act(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p, int kind, int q0, int q1, const Wd& hv, int& nh, uint32_t& err) {
+    switch (kind) {
+        case QG_H: pn_h(c, S, p, q0); break;
+        case QG_S: pn_s(c, S, p, q0, false); break;
+        case QG_SDG: pn_s(c, S, p, q0, true); break;
+        case QG_SX: pn_sx(c, S, p, q0, false); break;
+        case QG_SXDG: pn_sx(c, S, p, q0, true); break;
+        case QG_CX: pn_cnot(c, S, X, p, q0, q1, hv, nh, err); break;
+        case QG_CZ: pn_h(c, S, p, q1); pn_cnot(c, S, X, p, q0, q1, hv, nh, err); pn_h(c, S, p, q1); break;
+        case QG_SWAP: pn_cnot(c, S, X, p, q0, q1, hv, nh, err); pn_cnot(c, S, X, p, q1, q0, hv, nh, err); pn_cnot(c, S, X, p, q0, q1, hv, nh, err); break;
+    }
+}
+// pauli_network.rs:167-173
+template <class Wd>
+__device__ __forceinline__ bool pn_solved(const DevCfg& c, const Wd& S, const PauliRegs& p) {
+    if ((p.misc >> 24) != 0) return false;
+    const int D = 2 * c.n;
+    for (int r = 0; r < D; ++r)
+        for (int c0 = 0; c0 < D; c0 += 32) {
+            const int len = min(32, D - c0);
+            const uint32_t want = (r >= c0 && r < c0 + len) ? (1u << (r - c0)) : 0u;
+            if (get_bits(S, r * c.CW + c0, len) != want) return false;
+        }
+    return true;
+}
+// observe(): pad_and_collect (pauli.rs:411-437) + apply_perm_to_obs (445-485) -> obs bit stream O
+template <class Wd>
+__device__ void pn_build_obs(const DevCfg& c, const Wd& S, const PauliRegs& p, const Wd& O, int perm_idx) {
+    const int n = c.n, D = 2 * n, OC = c.obs_cols;
+    for (int w = 0; w < c.OW; ++w) O[w] = 0;
+    const int m = min((int)(p.misc >> 24), c.max_rot);
+    const uint8_t* perm = (c.nperms > 0) ? (c.qperms + (size_t)perm_idx * n) : nullptr;
+    for (int r = 0; r < D; ++r) {
+        int src = r;
+        if (perm) src = (r < n) ? (int)perm[r] : n + (int)perm[r - n];
+        const uint32_t rb = rot_bits(c, S, src);
+        uint32_t rot = 0;
+        for (int i = 0; i < m; ++i) rot |= ((rb >> ord_get(p, i)) & 1u) << i;
+        if (!perm) {
+            for (int c0 = 0; c0 < D; c0 += 32) { const int len = min(32, D - c0); xor_bits(O, r * OC + c0, len, get_bits(S, src * c.CW + c0, len)); }
+        } else {
+            for (int col = 0; col < D; ++col) {
+                const int sc = (col < n) ? (int)perm[col] : n + (int)perm[col - n];
+                if (get_bit(S, src * c.CW + sc)) xor_bits(O, r * OC + col, 1, 1u);
+            }
+        }
+        if (m > 0) xor_bits(O, r * OC + D, m, rot);
+    }
+}
+
+// ---- the fused kernel ----------------------------------------------------------------------------------
+template <int KIND, int EPC, int MODE>
+__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x;
+    const int64_t e0 = (int64_t)blockIdx.x * EPC;
+    const int cnt = (int)min((int64_t)EPC, c.B - e0);
+    uint32_t* aux = smem + a.sm_aux;               // per env: bit0 = mask value (!success), bit1 = outputs enabled
+
+    if (tid < cnt) {
+        typedef SmWords<EPC> Wd;
+        const int64_t env = e0 + tid;
+        const Wd R{smem + tid};
+        const Wd LG = R.at(c.off_lastg), LC = R.at(c.off_lastcx), S = R.at(c.off_state), X = R.at(c.off_extra);
+        const Wd SCR{smem + a.sm_scr + tid}, O{smem + a.sm_obs + tid};
+#pragma unroll 4
+        for (int w = 0; w < c.W; ++w) R[w] = c.rec[(size_t)w * c.Bpad + env];
+
+        uint32_t depth = R[HD_DEPTH], flags = R[HD_FLAGS], tick = R[HD_TICK];
+        bool success = (flags & FL_SUCCESS) != 0;
+        bool enabled = true;
+        PauliRegs pr{};
+        if (KIND == QG_ENV_PAULI_NETWORK) { pr.plo = X[PX_PLO]; pr.phi = X[PX_PHI]; pr.alive = X[PX_ALIVE]; pr.ord0 = X[PX_ORD0]; pr.ord1 = X[PX_ORD1]; pr.misc = X[PX_MISC]; }
+
+        int action = -1;
+        if (MODE == MODE_STEP) action = a.actions[env];
+        if (MODE == MODE_SEARCH) {
+            // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
+            enabled = !(depth == 0 || success);
+            if (enabled) {
+                const float* wt = a.weights + (size_t)env * c.A;
+                if (a.deterministic) {
+                    float best = wt[0]; action = 0;
+                    for (int k = 1; k < c.A; ++k) { const float v = wt[k]; if (v > best) { best = v; action = k; } }
+                } else {
+                    float total = 0.0f;
+                    for (int k = 0; k < c.A; ++k) total = __fadd_rn(total, wt[k]);
+                    const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_SAMPLE);
+                    if (!(total > 0.0f)) action = (int)__umulhi(raw, (uint32_t)c.A);
+                    else {
+                        const float target = __fmul_rn((float)(raw >> 8) * (1.0f / 16777216.0f), total);
+                        float cum = 0.0f; action = c.A - 1;
+                        for (int k = 0; k < c.A; ++k) { cum = __fadd_rn(cum, wt[k]); if (cum > target) { action = k; break; } }
+                    }
+                }
+            }
+            if (a.chosen) a.chosen[env] = enabled ? action : -1;
+        }
+
+        if (MODE != MODE_OBSERVE && enabled) {
+            uint32_t err = 0;
+            float penalty = 0.0f;
+            int nh = 0;                                     // rotations harvested by this step (PauliNetwork)
+            int act = action;
+            if (act < 0) { err |= QG_FLAG_BAD_ACTION; act = 0x7FFFFFFF; }
+            if (KIND == QG_ENV_PAULI_NETWORK && c.nperms > 0 && act < c.A)
+                act = (int)c.aperms[(size_t)(pr.misc & 0xFFFFu) * c.A + act];       // pauli.rs:594-599
+            const bool valid = act < c.A;
+            uint32_t sol_len = flags >> FL_LEN_SHIFT;
+            auto push = [&](uint32_t v) {
+                if ((int)sol_len < c.sol_cap) { c.sol[(size_t)sol_len * c.Bpad + env] = v; ++sol_len; }
+                else err |= QG_FLAG_SOLUTION_OVERFLOW;
+            };
+            if (valid) {
+                const uint32_t g = __ldg(c.gates + act);
+                const int kind = (int)(g & 0xFFu), q0 = (int)((g >> 8) & 0xFFu), q1 = (int)((g >> 16) & 0xFFu);
+                Counts prev{R[HD_NCNOTS], R[HD_NGATES], R[HD_LAYERS] & 0xFFFFu, R[HD_LAYERS] >> 16};
+                Counts now = prev;
+                met_gate(LG, LC, c.n, kind, q0, q1, now, err);
+                penalty = weighted_delta(c, now, prev);
+                R[HD_NCNOTS] = now.nc; R[HD_NGATES] = now.ng; R[HD_LAYERS] = (now.nl & 0xFFFFu) | (now.nlc << 16);
+                if (KIND == QG_ENV_PAULI_NETWORK) pn_act(c, S, X, pr, kind, q0, q1, SCR, nh, err);
+                else apply_gate_state<KIND>(c, S, kind, q0, q1);
+            }
+            // solution log: Permutation only for valid actions (permutation.rs:210-216), LF/Clifford always
+            // (linear_function.rs:315-321, clifford.rs:334-340), PauliNetwork gate + harvested rotations (pauli.rs:612-627)
+            if (c.track) {
+                if (KIND == QG_ENV_PAULI_NETWORK) {
+                    if (valid) {
+                        push((uint32_t)act);
+                        if (nh > 0) {
+                            uint32_t ylo = 0, yhi = 0;      // #Y per rotation mod 4 (pauli.rs:125-133), after the whole act()
+                            for (int q = 0; q < c.n; ++q) { const uint32_t y = rot_bits(c, S, q) & rot_bits(c, S, c.n + q); const uint32_t cy = ylo & y; ylo ^= y; yhi ^= cy; }
+                            for (int k = 0; k < nh; ++k) {
+                                const uint32_t h = SCR[k], r = (h >> 1) & 0xFu;
+                                const uint32_t bp = ((pr.plo >> r) & 1u) | (((pr.phi >> r) & 1u) << 1);
+                                const uint32_t ys = ((ylo >> r) & 1u) | (((yhi >> r) & 1u) << 1);
+                                const uint32_t ph = (bp - ys) & 3u;
+                                push(0x80000000u | h | (ph == 2u ? 0u : 1u));
+                            }
+                        }
+                    }
+                } else if (KIND != QG_ENV_PERMUTATION || valid) {
+                    push(((uint32_t)action & 0x7FFFFFFFu) | ((flags & FL_INVERTED) ? 0x80000000u : 0u));
+                }
+            }
+            depth = depth > 0 ? depth - 1 : 0;              // saturating_sub
+            if (KIND != QG_ENV_PAULI_NETWORK && c.add_inverts) {
+                bool coin;
+                if (a.coins) coin = a.coins[env] != 0;
+                else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
+                if (coin) {
+                    if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; }
+                    else if (invert_matrix(c, S, SCR, SCR.at(c.SW))) flags ^= FL_INVERTED;
+                    else err |= QG_FLAG_SINGULAR;
+                }
+            }
+            success = (KIND == QG_ENV_PAULI_NETWORK) ? pn_solved(c, S, pr) : solved_state<KIND>(c, S);
+            float reward = __fsub_rn(success ? 1.0f : 0.0f, penalty);
+            if (KIND == QG_ENV_PAULI_NETWORK) reward = __fadd_rn(reward, __fmul_rn(c.plr, (float)nh));   // pauli.rs:634
+            flags = (flags & (FL_INVERTED | (0xFFu << FL_ERR_SHIFT))) | (success ? FL_SUCCESS : 0u) | (err << FL_ERR_SHIFT) | (sol_len << FL_LEN_SHIFT);
+            tick += 1;
+            R[HD_DEPTH] = depth; R[HD_FLAGS] = flags; R[HD_REWARD] = __float_as_uint(reward); R[HD_TICK] = tick;
+            if (MODE == MODE_SEARCH) c.ret[env] = __fadd_rn(c.ret[env], reward);
+            if (a.reward) a.reward[env] = reward;
+        }
+        if (MODE == MODE_OBSERVE || !enabled) { if (a.reward && MODE != MODE_SEARCH) a.reward[env] = __uint_as_float(R[HD_REWARD]); }
+        if (enabled || MODE != MODE_SEARCH) {
+            if (a.done) a.done[env] = (depth == 0 || success) ? 1 : 0;
+            if (a.success) a.success[env] = success ? 1 : 0;
+        }
+
+        // observe(): build the observation bit stream (PauliNetwork picks its permutation here, pauli.rs:653-665)
+        if (KIND == QG_ENV_PAULI_NETWORK && enabled) {
+            int perm_idx = 0;
+            if (c.nperms > 0 && a.obs) {
+                const uint32_t raw = a.perm_raw ? a.perm_raw[env] : philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_PERM);
+                perm_idx = (int)__umulhi(raw, (uint32_t)c.nperms);
+                pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
+            }
+            if (a.obs) pn_build_obs(c, S, pr, O, perm_idx);
+            X[PX_PLO] = pr.plo; X[PX_PHI] = pr.phi; X[PX_ALIVE] = pr.alive; X[PX_ORD0] = pr.ord0; X[PX_ORD1] = pr.ord1; X[PX_MISC] = pr.misc;
+        }
+        if (enabled) {
+            if (MODE != MODE_OBSERVE) {
+#pragma unroll 4
+                for (int w = 0; w < c.W; ++w) c.rec[(size_t)w * c.Bpad + env] = R[w];
+            } else if (KIND == QG_ENV_PAULI_NETWORK) {
+                c.rec[(size_t)(c.off_extra + PX_MISC) * c.Bpad + env] = X[PX_MISC];
+            }
+        }
+        aux[tid] = (success ? 0u : 1u) | (enabled ? 2u : 0u);
+    }
+    if (MODE == MODE_SEARCH && a.num_active) {
+        const bool en = (tid < cnt) && (aux[tid] & 2u);      // own write, same thread
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, en);
+        if ((tid & 31) == 0 && b) atomicAdd(a.num_active, __popc(b));
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: expand bits -> float observation slab, mask slab ------------------------
+    if (a.obs) {
+        float* out = a.obs + (size_t)e0 * c.obs_size;
+        const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size;
+        const uint32_t nvec = total >> 2;
+        const uint32_t* bits = (KIND == QG_ENV_PAULI_NETWORK) ? (smem + a.sm_obs) : (smem + (size_t)c.off_state * EPC);
+        auto elem = [&](int e, uint32_t off) -> float {
+            if (KIND == QG_ENV_PERMUTATION) {
+                const uint32_t i = (uint32_t)(((uint64_t)off * c.magic_n) >> 32), col = off - i * (uint32_t)c.n;
+                const uint32_t v = (bits[(i >> 2) * EPC + e] >> ((i & 3) * 8)) & 0xFFu;      // observe(): index i*n + state[i] (permutation.rs:241-243)
+                return v == col ? 1.0f : 0.0f;
+            }
+            return ((bits[(off >> 5) * EPC + e] >> (off & 31)) & 1u) ? 1.0f : 0.0f;
+        };
+        for (uint32_t j = tid; j < nvec; j += kThreads) {
+            const uint32_t f0 = j << 2;
+            int e = (int)fastdiv40(f0, a.magic_obs);
+            uint32_t off = f0 - (uint32_t)e * (uint32_t)c.obs_size;
+            if (off + 4 <= (uint32_t)c.obs_size) {
+                if (MODE == MODE_SEARCH && !(aux[e] & 2u)) continue;
+                float4 v;
+                if (KIND == QG_ENV_PERMUTATION) { v.x = elem(e, off); v.y = elem(e, off + 1); v.z = elem(e, off + 2); v.w = elem(e, off + 3); }
+                else {
+                    const uint32_t w = off >> 5, s = off & 31;
+                    const uint32_t lo = bits[w * EPC + e], hi = (s > 28) ? bits[(w + 1) * EPC + e] : 0u;
+                    const uint32_t nib = __funnelshift_r(lo, hi, s);
+                    v.x = (nib & 1u) ? 1.0f : 0.0f; v.y = (nib & 2u) ? 1.0f : 0.0f; v.z = (nib & 4u) ? 1.0f : 0.0f; v.w = (nib & 8u) ? 1.0f : 0.0f;
+                }
+                __stcs(reinterpret_cast<float4*>(out) + j, v);
+            } else {
+                for (int k = 0; k < 4; ++k) {                 // vector straddles two environments
+                    if (off == (uint32_t)c.obs_size) { off = 0; ++e; }
+                    if (MODE != MODE_SEARCH || (aux[e] & 2u)) out[f0 + k] = elem(e, off);
+                    ++off;
+                }
+            }
+        }
+        for (uint32_t f = (nvec << 2) + tid; f < total; f += kThreads) {
+            const int e = (int)fastdiv40(f, a.magic_obs);
+            if (MODE != MODE_SEARCH || (aux[e] & 2u)) out[f] = elem(e, f - (uint32_t)e * (uint32_t)c.obs_size);
+        }
+    }
+    if (a.mask) {                                             // masks() = [!success; A] (clifford.rs:349-351)
+        uint8_t* out = a.mask + (size_t)e0 * c.A;
+        const uint32_t total = (uint32_t)cnt * (uint32_t)c.A;
+        const uint32_t nvec = total >> 4;
+        for (uint32_t j = tid; j < nvec; j += kThreads) {
+            const uint32_t b0 = j << 4;
+            int e = (int)fastdiv40(b0, a.magic_A);
+            uint32_t r = b0 - (uint32_t)e * (uint32_t)c.A;
+            if (r + 16 <= (uint32_t)c.A) {
+                if (MODE == MODE_SEARCH && !(aux[e] & 2u)) continue;
+                const uint32_t v = (aux[e] & 1u) ? 0x01010101u : 0u;
+                __stcs(reinterpret_cast<uint4*>(out) + j, make_uint4(v, v, v, v));
+            } else {
+                bool all_on = true; uint32_t wv[4] = {0, 0, 0, 0};
+                int e2 = e; uint32_t r2 = r;
+                for (int k = 0; k < 16; ++k) {
+                    if (r2 == (uint32_t)c.A) { r2 = 0; ++e2; }
+                    if (MODE == MODE_SEARCH && !(aux[e2] & 2u)) all_on = false;
+                    wv[k >> 2] |= (aux[e2] & 1u) << ((k & 3) * 8);
+                    ++r2;
+                }
+                if (all_on) __stcs(reinterpret_cast<uint4*>(out) + j, make_uint4(wv[0], wv[1], wv[2], wv[3]));
+                else for (int k = 0; k < 16; ++k) {
+                    if (r == (uint32_t)c.A) { r = 0; ++e; }
+                    if (aux[e] & 2u) out[b0 + k] = (uint8_t)(aux[e] & 1u);
+                    ++r;
+                }
+            }
+        }
+        for (uint32_t b = (nvec << 4) + tid; b < total; b += kThreads) {
+            const int e = (int)fastdiv40(b, a.magic_A);
+            if (MODE != MODE_SEARCH || (aux[e] & 2u)) out[b] = (uint8_t)(aux[e] & 1u);
+        }
+    }
+}
+
+// ---- load (set_state / constructor) --------------------------------------------------------------
+// staged: [count][PW] words per env = state words (+ PauliNetwork extras); broadcast: every env reads payload 0.
+template <int KIND>
+__global__ void k_load(const __grid_constant__ DevCfg c, const uint32_t* __restrict__ staged, int PW, int64_t first, int64_t count, int broadcast, uint32_t depth_init) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t env = first + i;
+    const uint32_t* src = staged + (size_t)(broadcast ? 0 : i) * PW;
+    auto put = [&](int w, uint32_t v) { c.rec[(size_t)w * c.Bpad + env] = v; };
+    bool ok = true;
+    if (KIND == QG_ENV_PERMUTATION) {
+        for (int q = 0; q < c.n; ++q) if (((src[q >> 2] >> ((q & 3) * 8)) & 0xFFu) != (uint32_t)q) ok = false;
+    } else if (KIND == QG_ENV_PAULI_NETWORK) {
+        ok = (src[PW - 1] & 1u) != 0;      // PauliNetwork::solved precomputed by the host packer (last staged word)
+    } else {
+        for (int w = 0; w < c.SW; ++w) if (src[w] != c.ident[w]) ok = false;
+    }
+    for (int w = 0; w < c.SW; ++w) put(c.off_state + w, src[w]);
+    if (KIND == QG_ENV_PAULI_NETWORK) {
+        const int XW = PW - c.SW - 1;
+        for (int w = 0; w < XW; ++w) put(c.off_extra + w, src[c.SW + w]);
+    }
+    for (int w = 0; w < c.MW; ++w) { put(c.off_lastg + w, 0xFFFFFFFFu); put(c.off_lastcx + w, 0xFFFFFFFFu); }
+    put(HD_DEPTH, depth_init);
+    put(HD_FLAGS, ok ? FL_SUCCESS : 0u);
+    put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
+    put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
+    put(HD_TICK, 0);
+}
+
+// ---- reset (Permutation / LinearFunction / Clifford): identity scrambled by `difficulty` Philox-drawn gates
+// (permutation.rs:175-192, linear_function.rs:285-300, clifford.rs:306-319) --------------------------
+template <int KIND, int EPC>
+__global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * EPC + tid;
+    if (env >= c.B) return;
+    typedef SmWords<EPC> Wd;
+    const Wd S{smem + tid};
+    if (KIND == QG_ENV_PERMUTATION) { for (int w = 0; w < c.SW; ++w) S[w] = 0; for (int q = 0; q < c.n; ++q) set8(S, q, (uint32_t)q); }
+    else for (int w = 0; w < c.SW; ++w) S[w] = c.ident[w];
+    for (int k = 0; k < c.difficulty; ++k) {
+        const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), (uint32_t)k, STREAM_RESET);
+        const int act = (int)__umulhi(raw, (uint32_t)c.A);      // Uniform::new(0, num_actions)
+        const uint32_t g = __ldg(c.gates + act);
+        apply_gate_state<KIND>(c, S, (int)(g & 0xFFu), (int)((g >> 8) & 0xFFu), (int)((g >> 16) & 0xFFu));
+    }
+    const bool ok = solved_state<KIND>(c, S);
+    auto put = [&](int w, uint32_t v) { c.rec[(size_t)w * c.Bpad + env] = v; };
+    for (int w = 0; w < c.SW; ++w) put(c.off_state + w, S[w]);
+    for (int w = 0; w < c.MW; ++w) { put(c.off_lastg + w, 0xFFFFFFFFu); put(c.off_lastcx + w, 0xFFFFFFFFu); }
+    const long long d = (long long)c.depth_slope * (long long)c.difficulty;
+    put(HD_DEPTH, (uint32_t)(d < (long long)c.max_depth ? d : (long long)c.max_depth));
+    put(HD_FLAGS, ok ? FL_SUCCESS : 0u);
+    put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
+    put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
+    put(HD_TICK, 0);
+}
+
+// ---- small readers -----------------------------------------------------------------------------------
+__global__ void k_read_status(const __grid_constant__ DevCfg c, float* reward, uint8_t* done, uint8_t* success, int32_t* depth) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= c.B) return;
+    const uint32_t d = c.rec[(size_t)HD_DEPTH * c.Bpad + env], f = c.rec[(size_t)HD_FLAGS * c.Bpad + env];
+    if (reward) reward[env] = __uint_as_float(c.rec[(size_t)HD_REWARD * c.Bpad + env]);
+    if (done) done[env] = (d == 0 || (f & FL_SUCCESS)) ? 1 : 0;
+    if (success) success[env] = (f & FL_SUCCESS) ? 1 : 0;
+    if (depth) depth[env] = (int32_t)d;
+}
+__global__ void k_read_metrics(const __grid_constant__ DevCfg c, uint32_t* out) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= c.B) return;
+    const uint32_t l = c.rec[(size_t)HD_LAYERS * c.Bpad + env];
+    reinterpret_cast<uint4*>(out)[env] = make_uint4(c.rec[(size_t)HD_NCNOTS * c.Bpad + env], l >> 16, l & 0xFFFFu, c.rec[(size_t)HD_NGATES * c.Bpad + env]);
+}
+__global__ void k_read_errors(const __grid_constant__ DevCfg c, uint32_t* out) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= c.B) return;
+    out[env] = (c.rec[(size_t)HD_FLAGS * c.Bpad + env] >> FL_ERR_SHIFT) & 0xFFu;
+}
+__global__ void k_fill_f32(float* p, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_copy_f32(const float* src, float* dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// ---- best-rollout reduction (synth search): arg-max of a packed key ----------------------------------
+// key = success<<62 | orderable_u32(return)<<30 | (2^30-1 - global rollout id)
+__device__ __forceinline__ unsigned long long rollout_key(bool success, float ret, int64_t gid) {
+    uint32_t u = __float_as_uint(ret);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving map f32 -> u32
+    return ((unsigned long long)(success ? 1 : 0) << 62) | ((unsigned long long)u << 30) | (unsigned long long)((0x3FFFFFFFll - gid) & 0x3FFFFFFFll);
+}
+__global__ void k_best(const __grid_constant__ DevCfg c, unsigned long long* best) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = 0;
+    if (env < c.B) {
+        const uint32_t f = c.rec[(size_t)HD_FLAGS * c.Bpad + env];
+        key = rollout_key((f & FL_SUCCESS) != 0, c.ret[env], c.first_id + env);
+    }
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = other > key ? other : key; }
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
+}
+
+}  // namespace qg

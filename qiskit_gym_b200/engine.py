@@ -1,0 +1,215 @@
+"""BatchedEnv — B independent synthesis environments stepped by one fused CUDA launch.
+
+Host-side mirror of the reference's raw-env interface (`impl twisterl::rl::env::Env for
+{Permutation, LinearFunction, Clifford, PauliEnv}`, e.g. rust/src/envs/clifford.rs:285-382) with a
+leading batch dimension.  PyTorch only provides device memory and streams; every computation is a
+call into the C ABI (include/qg_engine.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._lib import check, lib
+
+
+def _dptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedEnv:
+    def __init__(self, env_kind: int, num_qubits: int, gateset: Iterable, batch: int, device: int | None = None,
+                 difficulty: int = 1, depth_slope: int = 2, max_depth: int = 128, **kwargs):
+        L = lib()
+        gateset = list(gateset)
+        gates = _abi.parse_gateset(gateset, L.qg_gate_kind_from_name)
+        self._gateset = [(str(n), tuple(int(q) for q in idx)) for n, idx in gateset]
+        self.cfg = _abi.make_config(env_kind, num_qubits, difficulty, gates, len(self._gateset), depth_slope, max_depth, **kwargs)
+        check(L.qg_config_validate(C.byref(self.cfg)))
+        if not torch.cuda.is_available():
+            raise RuntimeError("qiskit_gym_b200 needs a CUDA device (no CPU fallback)")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.batch = int(batch)
+        nbytes = check(L.qg_workspace_bytes(C.byref(self.cfg), self.batch))
+        self._workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(L.qg_create(C.byref(self.cfg), self.device_index, self.batch, _dptr(self._workspace), C.byref(h)))
+        self._h = h
+        shp = (C.c_int32 * 2)()
+        L.qg_obs_shape(self._h, shp)
+        self._obs_shape = (int(shp[0]), int(shp[1]))
+        self._obs_size = int(L.qg_obs_size(self._h))
+        self._A = int(L.qg_num_actions(self._h))
+        B = self.batch
+        dev = self.device
+        self.obs = torch.zeros((B,) + self._obs_shape, dtype=torch.float32, device=dev)
+        self.mask = torch.zeros((B, self._A), dtype=torch.bool, device=dev)
+        self.reward = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(B, dtype=torch.bool, device=dev)
+        self.success = torch.zeros(B, dtype=torch.bool, device=dev)
+        self._twists = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().qg_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ shape / config
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def obs_shape(self):
+        return list(self._obs_shape)
+
+    def num_actions(self):
+        return self._A
+
+    @property
+    def gateset(self):
+        return list(self._gateset)
+
+    @property
+    def difficulty(self):
+        return int(lib().qg_get_difficulty(self._h))
+
+    @difficulty.setter
+    def difficulty(self, d):
+        check(lib().qg_set_difficulty(self._h, int(d)))
+
+    def twists(self):
+        """(obs_perms, act_perms) of Env::twists (symmetry.rs:297-361)."""
+        if self._twists is None:
+            L = lib()
+            t = C.c_void_p()
+            check(L.qg_twists_create(C.byref(self.cfg), C.byref(t)))
+            try:
+                cnt, ol, al = L.qg_twists_count(t), L.qg_twists_obs_len(t), L.qg_twists_act_len(t)
+                obs = np.zeros((cnt, ol), dtype=np.int64)
+                act = np.zeros((cnt, al), dtype=np.int64)
+                check(L.qg_twists_copy(t, obs.ctypes.data_as(C.c_void_p), act.ctypes.data_as(C.c_void_p)))
+            finally:
+                L.qg_twists_destroy(t)
+            self._twists = (obs.tolist(), act.tolist())
+        return self._twists
+
+    # ------------------------------------------------------------------ state in
+    def set_state(self, states, first: int = 0):
+        """Env::set_state.  `states`: one payload (list[int]) => loaded into every env, or a sequence /
+        int64 array of per-env payloads."""
+        if isinstance(states, np.ndarray) and states.ndim == 2:
+            arr = np.ascontiguousarray(states, dtype=np.int64)
+            count, stride, bcast = arr.shape[0], arr.shape[1], 0
+        elif len(states) > 0 and isinstance(states[0], (list, tuple, np.ndarray)):
+            stride = max(len(s) for s in states)
+            arr = np.zeros((len(states), stride), dtype=np.int64)
+            for i, s in enumerate(states):
+                arr[i, : len(s)] = s
+            count, bcast = len(states), 0
+        else:
+            arr = np.asarray(list(states), dtype=np.int64).reshape(1, -1)
+            count, stride, bcast = self.batch - first, arr.shape[1], 1
+        with torch.cuda.device(self.device):
+            check(lib().qg_set_state(self._h, arr.ctypes.data_as(C.c_void_p), stride, first, count, bcast, self._stream()))
+
+    def reset(self, seed: int = 0, first_env_id: int = 0):
+        check(lib().qg_reset(self._h, C.c_uint64(seed & (2**64 - 1)), first_env_id, self._stream()))
+
+    def snapshot(self):
+        """Clone of the whole batch (device copy of every env record)."""
+        check(lib().qg_snapshot(self._h, self._stream()))
+
+    def restore(self):
+        check(lib().qg_restore(self._h, self._stream()))
+
+    # ------------------------------------------------------------------ fused step
+    def step(self, actions: torch.Tensor, coins: torch.Tensor | None = None, perm_raw: torch.Tensor | None = None,
+             obs: torch.Tensor | None | bool = True, mask: torch.Tensor | None | bool = True):
+        """One fused step for all envs.  `actions`: int32 CUDA tensor [B].  obs/mask: True = write into the
+        engine-owned tensors, None/False = skip, or a caller tensor to write into.  Returns (obs, reward, done)."""
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.numel() == self.batch
+        obs_t = self.obs if obs is True else (None if obs is False else obs)
+        mask_t = self.mask if mask is True else (None if mask is False else mask)
+        check(lib().qg_step(self._h, _dptr(actions), _dptr(coins), _dptr(perm_raw), _dptr(obs_t), _dptr(mask_t),
+                            _dptr(self.reward), _dptr(self.done), _dptr(self.success), self._stream()))
+        return obs_t, self.reward, self.done
+
+    def step_host(self, actions: np.ndarray, reward: np.ndarray, done: np.ndarray, success: np.ndarray | None = None,
+                  coins: np.ndarray | None = None, obs: torch.Tensor | None = None, mask: torch.Tensor | None = None):
+        """End-to-end step with host buffers (pinned numpy views recommended): H2D actions, fused step
+        (observation written to the device tensor `obs`), D2H reward/done/success, stream synchronised."""
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib().qg_step_host(self._h, p(actions), p(coins), _dptr(obs), _dptr(mask), p(reward), p(done), p(success), self._stream()))
+
+    # ------------------------------------------------------------------ reads
+    def observe(self, perm_raw: torch.Tensor | None = None, out: torch.Tensor | None = None):
+        out = self.obs if out is None else out
+        check(lib().qg_observe(self._h, _dptr(perm_raw), _dptr(out), self._stream()))
+        return out
+
+    def masks(self, out: torch.Tensor | None = None):
+        out = self.mask if out is None else out
+        check(lib().qg_masks(self._h, _dptr(out), self._stream()))
+        return out
+
+    def status(self):
+        """(reward f32[B], is_final bool[B], success bool[B], depth int32[B]) read back from the records."""
+        depth = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+        check(lib().qg_read_status(self._h, _dptr(self.reward), _dptr(self.done), _dptr(self.success), _dptr(depth), self._stream()))
+        return self.reward, self.done, self.success, depth
+
+    def metrics(self):
+        """uint32[B,4]: n_cnots, n_layers_cnots, n_layers, n_gates (MetricsCounts, metrics.rs:126-133)."""
+        out = torch.zeros((self.batch, 4), dtype=torch.int32, device=self.device)
+        check(lib().qg_read_metrics(self._h, _dptr(out), self._stream()))
+        return out
+
+    def errors(self):
+        out = torch.zeros(self.batch, dtype=torch.int32, device=self.device)
+        check(lib().qg_read_errors(self._h, _dptr(out), self._stream()))
+        return out
+
+    def get_state(self, env: int = 0) -> np.ndarray:
+        cap = 1 << 16
+        buf = np.zeros(cap, dtype=np.uint8)
+        n = C.c_int64()
+        check(lib().qg_get_state_host(self._h, env, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._stream()))
+        return buf[: n.value].copy()
+
+    def solution(self, env: int = 0) -> list[int]:
+        cap = 65536
+        buf = np.zeros(cap, dtype=np.uint32)
+        n = C.c_int32()
+        check(lib().qg_solution_host(self._h, env, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._stream()))
+        return [int(v) for v in buf[: n.value]]
+
+    # ------------------------------------------------------------------ synth search pieces
+    def search_begin(self, seed: int = 0, first_rollout_id: int = 0):
+        check(lib().qg_search_begin(self._h, C.c_uint64(seed & (2**64 - 1)), first_rollout_id, self._stream()))
+
+    def search_step(self, weights: torch.Tensor, deterministic: bool = False, obs: torch.Tensor | None | bool = True,
+                    chosen: torch.Tensor | None = None, num_active: torch.Tensor | None = None):
+        assert weights.dtype == torch.float32 and weights.is_cuda and weights.is_contiguous()
+        obs_t = self.obs if obs is True else (None if obs is False else obs)
+        check(lib().qg_search_step(self._h, _dptr(weights), 1 if deterministic else 0, _dptr(obs_t), None, _dptr(chosen),
+                                   _dptr(num_active), self._stream()))
+        return obs_t
+
+    def search_best(self):
+        key, env = C.c_int64(), C.c_int64()
+        check(lib().qg_search_best(self._h, C.byref(key), C.byref(env), self._stream()))
+        return key.value, env.value
+
+    def returns(self):
+        out = torch.zeros(self.batch, dtype=torch.float32, device=self.device)
+        check(lib().qg_read_returns(self._h, _dptr(out), self._stream()))
+        return out
