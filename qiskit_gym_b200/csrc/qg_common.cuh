@@ -55,6 +55,7 @@ struct DevCfg {
     const uint32_t* ident;    // [SW] identity state (LF/Clifford) — solved() target
     const uint8_t* qperms;    // [nperms][n]   PauliNetwork qubit permutations (pauli.rs:289-290)
     const uint16_t* aperms;   // [nperms][A]
+    const uint32_t* pgen;     // PauliNetwork reset generator tables (see k_reset_pauli)
     uint64_t seed; int64_t first_id;
     uint32_t magic_n;         // ceil(2^32 / n): exact division of obs offsets by n (Permutation expander)
 };

@@ -31,8 +31,8 @@ struct qg_engine {
     // pinned host staging
     uint32_t* h_staged = nullptr; int64_t h_staged_words = 0;
     unsigned long long* h_best = nullptr;
-    int epc = 64; size_t smem_bytes = 0; int sm_scr = 0, sm_obs = 0, sm_aux = 0;
-    uint64_t magic_obs = 0, magic_A = 0;
+    size_t smem_bytes = 0; int sm_warp_words = 0, sm_scr = 0, sm_obs = 0;
+    uint64_t magic_obs = 0, magic_A = 0; uint32_t magic_vpe = 0, magic_a4 = 0;
     int nperms = 0;
 };
 
@@ -51,9 +51,9 @@ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 inline uint64_t magic40(uint32_t d) { return ((1ull << 40) + d - 1) / d; }
 
 struct WsPlan {
-    int64_t rec, snap, sol, ret, gates, ident, qperms, aperms, staged, io_actions, io_coins, io_reward, io_done, io_success, best, total;
+    int64_t rec, snap, sol, ret, gates, ident, qperms, aperms, pgen, staged, io_actions, io_coins, io_reward, io_done, io_success, best, total;
 };
-WsPlan plan_ws(const Layout& L, int64_t B, int64_t nperms) {
+WsPlan plan_ws(const Layout& L, int64_t B, int64_t nperms, int64_t pgen_words) {
     const int64_t Bpad = align_up(std::max<int64_t>(B, 1), 32);
     WsPlan p{}; int64_t o = 0;
     auto take = [&](int64_t bytes) { const int64_t at = o; o = align_up(o + bytes, 256); return at; };
@@ -65,6 +65,7 @@ WsPlan plan_ws(const Layout& L, int64_t B, int64_t nperms) {
     p.ident = take((int64_t)L.SW * 4);
     p.qperms = take(std::max<int64_t>(nperms * L.n, 1));
     p.aperms = take(std::max<int64_t>(nperms * L.A * 2, 1));
+    p.pgen = take(std::max<int64_t>(pgen_words * 4, 4));
     p.staged = take((int64_t)L.PW * Bpad * 4);
     p.io_actions = take(Bpad * 4); p.io_coins = take(Bpad); p.io_reward = take(Bpad * 4); p.io_done = take(Bpad); p.io_success = take(Bpad);
     p.best = take(64);
@@ -77,24 +78,14 @@ int pauli_perms(const qg_config* cfg, Twists& tw) {
     return compute_twists(cfg, true, tw);
 }
 
-template <int KIND, int EPC, int MODE>
-int launch_step_t(qg_engine* e, const StepArgs& a, cudaStream_t st) {
-    auto kern = k_step<KIND, EPC, MODE>;
-    const unsigned grid = (unsigned)((e->B + EPC - 1) / EPC);
-    kern<<<grid, kThreads, e->smem_bytes, st>>>(e->dc, a);
-    CUDA_OK(cudaGetLastError());
-    return QG_OK;
-}
-template <int KIND, int EPC>
-int prepare_kernels_t(qg_engine* e) {   // opt in to > 48 KB dynamic shared memory once, outside any stream capture
-    if (e->smem_bytes <= 48 * 1024) return QG_OK;
-    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, EPC, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, EPC, MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, EPC, MODE_SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    return QG_OK;
-}
 template <int KIND>
-int prepare_kernels_k(qg_engine* e) { return e->epc == 64 ? prepare_kernels_t<KIND, 64>(e) : prepare_kernels_t<KIND, 32>(e); }
+int prepare_kernels_k(qg_engine* e) {   // opt in to > 48 KB dynamic shared memory once, outside any stream capture
+    if (e->smem_bytes <= 48 * 1024) return QG_OK;
+    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, MODE_SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    return QG_OK;
+}
 int prepare_kernels(qg_engine* e) {
     switch (e->L.kind) {
         case QG_ENV_PERMUTATION: return prepare_kernels_k<QG_ENV_PERMUTATION>(e);
@@ -105,7 +96,11 @@ int prepare_kernels(qg_engine* e) {
 }
 template <int KIND, int MODE>
 int launch_step_k(qg_engine* e, const StepArgs& a, cudaStream_t st) {
-    return e->epc == 64 ? launch_step_t<KIND, 64, MODE>(e, a, st) : launch_step_t<KIND, 32, MODE>(e, a, st);
+    const int64_t tiles = (e->B + 31) / 32;
+    const unsigned grid = (unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta);
+    k_step<KIND, MODE><<<grid, kWarpsPerCta * 32, e->smem_bytes, st>>>(e->dc, a);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
 }
 template <int MODE>
 int launch_step(qg_engine* e, StepArgs a, cudaStream_t st) {
@@ -113,7 +108,8 @@ int launch_step(qg_engine* e, StepArgs a, cudaStream_t st) {
     int cur = -1;
     CUDA_OK(cudaGetDevice(&cur));
     if (cur != e->device) CUDA_OK(cudaSetDevice(e->device));
-    a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.sm_aux = e->sm_aux; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     if (a.mask && (reinterpret_cast<uintptr_t>(a.mask) & 15)) { set_error("mask_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     switch (e->L.kind) {
@@ -213,7 +209,9 @@ int64_t qg_workspace_bytes(const qg_config* cfg, int64_t batch) {
     if (batch < 0) { set_error("batch must be >= 0"); return QG_ERR_INVALID; }
     Twists tw; rc = pauli_perms(cfg, tw);
     if (rc != QG_OK) return rc;
-    return plan_ws(L, batch, (int64_t)tw.act_perms.size()).total;
+    std::vector<uint32_t> pg;
+    if (cfg->env_kind == QG_ENV_PAULI_NETWORK) pauli_gen_tables(cfg, pg);
+    return plan_ws(L, batch, (int64_t)tw.act_perms.size(), (int64_t)pg.size()).total;
 }
 
 int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspace_dev, qg_engine** out) {
@@ -235,7 +233,9 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     e->cfg = *cfg; e->gates.assign(cfg->gateset, cfg->gateset + cfg->num_gates); e->cfg.gateset = e->gates.data();
     e->L = L; e->device = device; e->B = batch; e->Bpad = align_up(std::max<int64_t>(batch, 1), 32);
     e->nperms = (int)tw.act_perms.size();
-    const WsPlan p = plan_ws(L, batch, e->nperms);
+    std::vector<uint32_t> pg;
+    if (cfg->env_kind == QG_ENV_PAULI_NETWORK) pauli_gen_tables(cfg, pg);
+    const WsPlan p = plan_ws(L, batch, e->nperms, (int64_t)pg.size());
     auto fail = [&](int code) { qg_destroy(e); return code; };
     if (workspace_dev) {
         if (reinterpret_cast<uintptr_t>(workspace_dev) & 255) { set_error("workspace must be 256-byte aligned"); return fail(QG_ERR_INVALID); }
@@ -245,14 +245,14 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
         if (ce != cudaSuccess) { set_error(std::string("cudaMalloc workspace: ") + cudaGetErrorString(ce)); e->ws = nullptr; return fail(QG_ERR_CUDA); }
         e->owns_ws = true;
     }
-    // shared-memory plan: [W | SCR | OW] words per env + one aux word
-    const int words = L.W + L.SCR + L.OW + 1;
-    e->epc = 64;
-    if ((size_t)words * 64 * 4 > 200 * 1024) e->epc = 32;
-    if ((size_t)words * e->epc * 4 > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
-    e->sm_scr = L.W * e->epc; e->sm_obs = (L.W + L.SCR) * e->epc; e->sm_aux = (L.W + L.SCR + L.OW) * e->epc;
-    e->smem_bytes = (size_t)words * e->epc * 4;
+    // shared-memory plan: each warp owns [W | SCR | OW] words x kStride for its 32 envs
+    const int words = L.W + L.SCR + L.OW;
+    e->sm_warp_words = words * kStride; e->sm_scr = L.W * kStride; e->sm_obs = (L.W + L.SCR) * kStride;
+    e->smem_bytes = (size_t)e->sm_warp_words * kWarpsPerCta * 4;
+    if (e->smem_bytes > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
     e->magic_obs = magic40((uint32_t)L.obs_size); e->magic_A = magic40((uint32_t)L.A);
+    auto magic32 = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
+    e->magic_vpe = magic32((uint32_t)L.obs_size / 4); e->magic_a4 = magic32((uint32_t)L.A / 4);
     rc = prepare_kernels(e);
     if (rc != QG_OK) return fail(rc);
 
@@ -266,7 +266,7 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     d.B = batch; d.Bpad = e->Bpad;
     d.rec = (uint32_t*)(e->ws + p.rec); d.sol = (uint32_t*)(e->ws + p.sol); d.ret = (float*)(e->ws + p.ret);
     d.gates = (const uint32_t*)(e->ws + p.gates); d.ident = (const uint32_t*)(e->ws + p.ident);
-    d.qperms = (const uint8_t*)(e->ws + p.qperms); d.aperms = (const uint16_t*)(e->ws + p.aperms);
+    d.qperms = (const uint8_t*)(e->ws + p.qperms); d.aperms = (const uint16_t*)(e->ws + p.aperms); d.pgen = (const uint32_t*)(e->ws + p.pgen);
     d.seed = 0; d.first_id = 0;
     d.magic_n = (uint32_t)(((1ull << 32) + (uint32_t)L.n - 1) / (uint32_t)L.n);
     e->staged = (uint32_t*)(e->ws + p.staged);
@@ -289,6 +289,7 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
         ce = cudaMemcpy((void*)d.qperms, qp.data(), qp.size(), cudaMemcpyHostToDevice);
         if (ce == cudaSuccess) ce = cudaMemcpy((void*)d.aperms, ap.data(), ap.size() * 2, cudaMemcpyHostToDevice);
     }
+    if (ce == cudaSuccess && !pg.empty()) ce = cudaMemcpy((void*)d.pgen, pg.data(), pg.size() * 4, cudaMemcpyHostToDevice);
     if (ce == cudaSuccess) ce = cudaMallocHost(&e->h_best, 64);
     if (ce != cudaSuccess) { set_error(std::string("engine table upload: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
     // constructor state: identity, depth 1, success, reward 1.0 (permutation.rs:75-98, clifford.rs:205-236, pauli.rs:354-409)
@@ -346,11 +347,17 @@ int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride, int64
 
 int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream) {
     if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
-    if (e->L.kind == QG_ENV_PAULI_NETWORK) { set_error("PauliNetwork reset runs on the host side of the binding (generator pauli.rs:115-271); use qg_set_state with generated targets"); return QG_ERR_UNSUPPORTED; }
     CUDA_OK(cudaSetDevice(e->device));
     e->dc.seed = seed; e->dc.first_id = first_env_id;
     if (e->B == 0) return QG_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (e->L.kind == QG_ENV_PAULI_NETWORK) {
+        const int words = e->L.SW + e->L.XW + 3 * e->L.Rtot;
+        const int fl = e->cfg.final_pauli_layers >= 0 ? e->cfg.final_pauli_layers : e->cfg.max_rotations + 2;
+        k_reset_pauli<32><<<(unsigned)((e->B + 31) / 32), 32, (size_t)words * 32 * 4, st>>>(e->dc, std::max(e->cfg.pauli_diff_scale, 1), e->cfg.num_qubits_decay, fl);
+        CUDA_OK(cudaGetLastError());
+        return QG_OK;
+    }
     const unsigned grid = (unsigned)((e->B + 63) / 64);
     const size_t sm = (size_t)e->L.SW * 64 * 4;
     switch (e->L.kind) {

@@ -199,6 +199,36 @@ int compute_twists(const qg_config* cfg, bool internal_pauli, Twists& out) {
     return QG_OK;
 }
 
+// BFS all-pairs distances over the CX coupling graph, grouped by distance (pauli.rs:56-111).
+void pauli_gen_tables(const qg_config* cfg, std::vector<uint32_t>& out) {
+    const int n = cfg->num_qubits;
+    std::vector<std::vector<int>> nb(n);
+    std::vector<uint32_t> cx;
+    for (int i = 0; i < cfg->num_gates; ++i) {
+        const qg_gate& g = cfg->gateset[i];
+        if (g.kind != QG_CX) continue;
+        cx.push_back((uint32_t)g.q0 | ((uint32_t)g.q1 << 8));
+        if (std::find(nb[g.q0].begin(), nb[g.q0].end(), g.q1) == nb[g.q0].end()) nb[g.q0].push_back(g.q1);
+        if (std::find(nb[g.q1].begin(), nb[g.q1].end(), g.q0) == nb[g.q1].end()) nb[g.q1].push_back(g.q0);
+    }
+    std::map<int, std::vector<uint32_t>> by_dist;
+    for (int src = 0; src < n; ++src) {
+        std::vector<int> dist(n, -1), frontier{src};
+        dist[src] = 0;
+        for (size_t h = 0; h < frontier.size(); ++h) for (int v : nb[frontier[h]]) if (dist[v] < 0) { dist[v] = dist[frontier[h]] + 1; frontier.push_back(v); }
+        for (int dst = src + 1; dst < n; ++dst) if (dist[dst] >= 0) by_dist[dist[dst]].push_back((uint32_t)src | ((uint32_t)dst << 8));
+    }
+    size_t np = 0; for (auto& kv : by_dist) np += kv.second.size();
+    out.clear();
+    out.push_back((uint32_t)by_dist.size()); out.push_back((uint32_t)np); out.push_back((uint32_t)cx.size());
+    for (auto& kv : by_dist) out.push_back((uint32_t)kv.first);
+    uint32_t off = 0;
+    for (auto& kv : by_dist) { out.push_back(off); off += (uint32_t)kv.second.size(); }
+    out.push_back(off);
+    for (auto& kv : by_dist) out.insert(out.end(), kv.second.begin(), kv.second.end());
+    out.insert(out.end(), cx.begin(), cx.end());
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // set_state packers
 // ---------------------------------------------------------------------------------------------------------

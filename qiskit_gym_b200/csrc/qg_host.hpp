@@ -35,6 +35,9 @@ struct Twists {
 };
 int compute_twists(const qg_config* cfg, bool internal_pauli, Twists& out);
 
+// PauliNetwork reset generator tables: coupling-graph distance classes (pauli.rs:56-111) and CX pairs (pauli.rs:357-364)
+void pauli_gen_tables(const qg_config* cfg, std::vector<uint32_t>& out);
+
 // set_state payload -> staged words.  Returns QG_OK / QG_ERR_STATE.  `used` = i64 entries consumed.
 int pack_state(const qg_config* cfg, const Layout& L, const int64_t* payload, int64_t avail, uint32_t* out, int64_t* used);
 // identity payload words (constructor state)

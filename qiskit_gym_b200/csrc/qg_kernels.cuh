@@ -6,8 +6,8 @@
 //       gate lookup -> MetricsTracker update (metrics.rs:64-123) -> weighted penalty (metrics.rs:135-146)
 //       -> gate applied as row XOR / row swap on the packed GF(2) state -> solution log -> depth tick
 //       -> optional inverse (coin) -> solved() -> reward -> write-back;
-//   phase 2 (whole CTA): the CTA's contiguous slab of the dense float observation tensor and of the
-//       uint8 action-mask tensor is produced from the packed bits with 16-byte coalesced stores.
+//   phase 2 (the whole warp, for its 32 environments): the contiguous slab of the dense float observation tensor and
+//       of the uint8 action-mask tensor is produced from the packed bits with 16-byte coalesced streaming stores.
 #pragma once
 #include "qg_common.cuh"
 
@@ -24,8 +24,9 @@ struct StepArgs {
     float* reward; uint8_t* done; uint8_t* success;   // [B] or null
     int32_t* chosen;             // [B] or null    (MODE_SEARCH)
     int32_t* num_active;         // [1] or null    (MODE_SEARCH)
-    int32_t sm_scr, sm_obs, sm_aux;   // shared-memory region offsets in words
-    uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)
+    int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
+    uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
+    uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
 };
 
 enum { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_SEARCH = 2 };
@@ -260,31 +261,47 @@ __device__ void pn_build_obs(const DevCfg& c, const Wd& S, const PauliRegs& p, c
 }
 
 // ---- the fused kernel ----------------------------------------------------------------------------------
-template <int KIND, int EPC, int MODE>
-__global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * EPC;
-    const int cnt = (int)min((int64_t)EPC, c.B - e0);
-    uint32_t* aux = smem + a.sm_aux;               // per env: bit0 = mask value (!success), bit1 = outputs enabled
+// Work decomposition: one WARP owns a tile of 32 consecutive environments (lane == environment in phase 1) and a
+// private shared-memory region [word][kStride]; there is no block-level barrier, so warps drift apart and the
+// latency-bound phase 1 of one warp overlaps the store-bound phase 2 of the others on the same SM.
+constexpr int kStride = 33;          // odd word stride: bank = (word + lane) % 32 -> conflict free both for per-lane private
+                                     // access with a warp-uniform word and for the expander's broadcast reads of one env
+constexpr int kWarpsPerCta = 2;
 
-    if (tid < cnt) {
-        typedef SmWords<EPC> Wd;
-        const int64_t env = e0 + tid;
-        const Wd R{smem + tid};
+__device__ __forceinline__ void cp_async_4(uint32_t* smem_dst, const uint32_t* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
+    if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
+    const int cnt = (int)min((int64_t)32, c.B - e0);
+    uint32_t* const wbase = smem + (size_t)warp * a.sm_warp_words;
+    typedef SmWords<kStride> Wd;
+    const int64_t env = e0 + lane;
+    const bool live = lane < cnt;
+    bool success = false, enabled = false;
+
+    if (live) {
+        const Wd R{wbase + lane};
         const Wd LG = R.at(c.off_lastg), LC = R.at(c.off_lastcx), S = R.at(c.off_state), X = R.at(c.off_extra);
-        const Wd SCR{smem + a.sm_scr + tid}, O{smem + a.sm_obs + tid};
-#pragma unroll 4
-        for (int w = 0; w < c.W; ++w) R[w] = c.rec[(size_t)w * c.Bpad + env];
+        const Wd SCR{wbase + a.sm_scr + lane}, O{wbase + a.sm_obs + lane};
+        for (int w = 0; w < c.W; ++w) cp_async_4(&R[w], c.rec + (size_t)w * c.Bpad + env);   // all W loads in flight at once
+        int action = -1;
+        if (MODE == MODE_STEP) action = a.actions[env];
+        cp_async_wait_all();
 
         uint32_t depth = R[HD_DEPTH], flags = R[HD_FLAGS], tick = R[HD_TICK];
-        bool success = (flags & FL_SUCCESS) != 0;
-        bool enabled = true;
+        success = (flags & FL_SUCCESS) != 0;
+        enabled = true;
         PauliRegs pr{};
         if (KIND == QG_ENV_PAULI_NETWORK) { pr.plo = X[PX_PLO]; pr.phi = X[PX_PHI]; pr.alive = X[PX_ALIVE]; pr.ord0 = X[PX_ORD0]; pr.ord1 = X[PX_ORD1]; pr.misc = X[PX_MISC]; }
 
-        int action = -1;
-        if (MODE == MODE_STEP) action = a.actions[env];
         if (MODE == MODE_SEARCH) {
             // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
             enabled = !(depth == 0 || success);
@@ -375,8 +392,8 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevCf
             if (MODE == MODE_SEARCH) c.ret[env] = __fadd_rn(c.ret[env], reward);
             if (a.reward) a.reward[env] = reward;
         }
-        if (MODE == MODE_OBSERVE || !enabled) { if (a.reward && MODE != MODE_SEARCH) a.reward[env] = __uint_as_float(R[HD_REWARD]); }
-        if (enabled || MODE != MODE_SEARCH) {
+        if (MODE == MODE_OBSERVE && a.reward) a.reward[env] = __uint_as_float(R[HD_REWARD]);
+        if (enabled) {
             if (a.done) a.done[env] = (depth == 0 || success) ? 1 : 0;
             if (a.success) a.success[env] = success ? 1 : 0;
         }
@@ -400,89 +417,76 @@ __global__ void __launch_bounds__(kThreads) k_step(const __grid_constant__ DevCf
                 c.rec[(size_t)(c.off_extra + PX_MISC) * c.Bpad + env] = X[PX_MISC];
             }
         }
-        aux[tid] = (success ? 0u : 1u) | (enabled ? 2u : 0u);
     }
-    if (MODE == MODE_SEARCH && a.num_active) {
-        const bool en = (tid < cnt) && (aux[tid] & 2u);      // own write, same thread
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, en);
-        if ((tid & 31) == 0 && b) atomicAdd(a.num_active, __popc(b));
-    }
-    __syncthreads();
+    __syncwarp();
+    const uint32_t mask_bits = __ballot_sync(0xFFFFFFFFu, live && !success);     // masks() = [!success; A] (clifford.rs:349-351)
+    const uint32_t en_bits = __ballot_sync(0xFFFFFFFFu, live && enabled);
+    if (MODE == MODE_SEARCH && a.num_active && lane == 0 && en_bits) atomicAdd(a.num_active, __popc(en_bits));
 
-    // ---------------- phase 2: expand bits -> float observation slab, mask slab ------------------------
+    // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab ------------
     if (a.obs) {
         float* out = a.obs + (size_t)e0 * c.obs_size;
-        const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size;
-        const uint32_t nvec = total >> 2;
-        const uint32_t* bits = (KIND == QG_ENV_PAULI_NETWORK) ? (smem + a.sm_obs) : (smem + (size_t)c.off_state * EPC);
-        auto elem = [&](int e, uint32_t off) -> float {
-            if (KIND == QG_ENV_PERMUTATION) {
-                const uint32_t i = (uint32_t)(((uint64_t)off * c.magic_n) >> 32), col = off - i * (uint32_t)c.n;
-                const uint32_t v = (bits[(i >> 2) * EPC + e] >> ((i & 3) * 8)) & 0xFFu;      // observe(): index i*n + state[i] (permutation.rs:241-243)
-                return v == col ? 1.0f : 0.0f;
+        const uint32_t* bits = wbase + ((KIND == QG_ENV_PAULI_NETWORK) ? a.sm_obs : c.off_state * kStride);
+        if (KIND != QG_ENV_PERMUTATION && (c.obs_size & 3) == 0) {
+            // fast path: a float4 never straddles two environments; one LDS + one funnel shift per 4 outputs
+            const uint32_t VPE = (uint32_t)c.obs_size >> 2, total = (uint32_t)cnt * VPE;
+#pragma unroll 2
+            for (uint32_t j = lane; j < total; j += 32) {
+                const uint32_t e = (VPE == 1) ? j : __umulhi(j, a.magic_vpe);
+                const uint32_t v = j - e * VPE;
+                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+                const uint32_t nib = bits[(v >> 3) * kStride + e] >> ((v & 7u) << 2);
+                float4 f;
+                f.x = (nib & 1u) ? 1.0f : 0.0f; f.y = (nib & 2u) ? 1.0f : 0.0f; f.z = (nib & 4u) ? 1.0f : 0.0f; f.w = (nib & 8u) ? 1.0f : 0.0f;
+                __stcs(reinterpret_cast<float4*>(out) + j, f);
             }
-            return ((bits[(off >> 5) * EPC + e] >> (off & 31)) & 1u) ? 1.0f : 0.0f;
-        };
-        for (uint32_t j = tid; j < nvec; j += kThreads) {
-            const uint32_t f0 = j << 2;
-            int e = (int)fastdiv40(f0, a.magic_obs);
-            uint32_t off = f0 - (uint32_t)e * (uint32_t)c.obs_size;
-            if (off + 4 <= (uint32_t)c.obs_size) {
-                if (MODE == MODE_SEARCH && !(aux[e] & 2u)) continue;
-                float4 v;
-                if (KIND == QG_ENV_PERMUTATION) { v.x = elem(e, off); v.y = elem(e, off + 1); v.z = elem(e, off + 2); v.w = elem(e, off + 3); }
-                else {
-                    const uint32_t w = off >> 5, s = off & 31;
-                    const uint32_t lo = bits[w * EPC + e], hi = (s > 28) ? bits[(w + 1) * EPC + e] : 0u;
-                    const uint32_t nib = __funnelshift_r(lo, hi, s);
-                    v.x = (nib & 1u) ? 1.0f : 0.0f; v.y = (nib & 2u) ? 1.0f : 0.0f; v.z = (nib & 4u) ? 1.0f : 0.0f; v.w = (nib & 8u) ? 1.0f : 0.0f;
+        } else {
+            // general path: walk (env, offset) incrementally; Permutation reads the one-hot row from the packed bytes
+            const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, nvec = total >> 2, n = (uint32_t)c.n;
+            auto elem = [&](uint32_t e, uint32_t off) -> float {
+                if (KIND == QG_ENV_PERMUTATION) {
+                    const uint32_t i = __umulhi(off, c.magic_n), col = off - i * n;        // observe(): index i*n + state[i] (permutation.rs:241-243)
+                    return (((bits[(i >> 2) * kStride + e] >> ((i & 3u) * 8u)) & 0xFFu) == col) ? 1.0f : 0.0f;
                 }
-                __stcs(reinterpret_cast<float4*>(out) + j, v);
-            } else {
-                for (int k = 0; k < 4; ++k) {                 // vector straddles two environments
+                return ((bits[(off >> 5) * kStride + e] >> (off & 31u)) & 1u) ? 1.0f : 0.0f;
+            };
+            for (uint32_t j = lane; j < nvec; j += 32) {
+                const uint32_t f0 = j << 2;
+                uint32_t e = fastdiv40(f0, a.magic_obs), off = f0 - e * (uint32_t)c.obs_size;
+                float v[4]; bool all_on = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
                     if (off == (uint32_t)c.obs_size) { off = 0; ++e; }
-                    if (MODE != MODE_SEARCH || (aux[e] & 2u)) out[f0 + k] = elem(e, off);
-                    ++off;
+                    if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) all_on = false;
+                    v[k] = elem(e, off); ++off;
+                }
+                if (all_on) __stcs(reinterpret_cast<float4*>(out) + j, make_float4(v[0], v[1], v[2], v[3]));
+                else {
+                    uint32_t e2 = fastdiv40(f0, a.magic_obs), o2 = f0 - e2 * (uint32_t)c.obs_size;
+                    for (int k = 0; k < 4; ++k) { if (o2 == (uint32_t)c.obs_size) { o2 = 0; ++e2; } if ((en_bits >> e2) & 1u) out[f0 + k] = v[k]; ++o2; }
                 }
             }
-        }
-        for (uint32_t f = (nvec << 2) + tid; f < total; f += kThreads) {
-            const int e = (int)fastdiv40(f, a.magic_obs);
-            if (MODE != MODE_SEARCH || (aux[e] & 2u)) out[f] = elem(e, f - (uint32_t)e * (uint32_t)c.obs_size);
+            for (uint32_t f = (nvec << 2) + lane; f < total; f += 32) {
+                const uint32_t e = fastdiv40(f, a.magic_obs);
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[f] = elem(e, f - e * (uint32_t)c.obs_size);
+            }
         }
     }
-    if (a.mask) {                                             // masks() = [!success; A] (clifford.rs:349-351)
+    if (a.mask) {
         uint8_t* out = a.mask + (size_t)e0 * c.A;
-        const uint32_t total = (uint32_t)cnt * (uint32_t)c.A;
-        const uint32_t nvec = total >> 4;
-        for (uint32_t j = tid; j < nvec; j += kThreads) {
-            const uint32_t b0 = j << 4;
-            int e = (int)fastdiv40(b0, a.magic_A);
-            uint32_t r = b0 - (uint32_t)e * (uint32_t)c.A;
-            if (r + 16 <= (uint32_t)c.A) {
-                if (MODE == MODE_SEARCH && !(aux[e] & 2u)) continue;
-                const uint32_t v = (aux[e] & 1u) ? 0x01010101u : 0u;
-                __stcs(reinterpret_cast<uint4*>(out) + j, make_uint4(v, v, v, v));
-            } else {
-                bool all_on = true; uint32_t wv[4] = {0, 0, 0, 0};
-                int e2 = e; uint32_t r2 = r;
-                for (int k = 0; k < 16; ++k) {
-                    if (r2 == (uint32_t)c.A) { r2 = 0; ++e2; }
-                    if (MODE == MODE_SEARCH && !(aux[e2] & 2u)) all_on = false;
-                    wv[k >> 2] |= (aux[e2] & 1u) << ((k & 3) * 8);
-                    ++r2;
-                }
-                if (all_on) __stcs(reinterpret_cast<uint4*>(out) + j, make_uint4(wv[0], wv[1], wv[2], wv[3]));
-                else for (int k = 0; k < 16; ++k) {
-                    if (r == (uint32_t)c.A) { r = 0; ++e; }
-                    if (aux[e] & 2u) out[b0 + k] = (uint8_t)(aux[e] & 1u);
-                    ++r;
-                }
+        if ((c.A & 3) == 0) {
+            const uint32_t WPE = (uint32_t)c.A >> 2, total = (uint32_t)cnt * WPE;
+            for (uint32_t j = lane; j < total; j += 32) {
+                const uint32_t e = (WPE == 1) ? j : __umulhi(j, a.magic_a4);
+                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+                __stcs(reinterpret_cast<uint32_t*>(out) + j, ((mask_bits >> e) & 1u) ? 0x01010101u : 0u);
             }
-        }
-        for (uint32_t b = (nvec << 4) + tid; b < total; b += kThreads) {
-            const int e = (int)fastdiv40(b, a.magic_A);
-            if (MODE != MODE_SEARCH || (aux[e] & 2u)) out[b] = (uint8_t)(aux[e] & 1u);
+        } else {
+            const uint32_t total = (uint32_t)cnt * (uint32_t)c.A;
+            for (uint32_t b = lane; b < total; b += 32) {
+                const uint32_t e = fastdiv40(b, a.magic_A);
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[b] = (uint8_t)((mask_bits >> e) & 1u);
+            }
         }
     }
 }
@@ -542,6 +546,105 @@ __global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c)
     const long long d = (long long)c.depth_slope * (long long)c.difficulty;
     put(HD_DEPTH, (uint32_t)(d < (long long)c.max_depth ? d : (long long)c.max_depth));
     put(HD_FLAGS, ok ? FL_SUCCESS : 0u);
+    put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
+    put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
+    put(HD_TICK, 0);
+}
+
+// ---- PauliNetwork reset (pauli.rs:554-586): rotations from generate_paulis_with_difficulty (115-213), tableau from
+// random_clifford_tableau (220-271), then the initial clean.  All draws come from one Philox stream per env
+// (draw index = running counter), in the order the reference code makes them.
+// gen tables (c.pgen): [0]=ND, [1]=NP, [2]=NCX, dists[ND] ascending, pair_off[ND+1], pairs[NP] (q1 | q2<<8, q1<q2), cx[NCX] (q0 | q1<<8)
+template <int EPC>
+__global__ void __launch_bounds__(EPC) k_reset_pauli(const __grid_constant__ DevCfg c, int pauli_diff_scale, float decay, int final_layers) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x;
+    const int64_t env = (int64_t)blockIdx.x * EPC + tid;
+    if (env >= c.B) return;
+    typedef SmWords<EPC> Wd;
+    const Wd S{smem + tid}, X = S.at(c.SW), RX = X.at(c.W - c.off_extra), RZ = RX.at(c.Rtot), HV = RZ.at(c.Rtot);
+    const int n = c.n, D = 2 * n;
+    const uint32_t* tab = c.pgen;
+    const int ND = (int)tab[0], NCX = (int)tab[2];
+    const uint32_t* dists = tab + 3; const uint32_t* poff = dists + ND; const uint32_t* pairs = poff + ND + 1; const uint32_t* cxp = pairs + tab[1];
+    uint32_t ctr = 0;
+    auto draw = [&]() { return philox_draw(c.seed, (uint64_t)(c.first_id + env), ctr++, STREAM_RESET); };
+    auto below = [&](uint32_t k) { return __umulhi(draw(), k); };
+    auto unit = [&]() { return (float)(draw() >> 8) * (1.0f / 16777216.0f); };
+    auto count_le = [&](uint32_t lim) { int k = 0; while (k < ND && dists[k] <= lim) ++k; return k; };
+
+    // --- rotations
+    int R = 0;
+    uint32_t remaining = (uint32_t)c.difficulty / (uint32_t)pauli_diff_scale;
+    while (remaining > 0 && R < final_layers) {
+        const uint32_t diff = remaining;
+        const int nvalid = count_le(diff);
+        if (nvalid == 0) break;
+        uint32_t qubits = 0, pd = diff;
+        uint32_t nd = below((uint32_t)nvalid);
+        uint32_t pr = pairs[poff[nd] + below(poff[nd + 1] - poff[nd])];
+        qubits |= (1u << (pr & 0xFFu)) | (1u << (pr >> 8));
+        pd = pd > dists[nd] ? pd - dists[nd] : 0u;
+        for (;;) {
+            const int nvd = min(count_le(pd), nvalid);
+            if (pd == 0 || nvd == 0 || __popc(qubits) >= n) break;
+            if (unit() <= decay) break;
+            nd = below((uint32_t)nvd);
+            uint32_t nvp = 0;
+            for (uint32_t i = poff[nd]; i < poff[nd + 1]; ++i) { const uint32_t q = pairs[i]; if (((qubits >> (q & 0xFFu)) | (qubits >> (q >> 8))) & 1u) ++nvp; }
+            if (nvp == 0) continue;
+            uint32_t pick = below(nvp);
+            for (uint32_t i = poff[nd]; i < poff[nd + 1]; ++i) {
+                const uint32_t q = pairs[i];
+                if (((qubits >> (q & 0xFFu)) | (qubits >> (q >> 8))) & 1u) { if (pick == 0) { pr = q; break; } --pick; }
+            }
+            qubits |= (1u << (pr & 0xFFu)) | (1u << (pr >> 8));
+            pd = pd > dists[nd] ? pd - dists[nd] : 0u;
+        }
+        uint32_t x = 0, z = 0;
+        // the label string holds qubit q's axis at string position q, and Pauli::from_label reads position p as
+        // qubit n-1-p (pauli.rs:62), so the generated axis lands on qubit n-1-q.
+        for (int q = 0; q < n; ++q) if ((qubits >> q) & 1u) { const uint32_t ax = below(3u); const int k = n - 1 - q; if (ax != 2u) x |= 1u << k; if (ax != 0u) z |= 1u << k; }
+        RX[R] = x; RZ[R] = z; ++R;
+        const uint32_t cost = max(diff - pd, 1u);
+        remaining = remaining > cost ? remaining - cost : 0u;
+    }
+    // --- tableau
+    for (int w = 0; w < c.SW; ++w) S[w] = 0;
+    for (int r = 0; r < D; ++r) xor_bits(S, r * c.CW + r, 1, 1u);
+    if (c.difficulty != 0 && NCX != 0) {
+        for (int k = 0; k < c.difficulty; ++k) {
+            const float r = unit();
+            if (r > 0.3f) { const uint32_t pr = cxp[below((uint32_t)NCX)]; const int q0 = (int)(pr & 0xFFu), q1 = (int)(pr >> 8); row_xor(S, c.CW, q1, q0); row_xor(S, c.CW, n + q0, n + q1); }
+            else if (r > 0.15f) { const int q = (int)below((uint32_t)n); row_swap(S, c.CW, q, n + q); }
+            else { const int q = (int)below((uint32_t)n); row_xor(S, c.CW, n + q, q); }
+        }
+    }
+    // --- attach rotations: columns, phases (#Y mod 4), anticommutation rows
+    for (int w = 0; w < c.W - c.off_extra; ++w) X[w] = 0;
+    PauliRegs p{}; p.ord0 = 0x76543210u; p.ord1 = 0xFEDCBA98u;
+    for (int r = 0; r < R; ++r) {
+        const uint32_t x = RX[r], z = RZ[r];
+        for (int q = 0; q < n; ++q) { if ((x >> q) & 1u) xor_bits(S, q * c.CW + D + r, 1, 1u); if ((z >> q) & 1u) xor_bits(S, (n + q) * c.CW + D + r, 1, 1u); }
+        const uint32_t ys = (uint32_t)__popc(x & z) & 3u;
+        p.plo |= (ys & 1u) << r; p.phi |= (ys >> 1) << r;
+        uint32_t anti = 0;
+        for (int j = 0; j < r; ++j) if ((__popc(x & RZ[j]) + __popc(z & RX[j])) & 1) anti |= 1u << j;
+        X[PX_ANTI + (r >> 1)] |= anti << ((r & 1) * 16);
+    }
+    p.alive = (R >= 32) ? 0xFFFFFFFFu : ((1u << R) - 1u);
+    p.misc = ((uint32_t)R << 16) | ((uint32_t)R << 24);
+    int nh = 0; uint32_t err = 0;
+    pn_clean(c, S, X, p, HV, nh, err);                      // "clean initially trivial rotations" (pauli.rs:575)
+    const bool ok = pn_solved(c, S, p);
+    X[PX_PLO] = p.plo; X[PX_PHI] = p.phi; X[PX_ALIVE] = p.alive; X[PX_ORD0] = p.ord0; X[PX_ORD1] = p.ord1; X[PX_MISC] = p.misc;
+    auto put = [&](int w, uint32_t v) { c.rec[(size_t)w * c.Bpad + env] = v; };
+    for (int w = 0; w < c.SW; ++w) put(c.off_state + w, S[w]);
+    for (int w = 0; w < c.W - c.off_extra; ++w) put(c.off_extra + w, X[w]);
+    for (int w = 0; w < c.MW; ++w) { put(c.off_lastg + w, 0xFFFFFFFFu); put(c.off_lastcx + w, 0xFFFFFFFFu); }
+    const long long d = (long long)c.depth_slope * (long long)c.difficulty;
+    put(HD_DEPTH, (uint32_t)(d < (long long)c.max_depth ? d : (long long)c.max_depth));
+    put(HD_FLAGS, (ok ? FL_SUCCESS : 0u) | (err << FL_ERR_SHIFT));
     put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
     put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
     put(HD_TICK, 0);

@@ -102,3 +102,81 @@ def test_ragged_batch_sizes():
     for B in (1, 31, 33, 65, 100):
         run_parity("C3_clifford8_full", B=B, T=6, seed=B)
         run_parity("C1_perm_grid3", B=B, T=6, seed=B)
+
+
+@pytest.mark.parametrize("name,difficulty", [("C1_perm_grid3", 7), ("C2_lf8_line", 40), ("C3_clifford8_full", 256), ("C5_perm27_heavyhex", 100),
+                                              ("clifford5_allgates", 33), ("lf40_line", 64), ("C4_pauli10_line", 48), ("pauli6_line", 80),
+                                              ("pauli3_line", 20), ("C4_pauli10_line", 0)])
+def test_reset_parity(name, difficulty):
+    """Env::reset with the engine's Philox stream injected into the oracle: states, depth, success, observation."""
+    from qiskit_gym_b200 import BatchedEnv
+
+    kind, n, gateset, kw = H.config_table()[name]
+    B, seed, first = 300, 0xC0FFEE + difficulty, 1000
+    pk = dict(kw)
+    if kind != H.PAULI:
+        pk["add_inverts"] = False
+    env = BatchedEnv(kind, n, gateset, B, difficulty=difficulty, add_perms=False, **pk)
+    env.reset(seed=seed, first_env_id=first)
+    obs = env.observe().reshape(B, -1).cpu().numpy().astype(np.uint8)
+    reward, done, success, depth = [t.cpu().numpy() for t in env.status()]
+    ref = orc.OracleEnv(kind, n, gateset, difficulty=difficulty, add_perms=False, **pk)
+    assert int(env.errors().max().item()) == 0
+    for b in range(0, B, 3):
+        ref.reset(seed=seed, env_id=first + b)
+        assert np.array_equal(env.get_state(b), ref.raw_state()), f"{name}: reset state differs for env {b}"
+        d = np.zeros(obs.shape[1], dtype=np.uint8)
+        d[ref.observe()] = 1
+        assert np.array_equal(obs[b], d), f"{name}: reset observation differs for env {b}"
+        assert int(depth[b]) == ref.depth() and bool(success[b]) == ref.success() and bool(done[b]) == ref.is_final()
+        assert float(reward[b]) == ref.reward()
+    # a reset batch must step exactly like the oracle afterwards (metrics / DAG order were re-initialised)
+    rng = np.random.Generator(np.random.PCG64(1))
+    acts = H.random_actions(rng, 10, B, len(gateset))
+    refs = []
+    for b in range(0, B, 25):
+        r = orc.OracleEnv(kind, n, gateset, difficulty=difficulty, add_perms=False, **pk)
+        r.reset(seed=seed, env_id=first + b)
+        refs.append((b, r))
+    for t in range(10):
+        env.step(torch.from_numpy(acts[t]).to(env.device))
+        rw = env.reward.cpu().numpy()
+        for b, r in refs:
+            r.step(int(acts[t, b]))
+            assert pyref_bits(rw[b]) == pyref_bits(r.reward())
+    for b, r in refs:
+        assert np.array_equal(env.get_state(b), r.raw_state()) and env.solution(b) == r.solution()
+
+
+def pyref_bits(x):
+    import struct
+    return struct.unpack("<I", struct.pack("<f", float(x)))[0]
+
+
+def test_single_env_classes_match_notebook():
+    """The drop-in raw-env classes (batch of one) reproduce the reference notebook's LinearFunction walk-through."""
+    import json
+    import os
+    from qiskit_gym_b200 import LinearFunctionEnv, PermutationEnv
+
+    nb = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_kats.json")))
+    gs = [(g, tuple(q)) for g, q in nb["lf3_gateset"]]
+    env = LinearFunctionEnv(3, 1, gs, 2, 128, add_inverts=False)
+    assert env.num_actions() == nb["lf3_action_space"] and env.obs_shape() == nb["lf3_obs_space"]
+    assert env.is_final() and env.reward() == 1.0 and env.observe() == [0, 4, 8]      # constructor state: identity, success
+    for key in ("lf3_sequence_a", "lf3_sequence_b"):
+        seq = nb[key]
+        env.set_state(np.array(seq["start"]).reshape(-1).tolist())
+        for a, st, fin in zip(seq["actions"], seq["states"], seq["is_final"]):
+            env.step(a)
+            d = np.zeros(9, dtype=int); d[env.observe()] = 1
+            assert d.reshape(3, 3).tolist() == st and env.is_final() == fin
+        assert env.solution() == seq["actions"] and env.masks() == [False] * 8
+    obs_perms, act_perms = env.twists()
+    assert len(obs_perms) == 2 and len(act_perms[0]) == 8
+    env.difficulty = 5
+    assert env.difficulty == 5
+    env.reset(seed=3)
+    assert not env.is_final() or env.success()
+    p = PermutationEnv(9, 1, [(g, tuple(q)) for g, q in nb["perm_grid3_gateset"]], 2, 128)
+    assert p.obs_shape() == [9, 9] and p.num_actions() == 12 and len(p.twists()[0]) == 8
