@@ -6,9 +6,10 @@
 
 A "step" is one episode pass over the batch: every one of the B environments per GPU (default 65 536,
 BASELINE.json configs[2]: CliffordGym 8q all-to-all {H,S,CX}) is restored to its synthetic target and stepped
-T = max_depth = 128 times with a resident int32[T][B] action stream, i.e. T fused launches.  `value` is
-env-steps/sec over all GPUs with inputs resident in HBM; `e2e` is the same episode driven through the C-ABI
-call with HOST buffers (actions H2D, reward/done/success D2H every env-step, stream synchronised).
+T = max_depth = 128 times from a resident int32[T][B] action stream; every env-step materialises its dense float
+observation, mask, reward, done and success in HBM.  `value` plays the stream with one qg_replay launch per episode
+(`per_step_launch` reports the same episode as T single-step launches); `e2e` is the episode through the host-buffer
+C-ABI call qg_replay_host (actions H2D, reward/done/success D2H inside the timed region).
 """
 from __future__ import annotations
 
@@ -29,6 +30,9 @@ import numpy as np
 # algorithmic bytes per env-step (fp32 obs, u8 mask, i32 action, f32 reward, u8 done,
 # packed state + metrics read and written once).
 ALGO_BYTES = {"C1_perm_grid3": 449, "C2_lf8_line": 375, "C3_clifford8_full": 1249, "C4_pauli10_line": 2377, "C5_perm27_heavyhex": 3225}
+# dram__bytes_read.sum + dram__bytes_write.sum of one replay launch, from the committed ncu --set full capture (profiles/), keyed by
+# (config, envs per GPU, env-steps per launch); None where no capture exists.
+TRAFFIC_BYTES_PER_LAUNCH = {}
 METRIC = "batched env-steps/sec (CliffordGym 8q all-to-all {H,S,CX})"
 UNIT = "env-steps/s"
 
@@ -46,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="envs in the CPU baseline sample (0 = calibrate to ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-step", action="store_true", help="skip the one-launch-per-env-step leg (profiling runs)")
     return ap.parse_args()
 
 
@@ -210,92 +215,142 @@ def run_ours(args):
     coins = None
     if args.add_inverts and kind != W.PAULI:
         coins = torch.from_numpy(rng.integers(0, 2, size=(T, B)).astype(np.uint8)).to(dev)
-    # rotating observation / mask buffers: > 2x L2 in total
+    # rotating observation / mask ring: > 2x L2 in total, so every launch writes slabs that cannot stay resident
     obs_bytes = B * obs_size * 4
     nbuf = max(2, int(np.ceil(2 * 126e6 / max(obs_bytes, 1))) + 1)
     nbuf = min(nbuf, 64)
-    obs_bufs = [torch.empty((B, obs_size), dtype=torch.float32, device=dev) for _ in range(nbuf)]
-    mask_bufs = [torch.empty((B, A), dtype=torch.bool, device=dev) for _ in range(nbuf)]
+    obs_ring = torch.empty((nbuf, B, obs_size), dtype=torch.float32, device=dev)
+    mask_ring = torch.empty((nbuf, B, A), dtype=torch.bool, device=dev)
+    rew_tb = torch.empty((T, B), dtype=torch.float32, device=dev)
+    done_tb = torch.empty((T, B), dtype=torch.bool, device=dev)
+    succ_tb = torch.empty((T, B), dtype=torch.bool, device=dev)
 
-    def episode():
+    def episode_replay():
+        # one launch plays the whole resident action stream (qg_replay); state stays in the SMs between steps
+        env.restore()
+        env.replay(actions, coins=coins, obs=obs_ring, mask=mask_ring, reward=rew_tb, done=done_tb, success=succ_tb)
+
+    def episode_steps():
+        # policy-in-the-loop granularity: one fused launch per env-step (qg_step)
         env.restore()
         for t in range(T):
-            env.step(actions[t], coins=None if coins is None else coins[t], obs=obs_bufs[t % nbuf], mask=mask_bufs[t % nbuf])
+            env.step(actions[t], coins=None if coins is None else coins[t], obs=obs_ring[t % nbuf], mask=mask_ring[t % nbuf])
 
-    # capture one episode (restore + T fused launches) in a CUDA graph: the inner loop is launch-bound from Python
     stream = torch.cuda.Stream(device=dev)
+    sampler = ClockSampler(local)
+
+    def capture(fn):
+        with torch.cuda.stream(stream):
+            fn()
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                fn()
+            stream.synchronize()
+        return g
+
+    def timed(graph, sample_clocks=False):
+        """W warm-ups, then K replays of the captured episode, CUDA events on the launching stream."""
+        with torch.cuda.stream(stream):
+            for _ in range(max(Wm, 3)):
+                graph.replay()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if sample_clocks and rank == 0:
+                sampler.start()
+                time.sleep(0.25)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.time()
+            ev0.record(stream)
+            for _ in range(K):
+                graph.replay()
+            ev1.record(stream)
+            stream.synchronize()
+            w1 = time.time()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t_ms = ev0.elapsed_time(ev1)
+        clk = sampler.stop(w0, w1) if (sample_clocks and rank == 0) else None
+        if world > 1:
+            tms = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            t_ms = float(tms.item())
+        return t_ms, clk
+
+    g_replay = capture(episode_replay)
+    g_steps = None if args.no_per_step else capture(episode_steps)
+    # bring the GPU out of its idle power state before anything is timed (the first launches after process start-up
+    # otherwise run at idle clocks): about one second of the replay graph
     with torch.cuda.stream(stream):
-        episode()
-        stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            episode()
-        for _ in range(Wm):
-            graph.replay()
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-            time.sleep(0.25)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall0 = time.time()
-        ev0.record(stream)
-        for _ in range(K):
-            graph.replay()
-        ev1.record(stream)
-        stream.synchronize()
-        t_wall1 = time.time()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+        t_end = time.time() + 1.0
+        while time.time() < t_end:
+            for _ in range(20):
+                g_replay.replay()
+            stream.synchronize()
+    ms_steps = timed(g_steps)[0] if g_steps is not None else None
+    ms, clocks = timed(g_replay, sample_clocks=True)
     total_env_steps = world * B * T * K
     value = total_env_steps / (ms * 1e-3)
     errs = int(env.errors().max().item())
 
-    # ---- e2e: the same episode through the host-buffer C-ABI call (qg_step_host) -------------------------
+    # ---- e2e: the same episode through the host-buffer C-ABI calls ---------------------------------------
     e2e = None
     if not args.no_e2e:
         pin_a = torch.from_numpy(actions_h).pin_memory()
         a_np = pin_a.numpy()
-        rew = torch.empty(B, dtype=torch.float32).pin_memory(); don = torch.empty(B, dtype=torch.uint8).pin_memory(); suc = torch.empty(B, dtype=torch.uint8).pin_memory()
+        pin_c = None if coins is None else coins.cpu().pin_memory()
+        c_np = None if pin_c is None else pin_c.numpy()
+        rew = torch.empty((T, B), dtype=torch.float32).pin_memory(); don = torch.empty((T, B), dtype=torch.uint8).pin_memory(); suc = torch.empty((T, B), dtype=torch.uint8).pin_memory()
         rew_np, don_np, suc_np = rew.numpy(), don.numpy(), suc.numpy()
-        Ke = max(1, min(K, 5))
-        with torch.cuda.stream(stream):
-            def episode_host():
-                env.restore()
-                acc = 0.0
-                for t in range(T):
-                    env.step_host(a_np[t], rew_np, don_np, suc_np, obs=obs_bufs[t % nbuf], mask=mask_bufs[t % nbuf])
-                    acc += float(rew_np[0])
-                return acc
-            episode_host()
-            stream.synchronize()
+        Ke = max(1, min(K, 10))
+
+        def host_timed(fn, reps):
+            with torch.cuda.stream(stream):
+                fn()
+                stream.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(reps):
+                    fn()
+                e1.record(stream)
+                stream.synchronize()
+                t_ms = e0.elapsed_time(e1)
             if world > 1:
-                dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(Ke):
-                episode_host()
-            e1.record(stream)
-            stream.synchronize()
-            ems = e0.elapsed_time(e1)
-        if world > 1:
-            t2 = torch.tensor([ems], dtype=torch.float64, device=dev)
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-            ems = float(t2.item())
+                t2 = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+                t_ms = float(t2.item())
+            return t_ms
+
+        def episode_host():
+            # whole episode in one call: actions H2D, chunked fused launches, reward/done/success D2H, pipelined (qg_replay_host)
+            env.restore()
+            env.replay_host(a_np, rew_np, don_np, suc_np, coins=c_np, obs=obs_ring, mask=mask_ring)
+            return float(rew_np[T - 1, 0])
+
+        def episode_host_per_step():
+            # a host-side collector: one synchronous call per env-step (qg_step_host)
+            env.restore()
+            acc = 0.0
+            for t in range(T):
+                env.step_host(a_np[t], rew_np[0], don_np[0], suc_np[0], coins=None if c_np is None else c_np[t], obs=obs_ring[t % nbuf], mask=mask_ring[t % nbuf])
+                acc += float(rew_np[0, 0])
+            return acc
+
+        ems = host_timed(episode_host, Ke)
+        Ks = max(1, min(K, 3))
+        ems_ps = host_timed(episode_host_per_step, Ks)
         e2e = {"value": world * B * T * Ke / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": T * B * 4, "d2h_bytes_per_step": T * B * 6,
-               "note": "per env-step: int32 actions pinned H2D, fused step (obs+mask stay on device for the policy), f32 reward + u8 done + u8 success D2H, stream sync",
-               "steps": Ke}
+               "h2d_bytes_per_step": T * B * (4 + (1 if c_np is not None else 0)), "d2h_bytes_per_step": T * B * 6,
+               "note": "qg_replay_host: int32 actions [T][B] pinned H2D, chunked fused launches (obs+mask stay on device for the policy), "
+                       "f32 reward + u8 done + u8 success [T][B] D2H, copies pipelined with compute, call returns after the last byte arrived",
+               "steps": Ke,
+               "per_step_sync": {"value": world * B * T * Ks / (ems_ps * 1e-3), "unit": UNIT, "steps": Ks,
+                                 "note": "qg_step_host: one synchronous H2D + launch + D2H round trip per env-step (host-side collector)"}}
 
     if rank != 0:
         if world > 1:
@@ -308,13 +363,23 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     algo = ALGO_BYTES.get(args.config)
-    launch_us = ms * 1e3 / (T * K)
+    launch_us = ms * 1e3 / K                       # one replay launch (T env-steps for every env) + the 6 MB restore copy
+    step_launch_us = ms_steps * 1e3 / (T * K) if ms_steps else None
     roofline = None
+    per_step = None
     if algo:
-        achieved = algo * B / (launch_us * 1e-6) / 1e9
+        achieved = algo * B * T / (launch_us * 1e-6) / 1e9
+        traffic = TRAFFIC_BYTES_PER_LAUNCH.get((args.config, B, T))
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                    "kernel": "qg::k_step<CLIFFORD,64,STEP>", "algorithmic_bytes_per_env_step": algo, "avg_launch_us": launch_us}
+                    "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "kernel": f"qg::k_step<{args.config.split('_')[1]},STEP> nsteps={T} (qg_replay)", "algorithmic_bytes_per_env_step": algo,
+                    "algorithmic_bytes_per_launch": algo * B * T, "avg_launch_us": launch_us,
+                    "note": "algorithmic bytes count the state read+written every env-step (SURVEY 8d); the replay launch keeps it in the SM, "
+                            "so its actual traffic per env-step is lower by 2*(S_state+S_metrics)"}
+        ach1 = algo * B / (step_launch_us * 1e-6) / 1e9 if ms_steps else None
+        per_step = None if not ms_steps else {"value": world * B * T * K / (ms_steps * 1e-3), "unit": UNIT, "avg_launch_us": step_launch_us, "launches": T * K,
+                    "roofline_achieved_gbs": ach1, "roofline_frac": ach1 / peak,
+                    "note": "one fused launch per env-step (qg_step, policy-in-the-loop granularity), programmatic dependent launch, CUDA graph"}
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -328,7 +393,7 @@ def run_ours(args):
         "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (GF(2)) + f32 reward/obs", "data": "synthetic",
         "config": config_json(args, world, {"obs_buffers": nbuf, "cuda_graph": True}),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": T * K, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "per_step_launch": per_step, "cpu_baseline": cpu_baseline,
         "engine_error_flags": errs,
     }
     print(json.dumps(line), flush=True)

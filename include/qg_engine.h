@@ -152,6 +152,24 @@ QG_API int qg_restore(qg_engine* e, qg_stream stream);
 QG_API int qg_step(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev,
                    float* obs_dev, uint8_t* mask_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
                    qg_stream stream);
+/* `num_steps` consecutive fused steps in ONE launch from a resident action stream: the records are read once, stay
+ * in the SM while the steps are played, and are written back once; every step still materialises its observation,
+ * mask, reward, done and success exactly as num_steps calls of qg_step would (replaying a solution, evaluating a
+ * fixed action stream, the env-throughput benchmark).
+ *  actions_dev  int32[num_steps][B];  coins_dev uint8[num_steps][B] or NULL;  perm_raw_dev uint32[num_steps][B] or NULL
+ *  obs_dev      float[ring][B][obs_size] or NULL, mask_dev uint8[ring][B][num_actions] or NULL: step t writes slot t % ring
+ *  reward_dev   float[num_steps][B] or NULL;  done_dev / success_dev uint8[num_steps][B] or NULL */
+QG_API int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const uint8_t* coins_dev,
+                     const uint32_t* perm_raw_dev, float* obs_dev, uint8_t* mask_dev, int32_t ring,
+                     float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
+/* qg_replay with HOST buffers (pinned recommended): actions_host int32[num_steps][B] (coins_host uint8[num_steps][B] or
+ * NULL) go up, reward_host float[num_steps][B] / done_host / success_host uint8[num_steps][B] (each may be NULL) come back;
+ * observations / masks stay in the device ring for the policy.  Chunks of steps are pipelined over a copy-in stream, the
+ * caller's stream (one fused launch per chunk) and a copy-out stream; the call returns when everything has arrived.
+ * Allocates its staging buffers on first use. */
+QG_API int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host, const uint8_t* coins_host,
+                          float* obs_dev, uint8_t* mask_dev, int32_t ring,
+                          float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream);
 /* Same step with HOST buffers (pinned or pageable): copies actions (and coins) in, runs the step
  * writing obs/mask to the given DEVICE tensors (may be NULL), copies reward/done/success out and
  * synchronises.  This is the end-to-end call a host-side collector makes. */

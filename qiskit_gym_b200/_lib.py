@@ -21,7 +21,7 @@ SYMBOLS = [
     "qg_config_obs_shape", "qg_config_state_len", "qg_twists_create", "qg_twists_destroy", "qg_twists_count",
     "qg_twists_obs_len", "qg_twists_act_len", "qg_twists_copy", "qg_workspace_bytes", "qg_create", "qg_destroy",
     "qg_batch", "qg_num_actions", "qg_obs_size", "qg_obs_shape", "qg_set_difficulty", "qg_get_difficulty",
-    "qg_set_state", "qg_reset", "qg_snapshot", "qg_restore", "qg_step", "qg_step_host", "qg_observe", "qg_masks", "qg_read_status",
+    "qg_set_state", "qg_reset", "qg_snapshot", "qg_restore", "qg_step", "qg_replay", "qg_replay_host", "qg_step_host", "qg_observe", "qg_masks", "qg_read_status",
     "qg_read_metrics", "qg_read_errors", "qg_get_state_host", "qg_solution_host", "qg_search_begin",
     "qg_search_step", "qg_search_best", "qg_read_returns",
 ]
@@ -85,6 +85,8 @@ def lib():
     L.qg_snapshot.argtypes = [vp, vp]
     L.qg_restore.argtypes = [vp, vp]
     L.qg_step.argtypes = [vp] + [vp] * 8 + [vp]
+    L.qg_replay.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.qg_replay_host.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     L.qg_step_host.argtypes = [vp] + [vp] * 7 + [vp]
     L.qg_observe.argtypes = [vp, vp, vp, vp]
     L.qg_masks.argtypes = [vp, vp, vp]

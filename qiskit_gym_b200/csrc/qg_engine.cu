@@ -1,6 +1,7 @@
 // qg_engine.cu — implementation of the C ABI declared in include/qg_engine.h.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -34,6 +35,14 @@ struct qg_engine {
     size_t smem_bytes = 0; int sm_warp_words = 0, sm_scr = 0, sm_obs = 0;
     uint64_t magic_obs = 0, magic_A = 0; uint32_t magic_vpe = 0, magic_a4 = 0;
     int nperms = 0;
+    int pdl_mode = 2;                // QG_PDL=0|1|2 in the environment: programmatic dependent launch variants (see StepArgs)
+    int stagger_ns = 0, num_sms = 148;
+    // qg_replay_host pipeline (allocated on first use): two chunk buffers, copy-in / copy-out streams
+    int rp_chunk = 0;
+    int32_t* rp_actions[2] = {nullptr, nullptr}; uint8_t* rp_coins[2] = {nullptr, nullptr};
+    float* rp_reward[2] = {nullptr, nullptr}; uint8_t* rp_done[2] = {nullptr, nullptr}; uint8_t* rp_success[2] = {nullptr, nullptr};
+    cudaStream_t rp_in = nullptr, rp_out = nullptr;
+    cudaEvent_t rp_ev_in[2] = {nullptr, nullptr}, rp_ev_run[2] = {nullptr, nullptr}, rp_ev_out[2] = {nullptr, nullptr}, rp_ev_start = nullptr;
 };
 
 namespace {
@@ -98,8 +107,14 @@ template <int KIND, int MODE>
 int launch_step_k(qg_engine* e, const StepArgs& a, cudaStream_t st) {
     const int64_t tiles = (e->B + 31) / 32;
     const unsigned grid = (unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta);
-    k_step<KIND, MODE><<<grid, kWarpsPerCta * 32, e->smem_bytes, st>>>(e->dc, a);
-    CUDA_OK(cudaGetLastError());
+    // programmatic dependent launch: the grid may start while its predecessor in the stream drains; the kernel
+    // waits (griddepcontrol.wait) before it touches the records
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(kWarpsPerCta * 32); lc.dynamicSmemBytes = e->smem_bytes; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = a.pdl_mode ? 1 : 0;
+    CUDA_OK(cudaLaunchKernelEx(&lc, k_step<KIND, MODE>, e->dc, a));
     return QG_OK;
 }
 template <int MODE>
@@ -108,6 +123,10 @@ int launch_step(qg_engine* e, StepArgs a, cudaStream_t st) {
     int cur = -1;
     CUDA_OK(cudaGetDevice(&cur));
     if (cur != e->device) CUDA_OK(cudaSetDevice(e->device));
+    if (a.nsteps <= 0) a.nsteps = 1;
+    if (a.ring <= 0) a.ring = 1;
+    a.pdl_mode = e->pdl_mode; a.num_sms = e->num_sms;
+    a.stagger_ns = (MODE == MODE_STEP && a.nsteps >= 8) ? e->stagger_ns : 0;
     a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
@@ -233,6 +252,13 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     e->cfg = *cfg; e->gates.assign(cfg->gateset, cfg->gateset + cfg->num_gates); e->cfg.gateset = e->gates.data();
     e->L = L; e->device = device; e->B = batch; e->Bpad = align_up(std::max<int64_t>(batch, 1), 32);
     e->nperms = (int)tw.act_perms.size();
+    if (const char* v = std::getenv("QG_PDL")) e->pdl_mode = std::atoi(v);
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
+    {   // replay stagger: the time one warp's observation + mask slab takes at the SM's share of the write bandwidth
+        const double slab = 32.0 * (4.0 * L.obs_size + L.A + 6.0), sm_bw = 6.6e12 / e->num_sms;
+        e->stagger_ns = (int)(slab / sm_bw * 1e9);
+        if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
+    }
     std::vector<uint32_t> pg;
     if (cfg->env_kind == QG_ENV_PAULI_NETWORK) pauli_gen_tables(cfg, pg);
     const WsPlan p = plan_ws(L, batch, e->nperms, (int64_t)pg.size());
@@ -307,6 +333,19 @@ void qg_destroy(qg_engine* e) {
     if (!e) return;
     if (e->h_staged) cudaFreeHost(e->h_staged);
     if (e->h_best) cudaFreeHost(e->h_best);
+    for (int b = 0; b < 2; ++b) {
+        if (e->rp_actions[b]) cudaFree(e->rp_actions[b]);
+        if (e->rp_coins[b]) cudaFree(e->rp_coins[b]);
+        if (e->rp_reward[b]) cudaFree(e->rp_reward[b]);
+        if (e->rp_done[b]) cudaFree(e->rp_done[b]);
+        if (e->rp_success[b]) cudaFree(e->rp_success[b]);
+        if (e->rp_ev_in[b]) cudaEventDestroy(e->rp_ev_in[b]);
+        if (e->rp_ev_run[b]) cudaEventDestroy(e->rp_ev_run[b]);
+        if (e->rp_ev_out[b]) cudaEventDestroy(e->rp_ev_out[b]);
+    }
+    if (e->rp_ev_start) cudaEventDestroy(e->rp_ev_start);
+    if (e->rp_in) cudaStreamDestroy(e->rp_in);
+    if (e->rp_out) cudaStreamDestroy(e->rp_out);
     if (e->owns_ws && e->ws) cudaFree(e->ws);
     delete e;
 }
@@ -388,6 +427,72 @@ int qg_step(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, 
     StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs = obs_dev; a.mask = mask_dev;
     a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
     return launch_step<MODE_STEP>(e, a, (cudaStream_t)stream);
+}
+
+int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev,
+              float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !actions_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (num_steps < 0 || ring < 1) { set_error("qg_replay: num_steps must be >= 0 and ring >= 1"); return QG_ERR_INVALID; }
+    if (num_steps == 0) return QG_OK;
+    StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs = obs_dev; a.mask = mask_dev;
+    a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    a.nsteps = num_steps; a.ring = ring; a.in_stride = e->B; a.out_stride = e->B;
+    return launch_step<MODE_STEP>(e, a, (cudaStream_t)stream);
+}
+
+// Episode replay with HOST buffers, pipelined in chunks of steps over three streams: the copy-in stream uploads the
+// actions of chunk c+1 while the caller's stream replays chunk c (one fused launch per chunk) and the copy-out
+// stream downloads the rewards / flags of chunk c-1.
+int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
+                   int32_t ring, float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream) {
+    if (!e || !actions_host) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (num_steps < 0 || ring < 1) { set_error("qg_replay_host: num_steps must be >= 0 and ring >= 1"); return QG_ERR_INVALID; }
+    if (num_steps == 0 || e->B == 0) return QG_OK;
+    CUDA_OK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)e->B;
+    if (!e->rp_in) {
+        // chunk: about 4 MB of actions per upload, at least 1 and at most 32 steps
+        e->rp_chunk = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(4 << 20) / std::max<int64_t>((int64_t)B * 4, 1)));
+        CUDA_OK(cudaStreamCreateWithFlags(&e->rp_in, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&e->rp_out, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&e->rp_ev_start, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            const size_t n = (size_t)e->rp_chunk * B;
+            CUDA_OK(cudaMalloc(&e->rp_actions[b], n * 4)); CUDA_OK(cudaMalloc(&e->rp_coins[b], n));
+            CUDA_OK(cudaMalloc(&e->rp_reward[b], n * 4)); CUDA_OK(cudaMalloc(&e->rp_done[b], n)); CUDA_OK(cudaMalloc(&e->rp_success[b], n));
+            CUDA_OK(cudaEventCreateWithFlags(&e->rp_ev_in[b], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&e->rp_ev_run[b], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&e->rp_ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    const int chunk = e->rp_chunk, nchunks = (num_steps + chunk - 1) / chunk;
+    CUDA_OK(cudaEventRecord(e->rp_ev_start, st));
+    CUDA_OK(cudaStreamWaitEvent(e->rp_in, e->rp_ev_start, 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1, t0 = c * chunk, ns = std::min(chunk, num_steps - t0);
+        const size_t n = (size_t)ns * B, o = (size_t)t0 * B;
+        if (c >= 2) CUDA_OK(cudaStreamWaitEvent(e->rp_in, e->rp_ev_run[b], 0));          // chunk c-2 has consumed this buffer
+        CUDA_OK(cudaMemcpyAsync(e->rp_actions[b], actions_host + o, n * 4, cudaMemcpyHostToDevice, e->rp_in));
+        if (coins_host) CUDA_OK(cudaMemcpyAsync(e->rp_coins[b], coins_host + o, n, cudaMemcpyHostToDevice, e->rp_in));
+        CUDA_OK(cudaEventRecord(e->rp_ev_in[b], e->rp_in));
+        CUDA_OK(cudaStreamWaitEvent(st, e->rp_ev_in[b], 0));
+        if (c >= 2) CUDA_OK(cudaStreamWaitEvent(st, e->rp_ev_out[b], 0));                // chunk c-2's results have left this buffer
+        StepArgs a{}; a.actions = e->rp_actions[b]; a.coins = coins_host ? e->rp_coins[b] : nullptr; a.obs = obs_dev; a.mask = mask_dev;
+        a.reward = reward_host ? e->rp_reward[b] : nullptr; a.done = done_host ? e->rp_done[b] : nullptr; a.success = success_host ? e->rp_success[b] : nullptr;
+        a.nsteps = ns; a.ring = ring; a.slot0 = t0 % ring; a.in_stride = e->B; a.out_stride = e->B;
+        const int rc = launch_step<MODE_STEP>(e, a, st);
+        if (rc != QG_OK) return rc;
+        CUDA_OK(cudaEventRecord(e->rp_ev_run[b], st));
+        CUDA_OK(cudaStreamWaitEvent(e->rp_out, e->rp_ev_run[b], 0));
+        if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host + o, e->rp_reward[b], n * 4, cudaMemcpyDeviceToHost, e->rp_out));
+        if (done_host) CUDA_OK(cudaMemcpyAsync(done_host + o, e->rp_done[b], n, cudaMemcpyDeviceToHost, e->rp_out));
+        if (success_host) CUDA_OK(cudaMemcpyAsync(success_host + o, e->rp_success[b], n, cudaMemcpyDeviceToHost, e->rp_out));
+        CUDA_OK(cudaEventRecord(e->rp_ev_out[b], e->rp_out));
+    }
+    for (int b = 0; b < std::min(2, nchunks); ++b) CUDA_OK(cudaStreamWaitEvent(st, e->rp_ev_out[b], 0));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return QG_OK;
 }
 
 int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,

@@ -83,7 +83,9 @@ int make_layout(const qg_config* cfg, Layout& L) {
         }
     }
     L.obs_size = L.obs_rows * L.obs_cols;
-    L.OW = (L.kind == QG_ENV_PAULI_NETWORK) ? (L.obs_size + 31) / 32 + 1 : 0;
+    // observation bit stream built next to the state: always for PauliNetwork; for Permutation (one-hot rows) while it
+    // fits comfortably in shared memory (n <= 64), else the expander tests the packed bytes directly
+    L.OW = (L.kind == QG_ENV_PAULI_NETWORK || (L.kind == QG_ENV_PERMUTATION && n <= 64)) ? (L.obs_size + 31) / 32 + 1 : 0;
     L.off_lastg = HD_WORDS; L.off_lastcx = L.off_lastg + L.MW; L.off_state = L.off_lastcx + L.MW; L.off_extra = L.off_state + L.SW;
     L.W = L.off_extra + L.XW;
     L.PW = L.SW + L.XW + 1;

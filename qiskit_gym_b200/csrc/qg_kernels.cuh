@@ -24,6 +24,14 @@ struct StepArgs {
     float* reward; uint8_t* done; uint8_t* success;   // [B] or null
     int32_t* chosen;             // [B] or null    (MODE_SEARCH)
     int32_t* num_active;         // [1] or null    (MODE_SEARCH)
+    int32_t nsteps;              // steps played by this launch (MODE_STEP; 1 otherwise)
+    int32_t ring;                // obs / mask hold `ring` step slots of [B][obs_size] / [B][A]; step t writes slot (slot0 + t) % ring
+    int32_t slot0;
+    int32_t pdl_mode;            // 0: plain launch; 1: dependents may launch right away; 2: only once this grid owns the records
+    int32_t stagger_ns, num_sms; // replay: warp k of an SM starts k * stagger_ns late so that the warps of an SM do not all
+                                 // alternate between the latency-bound step phase and the store-bound expansion in lock-step
+    int64_t in_stride;           // elements between consecutive steps of actions / coins / perm_raw
+    int64_t out_stride;          // elements between consecutive steps of reward / done / success
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
@@ -264,6 +272,8 @@ __device__ void pn_build_obs(const DevCfg& c, const Wd& S, const PauliRegs& p, c
 // Work decomposition: one WARP owns a tile of 32 consecutive environments (lane == environment in phase 1) and a
 // private shared-memory region [word][kStride]; there is no block-level barrier, so warps drift apart and the
 // latency-bound phase 1 of one warp overlaps the store-bound phase 2 of the others on the same SM.
+// The records are loaded once, then `nsteps` steps are played from a resident action stream (nsteps == 1 is the
+// policy-in-the-loop step; nsteps == T replays a whole episode without the state leaving the SM), then written back.
 constexpr int kStride = 33;          // odd word stride: bank = (word + lane) % 32 -> conflict free both for per-lane private
                                      // access with a warp-uniform word and for the expander's broadcast reads of one env
 constexpr int kWarpsPerCta = 2;
@@ -273,11 +283,115 @@ __device__ __forceinline__ void cp_async_4(uint32_t* smem_dst, const uint32_t* g
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// programmatic dependent launch: let the next grid of the stream start its prologue, and wait for the previous one
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+__device__ __forceinline__ float4 nibble_to_float4(uint32_t nib) {
+    float4 f;
+    f.x = (nib & 1u) ? 1.0f : 0.0f; f.y = (nib & 2u) ? 1.0f : 0.0f; f.z = (nib & 4u) ? 1.0f : 0.0f; f.w = (nib & 8u) ? 1.0f : 0.0f;
+    return f;
+}
+// 4 bits at bit offset `off` of environment e's observation bit stream (words at bits[w * kStride + e])
+__device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t e, uint32_t off) {
+    const uint32_t w = off >> 5, s = off & 31u;
+    const uint32_t lo = bits[w * kStride + e];
+    const uint32_t hi = (s > 28u) ? bits[(w + 1) * kStride + e] : 0u;
+    return __funnelshift_r(lo, hi, s);
+}
+
+// Phase 2a: bits -> floats.  The warp's slab out[0 .. cnt*obs_size) is contiguous in the [B][obs_size] tensor; lane l
+// stores the float4 number l, l+32, ... (512 contiguous bytes per warp instruction).  (e, off) of a lane's float4 is
+// tracked incrementally: advancing 32 float4s adds (q, r) with one conditional wrap, so the loop has no division.
+template <int MODE>
+__device__ __forceinline__ void expand_obs(const uint32_t* bits, float* out, uint32_t cnt, uint32_t obs, uint32_t en_bits, int lane,
+                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs) {
+    // 16-byte stores need an aligned slab: always true for the engine's own [B][obs] tensors; a ring slot of an odd-sized
+    // batch may start off the grid, then everything goes through the scalar tail loop
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (vec_ok && (obs & 3u) == 0) {
+        // a float4 never straddles two environments
+        const uint32_t VPE = obs >> 2, total = cnt * VPE;
+        uint32_t e = (VPE == 1) ? (uint32_t)lane : __umulhi((uint32_t)lane, magic_obs4), v = (uint32_t)lane - e * VPE;
+        const uint32_t q = 32u / VPE, r = 32u - q * VPE;
+#pragma unroll 4
+        for (uint32_t j = lane; j < total; j += 32) {
+            if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) {
+                const uint32_t nib = bits[(v >> 3) * kStride + e] >> ((v & 7u) << 2);
+                __stcs(reinterpret_cast<float4*>(out) + j, nibble_to_float4(nib));
+            }
+            e += q; v += r;
+            if (v >= VPE) { v -= VPE; ++e; }
+        }
+    } else {
+        const uint32_t total = cnt * obs, nvec = (vec_ok && obs >= 4u) ? (total >> 2) : 0u;
+        uint32_t e = fastdiv40((uint32_t)lane << 2, magic_obs), off = ((uint32_t)lane << 2) - e * obs;
+        const uint32_t q = 128u / obs, r = 128u - q * obs;
+        if (nvec) {
+#pragma unroll 2
+            for (uint32_t j = lane; j < nvec; j += 32) {
+                uint32_t nib = stream_nibble(bits, e, off);
+                const bool straddle = off + 4u > obs;                 // the float4 ends in environment e+1
+                if (straddle) { const uint32_t k = obs - off; nib = (nib & ((1u << k) - 1u)) | (bits[e + 1] << k); }
+                const bool on = (MODE != MODE_SEARCH) || (((en_bits >> e) & 1u) && (!straddle || ((en_bits >> (e + 1)) & 1u)));
+                if (on) __stcs(reinterpret_cast<float4*>(out) + j, nibble_to_float4(nib));
+                else {
+                    uint32_t ee = e, oo = off;
+                    for (int k = 0; k < 4; ++k) { if ((en_bits >> ee) & 1u) out[(j << 2) + k] = ((nib >> k) & 1u) ? 1.0f : 0.0f; if (++oo == obs) { oo = 0; ++ee; } }
+                }
+                e += q; off += r;
+                if (off >= obs) { off -= obs; ++e; }
+            }
+        }
+        // elements not covered by whole float4s (ragged last tile, or obs < 4)
+        for (uint32_t f = (nvec << 2) + lane; f < total; f += 32) {
+            const uint32_t ee = fastdiv40(f, magic_obs), oo = f - ee * obs;
+            if (MODE != MODE_SEARCH || ((en_bits >> ee) & 1u)) out[f] = ((bits[(oo >> 5) * kStride + ee] >> (oo & 31u)) & 1u) ? 1.0f : 0.0f;
+        }
+    }
+}
+
+// Phase 2b: masks() = [!success; A] per environment (clifford.rs:349-351) as a uint8 [B][A] slab, 16-byte stores.
+// G = bytes per granule that cannot straddle two environments (4 when A % 4 == 0, else 1).
+template <int MODE, int G>
+__device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t A, uint32_t mask_bits, uint32_t en_bits, int lane, uint64_t magic_A) {
+    const uint32_t total = cnt * A, nvec = (reinterpret_cast<uintptr_t>(out) & 15u) ? 0u : (total >> 4);   // whole 16-byte vectors of the (aligned) slab
+    const uint32_t P = A / G;                                     // granules per environment
+    const uint32_t g0 = ((uint32_t)lane << 4) / G;                // first granule of this lane's first vector
+    uint32_t e = fastdiv40(g0 * G, magic_A), off = g0 - e * P;
+    const uint32_t step = 512u / G, q = step / P, r = step - q * P;
+    for (uint32_t j = lane; j < nvec; j += 32) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        uint32_t ee = e, oo = off; bool all_on = true;
+#pragma unroll
+        for (int k = 0; k < 16 / G; ++k) {
+            const uint32_t bit = (mask_bits >> ee) & 1u;
+            if (MODE == MODE_SEARCH && !((en_bits >> ee) & 1u)) all_on = false;
+            if (G == 4) w[k] = bit ? 0x01010101u : 0u; else w[k >> 2] |= bit << ((k & 3) * 8);
+            if (++oo == P) { oo = 0; ++ee; }
+        }
+        if (MODE != MODE_SEARCH || all_on) __stcs(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]));
+        else {
+            uint32_t e2 = e, o2 = off;
+            for (int k = 0; k < 16 / G; ++k) {
+                if ((en_bits >> e2) & 1u) { for (int b = 0; b < G; ++b) out[(j << 4) + k * G + b] = (uint8_t)((mask_bits >> e2) & 1u); }
+                if (++o2 == P) { o2 = 0; ++e2; }
+            }
+        }
+        e += q; off += r;
+        if (off >= P) { off -= P; ++e; }
+    }
+    for (uint32_t b = (nvec << 4) + lane; b < total; b += 32) {   // ragged last tile
+        const uint32_t ee = fastdiv40(b, magic_A);
+        if (MODE != MODE_SEARCH || ((en_bits >> ee) & 1u)) out[b] = (uint8_t)((mask_bits >> ee) & 1u);
+    }
+}
 
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.pdl_mode == 1) pdl_launch_dependents();
     const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
     if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
     const int cnt = (int)min((int64_t)32, c.B - e0);
@@ -285,208 +399,198 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_step(const __grid_constan
     typedef SmWords<kStride> Wd;
     const int64_t env = e0 + lane;
     const bool live = lane < cnt;
-    bool success = false, enabled = false;
+    const Wd R{wbase + lane};
+    const Wd LG = R.at(c.off_lastg), LC = R.at(c.off_lastcx), S = R.at(c.off_state), X = R.at(c.off_extra);
+    const Wd SCR{wbase + a.sm_scr + lane}, O{wbase + a.sm_obs + lane};
+    const bool obs_from_O = (KIND == QG_ENV_PAULI_NETWORK) || (KIND == QG_ENV_PERMUTATION && c.OW > 0);
+    const uint32_t* const obs_bits = wbase + (obs_from_O ? a.sm_obs : c.off_state * kStride);
 
-    if (live) {
-        const Wd R{wbase + lane};
-        const Wd LG = R.at(c.off_lastg), LC = R.at(c.off_lastcx), S = R.at(c.off_state), X = R.at(c.off_extra);
-        const Wd SCR{wbase + a.sm_scr + lane}, O{wbase + a.sm_obs + lane};
-        for (int w = 0; w < c.W; ++w) cp_async_4(&R[w], c.rec + (size_t)w * c.Bpad + env);   // all W loads in flight at once
-        int action = -1;
-        if (MODE == MODE_STEP) action = a.actions[env];
-        cp_async_wait_all();
-
-        uint32_t depth = R[HD_DEPTH], flags = R[HD_FLAGS], tick = R[HD_TICK];
-        success = (flags & FL_SUCCESS) != 0;
-        enabled = true;
-        PauliRegs pr{};
-        if (KIND == QG_ENV_PAULI_NETWORK) { pr.plo = X[PX_PLO]; pr.phi = X[PX_PHI]; pr.alive = X[PX_ALIVE]; pr.ord0 = X[PX_ORD0]; pr.ord1 = X[PX_ORD1]; pr.misc = X[PX_MISC]; }
-
-        if (MODE == MODE_SEARCH) {
-            // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
-            enabled = !(depth == 0 || success);
-            if (enabled) {
-                const float* wt = a.weights + (size_t)env * c.A;
-                if (a.deterministic) {
-                    float best = wt[0]; action = 0;
-                    for (int k = 1; k < c.A; ++k) { const float v = wt[k]; if (v > best) { best = v; action = k; } }
-                } else {
-                    float total = 0.0f;
-                    for (int k = 0; k < c.A; ++k) total = __fadd_rn(total, wt[k]);
-                    const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_SAMPLE);
-                    if (!(total > 0.0f)) action = (int)__umulhi(raw, (uint32_t)c.A);
-                    else {
-                        const float target = __fmul_rn((float)(raw >> 8) * (1.0f / 16777216.0f), total);
-                        float cum = 0.0f; action = c.A - 1;
-                        for (int k = 0; k < c.A; ++k) { cum = __fadd_rn(cum, wt[k]); if (cum > target) { action = k; break; } }
-                    }
-                }
-            }
-            if (a.chosen) a.chosen[env] = enabled ? action : -1;
+    if (a.pdl_mode) pdl_wait();                      // the previous grid of the stream wrote the records
+    if (a.pdl_mode == 2) pdl_launch_dependents();
+    if (a.stagger_ns > 0) {
+        const long long wait_ns = (long long)(((int)blockIdx.x / a.num_sms) * kWarpsPerCta + warp) * a.stagger_ns;
+        long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 >= wait_ns) break;
+            __nanosleep(200);
         }
+    }
+    if (live) {
+        const uint32_t* src = c.rec + env;
+#pragma unroll 4
+        for (int w = 0; w < c.W; ++w, src += c.Bpad) cp_async_4(&R[w], src);       // all W loads in flight at once
+        cp_async_wait_all();
+    }
+    uint32_t depth = 0, flags = 0, tick = 0;
+    PauliRegs pr{};
+    if (live) {
+        depth = R[HD_DEPTH]; flags = R[HD_FLAGS]; tick = R[HD_TICK];
+        if (KIND == QG_ENV_PAULI_NETWORK) { pr.plo = X[PX_PLO]; pr.phi = X[PX_PHI]; pr.alive = X[PX_ALIVE]; pr.ord0 = X[PX_ORD0]; pr.ord1 = X[PX_ORD1]; pr.misc = X[PX_MISC]; }
+    }
+    bool dirty = false;                              // records changed: write them back at the end
+    int slot = a.slot0;                              // observation / mask ring slot of this step
 
-        if (MODE != MODE_OBSERVE && enabled) {
-            uint32_t err = 0;
-            float penalty = 0.0f;
-            int nh = 0;                                     // rotations harvested by this step (PauliNetwork)
-            int act = action;
-            if (act < 0) { err |= QG_FLAG_BAD_ACTION; act = 0x7FFFFFFF; }
-            if (KIND == QG_ENV_PAULI_NETWORK && c.nperms > 0 && act < c.A)
-                act = (int)c.aperms[(size_t)(pr.misc & 0xFFFFu) * c.A + act];       // pauli.rs:594-599
-            const bool valid = act < c.A;
-            uint32_t sol_len = flags >> FL_LEN_SHIFT;
-            auto push = [&](uint32_t v) {
-                if ((int)sol_len < c.sol_cap) { c.sol[(size_t)sol_len * c.Bpad + env] = v; ++sol_len; }
-                else err |= QG_FLAG_SOLUTION_OVERFLOW;
-            };
-            if (valid) {
-                const uint32_t g = __ldg(c.gates + act);
-                const int kind = (int)(g & 0xFFu), q0 = (int)((g >> 8) & 0xFFu), q1 = (int)((g >> 16) & 0xFFu);
-                Counts prev{R[HD_NCNOTS], R[HD_NGATES], R[HD_LAYERS] & 0xFFFFu, R[HD_LAYERS] >> 16};
-                Counts now = prev;
-                met_gate(LG, LC, c.n, kind, q0, q1, now, err);
-                penalty = weighted_delta(c, now, prev);
-                R[HD_NCNOTS] = now.nc; R[HD_NGATES] = now.ng; R[HD_LAYERS] = (now.nl & 0xFFFFu) | (now.nlc << 16);
-                if (KIND == QG_ENV_PAULI_NETWORK) pn_act(c, S, X, pr, kind, q0, q1, SCR, nh, err);
-                else apply_gate_state<KIND>(c, S, kind, q0, q1);
-            }
-            // solution log: Permutation only for valid actions (permutation.rs:210-216), LF/Clifford always
-            // (linear_function.rs:315-321, clifford.rs:334-340), PauliNetwork gate + harvested rotations (pauli.rs:612-627)
-            if (c.track) {
-                if (KIND == QG_ENV_PAULI_NETWORK) {
-                    if (valid) {
-                        push((uint32_t)act);
-                        if (nh > 0) {
-                            uint32_t ylo = 0, yhi = 0;      // #Y per rotation mod 4 (pauli.rs:125-133), after the whole act()
-                            for (int q = 0; q < c.n; ++q) { const uint32_t y = rot_bits(c, S, q) & rot_bits(c, S, c.n + q); const uint32_t cy = ylo & y; ylo ^= y; yhi ^= cy; }
-                            for (int k = 0; k < nh; ++k) {
-                                const uint32_t h = SCR[k], r = (h >> 1) & 0xFu;
-                                const uint32_t bp = ((pr.plo >> r) & 1u) | (((pr.phi >> r) & 1u) << 1);
-                                const uint32_t ys = ((ylo >> r) & 1u) | (((yhi >> r) & 1u) << 1);
-                                const uint32_t ph = (bp - ys) & 3u;
-                                push(0x80000000u | h | (ph == 2u ? 0u : 1u));
-                            }
+    for (int t = 0; t < a.nsteps; ++t) {
+        bool success = (flags & FL_SUCCESS) != 0, enabled = live;
+        if (live) {
+            int action = -1;
+            if (MODE == MODE_STEP) action = a.actions[(size_t)t * a.in_stride + env];
+            if (MODE == MODE_SEARCH) {
+                // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
+                enabled = !(depth == 0 || success);
+                if (enabled) {
+                    const float* wt = a.weights + (size_t)env * c.A;
+                    if (a.deterministic) {
+                        float best = wt[0]; action = 0;
+                        for (int k = 1; k < c.A; ++k) { const float v = wt[k]; if (v > best) { best = v; action = k; } }
+                    } else {
+                        float total = 0.0f;
+                        for (int k = 0; k < c.A; ++k) total = __fadd_rn(total, wt[k]);
+                        const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_SAMPLE);
+                        if (!(total > 0.0f)) action = (int)__umulhi(raw, (uint32_t)c.A);
+                        else {
+                            const float target = __fmul_rn((float)(raw >> 8) * (1.0f / 16777216.0f), total);
+                            float cum = 0.0f; action = c.A - 1;
+                            for (int k = 0; k < c.A; ++k) { cum = __fadd_rn(cum, wt[k]); if (cum > target) { action = k; break; } }
                         }
                     }
-                } else if (KIND != QG_ENV_PERMUTATION || valid) {
-                    push(((uint32_t)action & 0x7FFFFFFFu) | ((flags & FL_INVERTED) ? 0x80000000u : 0u));
                 }
+                if (a.chosen) a.chosen[env] = enabled ? action : -1;
             }
-            depth = depth > 0 ? depth - 1 : 0;              // saturating_sub
-            if (KIND != QG_ENV_PAULI_NETWORK && c.add_inverts) {
-                bool coin;
-                if (a.coins) coin = a.coins[env] != 0;
-                else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
-                if (coin) {
-                    if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; }
-                    else if (invert_matrix(c, S, SCR, SCR.at(c.SW))) flags ^= FL_INVERTED;
-                    else err |= QG_FLAG_SINGULAR;
-                }
-            }
-            success = (KIND == QG_ENV_PAULI_NETWORK) ? pn_solved(c, S, pr) : solved_state<KIND>(c, S);
-            float reward = __fsub_rn(success ? 1.0f : 0.0f, penalty);
-            if (KIND == QG_ENV_PAULI_NETWORK) reward = __fadd_rn(reward, __fmul_rn(c.plr, (float)nh));   // pauli.rs:634
-            flags = (flags & (FL_INVERTED | (0xFFu << FL_ERR_SHIFT))) | (success ? FL_SUCCESS : 0u) | (err << FL_ERR_SHIFT) | (sol_len << FL_LEN_SHIFT);
-            tick += 1;
-            R[HD_DEPTH] = depth; R[HD_FLAGS] = flags; R[HD_REWARD] = __float_as_uint(reward); R[HD_TICK] = tick;
-            if (MODE == MODE_SEARCH) c.ret[env] = __fadd_rn(c.ret[env], reward);
-            if (a.reward) a.reward[env] = reward;
-        }
-        if (MODE == MODE_OBSERVE && a.reward) a.reward[env] = __uint_as_float(R[HD_REWARD]);
-        if (enabled) {
-            if (a.done) a.done[env] = (depth == 0 || success) ? 1 : 0;
-            if (a.success) a.success[env] = success ? 1 : 0;
-        }
 
-        // observe(): build the observation bit stream (PauliNetwork picks its permutation here, pauli.rs:653-665)
-        if (KIND == QG_ENV_PAULI_NETWORK && enabled) {
-            int perm_idx = 0;
-            if (c.nperms > 0 && a.obs) {
-                const uint32_t raw = a.perm_raw ? a.perm_raw[env] : philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_PERM);
-                perm_idx = (int)__umulhi(raw, (uint32_t)c.nperms);
-                pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
+            if (MODE != MODE_OBSERVE && enabled) {
+                uint32_t err = 0;
+                float penalty = 0.0f;
+                int nh = 0;                                     // rotations harvested by this step (PauliNetwork)
+                int act = action;
+                if (act < 0) { err |= QG_FLAG_BAD_ACTION; act = 0x7FFFFFFF; }
+                if (KIND == QG_ENV_PAULI_NETWORK && c.nperms > 0 && act < c.A)
+                    act = (int)c.aperms[(size_t)(pr.misc & 0xFFFFu) * c.A + act];       // pauli.rs:594-599
+                const bool valid = act < c.A;
+                uint32_t sol_len = flags >> FL_LEN_SHIFT;
+                auto push = [&](uint32_t v) {
+                    if ((int)sol_len < c.sol_cap) { c.sol[(size_t)sol_len * c.Bpad + env] = v; ++sol_len; }
+                    else err |= QG_FLAG_SOLUTION_OVERFLOW;
+                };
+                if (valid) {
+                    const uint32_t g = __ldg(c.gates + act);
+                    const int kind = (int)(g & 0xFFu), q0 = (int)((g >> 8) & 0xFFu), q1 = (int)((g >> 16) & 0xFFu);
+                    Counts prev{R[HD_NCNOTS], R[HD_NGATES], R[HD_LAYERS] & 0xFFFFu, R[HD_LAYERS] >> 16};
+                    Counts now = prev;
+                    met_gate(LG, LC, c.n, kind, q0, q1, now, err);
+                    penalty = weighted_delta(c, now, prev);
+                    R[HD_NCNOTS] = now.nc; R[HD_NGATES] = now.ng; R[HD_LAYERS] = (now.nl & 0xFFFFu) | (now.nlc << 16);
+                    if (KIND == QG_ENV_PAULI_NETWORK) pn_act(c, S, X, pr, kind, q0, q1, SCR, nh, err);
+                    else apply_gate_state<KIND>(c, S, kind, q0, q1);
+                }
+                // solution log: Permutation only for valid actions (permutation.rs:210-216), LF/Clifford always
+                // (linear_function.rs:315-321, clifford.rs:334-340), PauliNetwork gate + harvested rotations (pauli.rs:612-627)
+                if (c.track) {
+                    if (KIND == QG_ENV_PAULI_NETWORK) {
+                        if (valid) {
+                            push((uint32_t)act);
+                            if (nh > 0) {
+                                uint32_t ylo = 0, yhi = 0;      // #Y per rotation mod 4 (pauli.rs:125-133), after the whole act()
+                                for (int q = 0; q < c.n; ++q) { const uint32_t y = rot_bits(c, S, q) & rot_bits(c, S, c.n + q); const uint32_t cy = ylo & y; ylo ^= y; yhi ^= cy; }
+                                for (int k = 0; k < nh; ++k) {
+                                    const uint32_t h = SCR[k], r = (h >> 1) & 0xFu;
+                                    const uint32_t bp = ((pr.plo >> r) & 1u) | (((pr.phi >> r) & 1u) << 1);
+                                    const uint32_t ys = ((ylo >> r) & 1u) | (((yhi >> r) & 1u) << 1);
+                                    const uint32_t ph = (bp - ys) & 3u;
+                                    push(0x80000000u | h | (ph == 2u ? 0u : 1u));
+                                }
+                            }
+                        }
+                    } else if (KIND != QG_ENV_PERMUTATION || valid) {
+                        push(((uint32_t)action & 0x7FFFFFFFu) | ((flags & FL_INVERTED) ? 0x80000000u : 0u));
+                    }
+                }
+                depth = depth > 0 ? depth - 1 : 0;              // saturating_sub
+                if (KIND != QG_ENV_PAULI_NETWORK && c.add_inverts) {
+                    bool coin;
+                    if (a.coins) coin = a.coins[(size_t)t * a.in_stride + env] != 0;
+                    else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
+                    if (coin) {
+                        if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; }
+                        else if (invert_matrix(c, S, SCR, SCR.at(c.SW))) flags ^= FL_INVERTED;
+                        else err |= QG_FLAG_SINGULAR;
+                    }
+                }
+                success = (KIND == QG_ENV_PAULI_NETWORK) ? pn_solved(c, S, pr) : solved_state<KIND>(c, S);
+                float reward = __fsub_rn(success ? 1.0f : 0.0f, penalty);
+                if (KIND == QG_ENV_PAULI_NETWORK) reward = __fadd_rn(reward, __fmul_rn(c.plr, (float)nh));   // pauli.rs:634
+                flags = (flags & (FL_INVERTED | (0xFFu << FL_ERR_SHIFT))) | (success ? FL_SUCCESS : 0u) | (err << FL_ERR_SHIFT) | (sol_len << FL_LEN_SHIFT);
+                tick += 1;
+                R[HD_REWARD] = __float_as_uint(reward);
+                dirty = true;
+                if (MODE == MODE_SEARCH) c.ret[env] = __fadd_rn(c.ret[env], reward);
+                if (a.reward) a.reward[(size_t)t * a.out_stride + env] = reward;
             }
-            if (a.obs) pn_build_obs(c, S, pr, O, perm_idx);
-            X[PX_PLO] = pr.plo; X[PX_PHI] = pr.phi; X[PX_ALIVE] = pr.alive; X[PX_ORD0] = pr.ord0; X[PX_ORD1] = pr.ord1; X[PX_MISC] = pr.misc;
+            if (MODE == MODE_OBSERVE && a.reward) a.reward[env] = __uint_as_float(R[HD_REWARD]);
+            if (enabled) {
+                if (a.done) a.done[(size_t)t * a.out_stride + env] = (depth == 0 || success) ? 1 : 0;
+                if (a.success) a.success[(size_t)t * a.out_stride + env] = success ? 1 : 0;
+            }
+
+            // observe(): build the observation bit stream where it is not the state itself
+            if (KIND == QG_ENV_PAULI_NETWORK && enabled) {
+                // PauliNetwork picks its qubit permutation here (pauli.rs:653-665)
+                int perm_idx = 0;
+                if (c.nperms > 0 && a.obs) {
+                    const uint32_t raw = a.perm_raw ? a.perm_raw[(size_t)t * a.in_stride + env] : philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_PERM);
+                    perm_idx = (int)__umulhi(raw, (uint32_t)c.nperms);
+                    pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
+                    dirty = true;
+                }
+                if (a.obs) pn_build_obs(c, S, pr, O, perm_idx);
+            }
+            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && enabled && a.obs) {
+                // one-hot rows: bit i*n + state[i] (permutation.rs:241-243)
+                for (int w = 0; w < c.OW; ++w) O[w] = 0;
+                for (int i = 0, b = 0; i < c.n; ++i, b += c.n) { const int bit = b + (int)get8(S, i); O[bit >> 5] |= 1u << (bit & 31); }
+            }
         }
-        if (enabled) {
-            if (MODE != MODE_OBSERVE) {
+        __syncwarp();
+        const uint32_t mask_bits = __ballot_sync(0xFFFFFFFFu, live && !success);     // masks() = [!success; A] (clifford.rs:349-351)
+        const uint32_t en_bits = __ballot_sync(0xFFFFFFFFu, live && enabled);
+        if (MODE == MODE_SEARCH && a.num_active && lane == 0 && en_bits) atomicAdd(a.num_active, __popc(en_bits));
+
+        // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab --------
+        if (a.obs) {
+            float* out = a.obs + ((size_t)slot * c.B + (size_t)e0) * c.obs_size;
+            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs);
+            else {
+                // large Permutation (no room for a bit stream in shared memory): one-hot test straight from the packed bytes
+                const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, n = (uint32_t)c.n;
+                const uint32_t* st = wbase + c.off_state * kStride;
+                for (uint32_t f = lane; f < total; f += 32) {
+                    const uint32_t e = fastdiv40(f, a.magic_obs), off = f - e * (uint32_t)c.obs_size;
+                    const uint32_t i = __umulhi(off, c.magic_n), col = off - i * n;
+                    if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[f] = (((st[(i >> 2) * kStride + e] >> ((i & 3u) * 8u)) & 0xFFu) == col) ? 1.0f : 0.0f;
+                }
+            }
+        }
+        if (a.mask) {
+            uint8_t* out = a.mask + ((size_t)slot * c.B + (size_t)e0) * c.A;
+            if ((c.A & 3) == 0) expand_mask<MODE, 4>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
+            else expand_mask<MODE, 1>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
+        }
+        if (++slot == a.ring) slot = 0;
+        __syncwarp();                                 // the next step's phase 1 rewrites the bits phase 2 just read
+    }
+
+    if (live && dirty) {
+        R[HD_DEPTH] = depth; R[HD_FLAGS] = flags; R[HD_TICK] = tick;
+        if (KIND == QG_ENV_PAULI_NETWORK) { X[PX_PLO] = pr.plo; X[PX_PHI] = pr.phi; X[PX_ALIVE] = pr.alive; X[PX_ORD0] = pr.ord0; X[PX_ORD1] = pr.ord1; X[PX_MISC] = pr.misc; }
+        if (MODE != MODE_OBSERVE) {
+            uint32_t* dst = c.rec + env;
 #pragma unroll 4
-                for (int w = 0; w < c.W; ++w) c.rec[(size_t)w * c.Bpad + env] = R[w];
-            } else if (KIND == QG_ENV_PAULI_NETWORK) {
-                c.rec[(size_t)(c.off_extra + PX_MISC) * c.Bpad + env] = X[PX_MISC];
-            }
-        }
-    }
-    __syncwarp();
-    const uint32_t mask_bits = __ballot_sync(0xFFFFFFFFu, live && !success);     // masks() = [!success; A] (clifford.rs:349-351)
-    const uint32_t en_bits = __ballot_sync(0xFFFFFFFFu, live && enabled);
-    if (MODE == MODE_SEARCH && a.num_active && lane == 0 && en_bits) atomicAdd(a.num_active, __popc(en_bits));
-
-    // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab ------------
-    if (a.obs) {
-        float* out = a.obs + (size_t)e0 * c.obs_size;
-        const uint32_t* bits = wbase + ((KIND == QG_ENV_PAULI_NETWORK) ? a.sm_obs : c.off_state * kStride);
-        if (KIND != QG_ENV_PERMUTATION && (c.obs_size & 3) == 0) {
-            // fast path: a float4 never straddles two environments; one LDS + one funnel shift per 4 outputs
-            const uint32_t VPE = (uint32_t)c.obs_size >> 2, total = (uint32_t)cnt * VPE;
-#pragma unroll 2
-            for (uint32_t j = lane; j < total; j += 32) {
-                const uint32_t e = (VPE == 1) ? j : __umulhi(j, a.magic_vpe);
-                const uint32_t v = j - e * VPE;
-                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
-                const uint32_t nib = bits[(v >> 3) * kStride + e] >> ((v & 7u) << 2);
-                float4 f;
-                f.x = (nib & 1u) ? 1.0f : 0.0f; f.y = (nib & 2u) ? 1.0f : 0.0f; f.z = (nib & 4u) ? 1.0f : 0.0f; f.w = (nib & 8u) ? 1.0f : 0.0f;
-                __stcs(reinterpret_cast<float4*>(out) + j, f);
-            }
-        } else {
-            // general path: walk (env, offset) incrementally; Permutation reads the one-hot row from the packed bytes
-            const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, nvec = total >> 2, n = (uint32_t)c.n;
-            auto elem = [&](uint32_t e, uint32_t off) -> float {
-                if (KIND == QG_ENV_PERMUTATION) {
-                    const uint32_t i = __umulhi(off, c.magic_n), col = off - i * n;        // observe(): index i*n + state[i] (permutation.rs:241-243)
-                    return (((bits[(i >> 2) * kStride + e] >> ((i & 3u) * 8u)) & 0xFFu) == col) ? 1.0f : 0.0f;
-                }
-                return ((bits[(off >> 5) * kStride + e] >> (off & 31u)) & 1u) ? 1.0f : 0.0f;
-            };
-            for (uint32_t j = lane; j < nvec; j += 32) {
-                const uint32_t f0 = j << 2;
-                uint32_t e = fastdiv40(f0, a.magic_obs), off = f0 - e * (uint32_t)c.obs_size;
-                float v[4]; bool all_on = true;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (off == (uint32_t)c.obs_size) { off = 0; ++e; }
-                    if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) all_on = false;
-                    v[k] = elem(e, off); ++off;
-                }
-                if (all_on) __stcs(reinterpret_cast<float4*>(out) + j, make_float4(v[0], v[1], v[2], v[3]));
-                else {
-                    uint32_t e2 = fastdiv40(f0, a.magic_obs), o2 = f0 - e2 * (uint32_t)c.obs_size;
-                    for (int k = 0; k < 4; ++k) { if (o2 == (uint32_t)c.obs_size) { o2 = 0; ++e2; } if ((en_bits >> e2) & 1u) out[f0 + k] = v[k]; ++o2; }
-                }
-            }
-            for (uint32_t f = (nvec << 2) + lane; f < total; f += 32) {
-                const uint32_t e = fastdiv40(f, a.magic_obs);
-                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[f] = elem(e, f - e * (uint32_t)c.obs_size);
-            }
-        }
-    }
-    if (a.mask) {
-        uint8_t* out = a.mask + (size_t)e0 * c.A;
-        if ((c.A & 3) == 0) {
-            const uint32_t WPE = (uint32_t)c.A >> 2, total = (uint32_t)cnt * WPE;
-            for (uint32_t j = lane; j < total; j += 32) {
-                const uint32_t e = (WPE == 1) ? j : __umulhi(j, a.magic_a4);
-                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
-                __stcs(reinterpret_cast<uint32_t*>(out) + j, ((mask_bits >> e) & 1u) ? 0x01010101u : 0u);
-            }
-        } else {
-            const uint32_t total = (uint32_t)cnt * (uint32_t)c.A;
-            for (uint32_t b = lane; b < total; b += 32) {
-                const uint32_t e = fastdiv40(b, a.magic_A);
-                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[b] = (uint8_t)((mask_bits >> e) & 1u);
-            }
+            for (int w = 0; w < c.W; ++w, dst += c.Bpad) *dst = R[w];
+        } else if (KIND == QG_ENV_PAULI_NETWORK) {
+            c.rec[(size_t)(c.off_extra + PX_MISC) * c.Bpad + env] = pr.misc;
         }
     }
 }

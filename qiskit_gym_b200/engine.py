@@ -143,6 +143,47 @@ class BatchedEnv:
                             _dptr(self.reward), _dptr(self.done), _dptr(self.success), self._stream()))
         return obs_t, self.reward, self.done
 
+    def replay(self, actions: torch.Tensor, coins: torch.Tensor | None = None, perm_raw: torch.Tensor | None = None,
+               obs: torch.Tensor | None = None, mask: torch.Tensor | None = None, reward: torch.Tensor | None = None,
+               done: torch.Tensor | None = None, success: torch.Tensor | None = None):
+        """T consecutive fused steps in one launch from a resident action stream `actions` int32[T, B] (qg_replay).
+        obs: float32[ring, B, obs...] / mask: bool[ring, B, A] ring buffers (step t writes slot t % ring; both must have the
+        same ring), reward float32[T, B], done / success bool[T, B]; any of them may be None."""
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous() and actions.shape[-1] == self.batch
+        T = int(actions.shape[0]) if actions.dim() == 2 else 1
+        ring = 1
+        if obs is not None:
+            assert obs.is_contiguous() and obs.numel() % (self.batch * self._obs_size) == 0
+            ring = obs.numel() // (self.batch * self._obs_size)
+        if mask is not None:
+            assert mask.is_contiguous() and mask.numel() % (self.batch * self._A) == 0
+            mring = mask.numel() // (self.batch * self._A)
+            assert obs is None or mring == ring, "obs and mask rings differ"
+            ring = mring
+        for t in (coins, perm_raw, reward, done, success):
+            assert t is None or (t.is_contiguous() and t.numel() == T * self.batch)
+        check(lib().qg_replay(self._h, T, _dptr(actions), _dptr(coins), _dptr(perm_raw), _dptr(obs), _dptr(mask), ring,
+                              _dptr(reward), _dptr(done), _dptr(success), self._stream()))
+
+    def replay_host(self, actions: np.ndarray, reward: np.ndarray | None = None, done: np.ndarray | None = None,
+                    success: np.ndarray | None = None, coins: np.ndarray | None = None, obs: torch.Tensor | None = None,
+                    mask: torch.Tensor | None = None):
+        """End-to-end episode replay with host buffers (qg_replay_host): int32 actions [T, B] up, reward f32 / done u8 /
+        success u8 [T, B] back, chunks pipelined over copy-in / compute / copy-out streams."""
+        assert actions.dtype == np.int32 and actions.flags.c_contiguous and actions.shape[-1] == self.batch
+        T = int(actions.shape[0])
+        ring = 1
+        if obs is not None:
+            ring = obs.numel() // (self.batch * self._obs_size)
+        if mask is not None:
+            mring = mask.numel() // (self.batch * self._A)
+            assert obs is None or mring == ring, "obs and mask rings differ"
+            ring = mring
+        for a_, dt in ((reward, np.float32), (done, np.uint8), (success, np.uint8), (coins, np.uint8)):
+            assert a_ is None or (a_.dtype == dt and a_.flags.c_contiguous and a_.size == T * self.batch)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib().qg_replay_host(self._h, T, p(actions), p(coins), _dptr(obs), _dptr(mask), ring, p(reward), p(done), p(success), self._stream()))
+
     def step_host(self, actions: np.ndarray, reward: np.ndarray, done: np.ndarray, success: np.ndarray | None = None,
                   coins: np.ndarray | None = None, obs: torch.Tensor | None = None, mask: torch.Tensor | None = None):
         """End-to-end step with host buffers (pinned numpy views recommended): H2D actions, fused step

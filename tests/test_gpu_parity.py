@@ -82,6 +82,117 @@ def test_step_parity_with_inverts(name):
     run_parity(name, add_inverts=True, seed=77)
 
 
+def run_replay_parity(name, B=200, T=40, seed=4321, add_inverts=False, add_perms=False, invalid_rate=0.05, ring=None, **extra):
+    """qg_replay (T fused steps in one launch) must deliver, step by step, exactly what the oracle's T single steps do."""
+    from qiskit_gym_b200 import BatchedEnv
+
+    kind, n, gateset, kw = H.config_table()[name]
+    kw = dict(kw, **extra)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pk = dict(kw)
+    if kind != H.PAULI:
+        pk["add_inverts"] = add_inverts
+    cfg = H.make_cfg(kind, n, gateset, add_perms=add_perms, **pk)
+    tarr = H.random_targets(kind, n, gateset, B, seed, scramble=24, num_rotations=kw.get("max_rotations", 5) + 1, vary_rotations=True)
+    lens = H.payload_lengths(kind, n, tarr)
+    A = len(gateset)
+    actions = H.random_actions(rng, T, B, A, invalid_rate)
+    coins = rng.integers(0, 2, size=(T, B)).astype(np.uint8) if (add_inverts and kind != H.PAULI) else None
+    perm_raw = rng.integers(0, 2**32, size=(T + 1, B), dtype=np.uint64).astype(np.uint32) if (kind == H.PAULI and add_perms) else None
+    ref = orc.run_batch(cfg, tarr, lens, actions, coins=coins, perm_raw=perm_raw)
+
+    env = BatchedEnv(kind, n, gateset, B, add_perms=add_perms, **pk)
+    dev = env.device
+    env.set_state(tarr)
+    if perm_raw is not None:
+        env.observe(perm_raw=torch.from_numpy(perm_raw[0].view(np.int32).copy()).to(dev))     # observe() after set_state picks perm 0
+    R = T if ring is None else ring
+    osz = int(np.prod(env.obs_shape()))
+    obs = torch.full((R, B, osz), 7.0, dtype=torch.float32, device=dev)
+    mask = torch.zeros((R, B, A), dtype=torch.bool, device=dev)
+    reward = torch.zeros((T, B), dtype=torch.float32, device=dev)
+    done = torch.zeros((T, B), dtype=torch.bool, device=dev)
+    success = torch.zeros((T, B), dtype=torch.bool, device=dev)
+    env.replay(torch.from_numpy(actions).to(dev), coins=None if coins is None else torch.from_numpy(coins).to(dev),
+               perm_raw=None if perm_raw is None else torch.from_numpy(perm_raw[1:].view(np.int32).copy()).to(dev),
+               obs=obs, mask=mask, reward=reward, done=done, success=success)
+    assert np.array_equal(reward.cpu().numpy().view(np.uint32), ref["reward"].view(np.uint32)), f"{name}: replay rewards differ"
+    assert np.array_equal(done.cpu().numpy().astype(np.uint8), ref["done"]) and np.array_equal(success.cpu().numpy().astype(np.uint8), ref["success"])
+    ob = obs.cpu().numpy()
+    mk = mask.cpu().numpy().astype(np.uint8)
+    for t in range(max(0, T - R), T):
+        assert np.array_equal(ob[t % R].astype(np.uint8), ref["obs"][t]), f"{name}: replay obs differs at step {t}"
+        assert np.array_equal(mk[t % R], np.repeat((1 - ref["success"][t])[:, None], A, axis=1)), f"{name}: replay mask differs at step {t}"
+    assert np.array_equal(env.metrics().cpu().numpy().astype(np.int64), ref["counts"][T - 1])
+    _, _, _, depth = env.status()
+    assert np.array_equal(depth.cpu().numpy().astype(np.int64), ref["depth"][T - 1])
+    for b in range(0, B, max(1, B // 40)):
+        L = int(ref["final_state_len"][b])
+        assert np.array_equal(env.get_state(b), ref["final_state"][b, :L]), f"{name}: replay final state differs for env {b}"
+        assert env.solution(b) == ref["solutions"][b, : int(ref["sol_len"][b])].tolist(), f"{name}: replay solution differs for env {b}"
+    # a replayed batch continues exactly like a stepped one
+    env.step(torch.zeros(B, dtype=torch.int32, device=dev), coins=None if coins is None else torch.zeros(B, dtype=torch.uint8, device=dev),
+             perm_raw=None if perm_raw is None else torch.zeros(B, dtype=torch.int32, device=dev))
+
+
+@pytest.mark.parametrize("name", ["C1_perm_grid3", "C2_lf8_line", "C3_clifford8_full", "C4_pauli10_line", "C5_perm27_heavyhex", "lf5_line_swap",
+                                  "lf11_line", "clifford3_allgates", "pauli3_line", "perm5_mixed"])
+def test_replay_parity(name):
+    run_replay_parity(name)
+
+
+@pytest.mark.parametrize("name", ["C1_perm_grid3", "C3_clifford8_full", "lf5_line_swap", "clifford20_line"])
+def test_replay_parity_with_inverts(name):
+    run_replay_parity(name, add_inverts=True, T=24, seed=11)
+
+
+def test_replay_ring_and_perms():
+    run_replay_parity("C3_clifford8_full", B=97, T=20, ring=3)
+    run_replay_parity("C1_perm_grid3", B=33, T=9, ring=2)
+    run_replay_parity("pauli6_line", B=70, T=30, add_perms=True, invalid_rate=0.0, seed=8)
+    run_replay_parity("C4_pauli10_line", B=40, T=12, add_perms=True, invalid_rate=0.0, ring=5, seed=9)
+
+
+@pytest.mark.parametrize("name,B,T,inv", [("C3_clifford8_full", 5000, 70, False), ("C1_perm_grid3", 300, 40, True), ("C4_pauli10_line", 257, 33, False)])
+def test_replay_host_pipeline(name, B, T, inv):
+    """qg_replay_host: chunked, pipelined episode replay with host buffers == the oracle's step-by-step results."""
+    from qiskit_gym_b200 import BatchedEnv
+
+    kind, n, gateset, kw = H.config_table()[name]
+    rng = np.random.Generator(np.random.PCG64(21))
+    pk = dict(kw)
+    if kind != H.PAULI:
+        pk["add_inverts"] = inv
+    cfg = H.make_cfg(kind, n, gateset, add_perms=False, **pk)
+    tarr = H.random_targets(kind, n, gateset, B, 21, scramble=30)
+    lens = H.payload_lengths(kind, n, tarr)
+    A = len(gateset)
+    actions = H.random_actions(rng, T, B, A, 0.02)
+    coins = rng.integers(0, 2, size=(T, B)).astype(np.uint8) if inv else None
+    ref = orc.run_batch(cfg, tarr, lens, actions, coins=coins, want_obs=True)
+    env = BatchedEnv(kind, n, gateset, B, add_perms=False, **pk)
+    env.set_state(tarr)
+    osz = int(np.prod(env.obs_shape()))
+    ring = 3
+    obs = torch.zeros((ring, B, osz), dtype=torch.float32, device=env.device)
+    mask = torch.zeros((ring, B, A), dtype=torch.bool, device=env.device)
+    a_pin = torch.from_numpy(actions).pin_memory()
+    rew = torch.zeros((T, B), dtype=torch.float32).pin_memory(); don = torch.zeros((T, B), dtype=torch.uint8).pin_memory(); suc = torch.zeros((T, B), dtype=torch.uint8).pin_memory()
+    env.replay_host(a_pin.numpy(), rew.numpy(), don.numpy(), suc.numpy(), coins=coins, obs=obs, mask=mask)
+    assert np.array_equal(rew.numpy().view(np.uint32), ref["reward"].view(np.uint32))
+    assert np.array_equal(don.numpy(), ref["done"]) and np.array_equal(suc.numpy(), ref["success"])
+    ob = obs.cpu().numpy().astype(np.uint8)
+    for t in range(T - ring, T):
+        assert np.array_equal(ob[t % ring], ref["obs"][t]), f"{name}: ring slot of step {t} differs"
+    for b in range(0, B, max(1, B // 25)):
+        assert env.solution(b) == ref["solutions"][b, : int(ref["sol_len"][b])].tolist()
+    # pageable host memory works too (copies are staged by the runtime)
+    env.set_state(tarr)
+    r2 = np.zeros((T, B), dtype=np.float32)
+    env.replay_host(actions, r2, coins=coins)
+    assert np.array_equal(r2.view(np.uint32), ref["reward"].view(np.uint32))
+
+
 @pytest.mark.parametrize("name", ["clifford20_line", "lf40_line"])
 def test_step_parity_wide_rows(name):
     run_parity(name, B=70, T=24, add_inverts=True, seed=5)
@@ -102,6 +213,27 @@ def test_ragged_batch_sizes():
     for B in (1, 31, 33, 65, 100):
         run_parity("C3_clifford8_full", B=B, T=6, seed=B)
         run_parity("C1_perm_grid3", B=B, T=6, seed=B)
+        run_parity("C2_lf8_line", B=B, T=6, seed=B)
+        run_parity("lf5_line_swap", B=B, T=6, seed=B)       # 25 observation entries, 16 actions
+        run_parity("clifford3_allgates", B=B, T=6, seed=B)
+
+
+def test_large_permutation_direct_expander():
+    """n > 64: no observation bit stream in shared memory, the expander tests the packed bytes (one-hot rows)."""
+    from qiskit_gym_b200 import BatchedEnv
+    n, B, T = 70, 37, 12
+    gs = [("SWAP", (i, i + 1)) for i in range(n - 1)]
+    rng = np.random.Generator(np.random.PCG64(3))
+    tarr = np.stack([rng.permutation(n) for _ in range(B)]).astype(np.int64)
+    actions = H.random_actions(rng, T, B, len(gs), 0.05)
+    cfg = H.make_cfg(H.PERM, n, gs, add_inverts=False, add_perms=False)
+    ref = orc.run_batch(cfg, tarr, H.payload_lengths(H.PERM, n, tarr), actions)
+    env = BatchedEnv(H.PERM, n, gs, B, add_inverts=False, add_perms=False)
+    env.set_state(tarr)
+    for t in range(T):
+        env.step(torch.from_numpy(actions[t]).to(env.device))
+        assert np.array_equal(env.obs.reshape(B, -1).cpu().numpy().astype(np.uint8), ref["obs"][t])
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), ref["reward"][t].view(np.uint32))
 
 
 @pytest.mark.parametrize("name,difficulty", [("C1_perm_grid3", 7), ("C2_lf8_line", 40), ("C3_clifford8_full", 256), ("C5_perm27_heavyhex", 100),
