@@ -32,7 +32,10 @@ import numpy as np
 ALGO_BYTES = {"C1_perm_grid3": 449, "C2_lf8_line": 375, "C3_clifford8_full": 1249, "C4_pauli10_line": 2377, "C5_perm27_heavyhex": 3225}
 # dram__bytes_read.sum + dram__bytes_write.sum of one replay launch, from the committed ncu --set full capture (profiles/), keyed by
 # (config, envs per GPU, env-steps per launch); None where no capture exists.
-TRAFFIC_BYTES_PER_LAUNCH = {}
+TRAFFIC_BYTES_PER_LAUNCH = {
+    # profiles/r1_v3_clifford8_ncu_full.txt: 39.7 MB read + 9 137.9 MB written by one k_step<2,0> nsteps=128 launch
+    ("C3_clifford8_full", 65536, 128): 39717376 + 9137894000,
+}
 METRIC = "batched env-steps/sec (CliffordGym 8q all-to-all {H,S,CX})"
 UNIT = "env-steps/s"
 
