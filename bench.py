@@ -30,6 +30,9 @@ import numpy as np
 # algorithmic bytes per env-step (fp32 obs, u8 mask, i32 action, f32 reward, u8 done,
 # packed state + metrics read and written once).
 ALGO_BYTES = {"C1_perm_grid3": 449, "C2_lf8_line": 375, "C3_clifford8_full": 1249, "C4_pauli10_line": 2377, "C5_perm27_heavyhex": 3225}
+# of which the packed state + metrics record, read and written once per LAUNCH (2*(S_state + S_metrics)): a replay launch of T env-steps moves
+# it once, not T times, so its algorithmic bytes are T*(ALGO - STATE) + STATE per env
+STATE_BYTES = {"C1_perm_grid3": 104, "C2_lf8_line": 96, "C3_clifford8_full": 144, "C4_pauli10_line": 264, "C5_perm27_heavyhex": 272}
 # dram__bytes_read.sum + dram__bytes_write.sum of one replay launch, from the committed ncu --set full capture (profiles/), keyed by
 # (config, envs per GPU, env-steps per launch); None where no capture exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
@@ -54,6 +57,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-per-step", action="store_true", help="skip the one-launch-per-env-step leg (profiling runs)")
+    ap.add_argument("--no-synth", action="store_true", help="skip the synth-search leg (BASELINE.json configs[4])")
+    ap.add_argument("--synth-rollouts", type=int, default=1000, help="num_searches per GPU of the synth leg")
+    ap.add_argument("--synth-searches", type=int, default=5, help="timed searches of the synth leg")
     return ap.parse_args()
 
 
@@ -355,6 +361,8 @@ def run_ours(args):
                "per_step_sync": {"value": world * B * T * Ks / (ems_ps * 1e-3), "unit": UNIT, "steps": Ks,
                                  "note": "qg_step_host: one synchronous H2D + launch + D2H round trip per env-step (host-side collector)"}}
 
+    synth = None if args.no_synth else run_synth(args, dev, local, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,14 +379,17 @@ def run_ours(args):
     roofline = None
     per_step = None
     if algo:
-        achieved = algo * B * T / (launch_us * 1e-6) / 1e9
+        st_b = STATE_BYTES.get(args.config, 0)
+        launch_bytes = (T * (algo - st_b) + st_b) * B          # record moved once per launch, streams T times
+        achieved = launch_bytes / (launch_us * 1e-6) / 1e9
         traffic = TRAFFIC_BYTES_PER_LAUNCH.get((args.config, B, T))
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "kernel": f"qg::k_step<{args.config.split('_')[1]},STEP> nsteps={T} (qg_replay)", "algorithmic_bytes_per_env_step": algo,
-                    "algorithmic_bytes_per_launch": algo * B * T, "avg_launch_us": launch_us,
-                    "note": "algorithmic bytes count the state read+written every env-step (SURVEY 8d); the replay launch keeps it in the SM, "
-                            "so its actual traffic per env-step is lower by 2*(S_state+S_metrics)"}
+                    "algorithmic_bytes_per_launch": launch_bytes, "avg_launch_us": launch_us,
+                    "note": f"one launch = {T} env-steps for every env: the obs/mask/reward/done/action streams ({algo - st_b} B per env-step) move "
+                            f"every env-step, the packed state + metrics record ({st_b} B, read + write) once per launch; "
+                            "peak is the measured device-copy bandwidth (a write-only fill reaches 7 426 GB/s on this part, tools/store_ceiling.py)"}
         ach1 = algo * B / (step_launch_us * 1e-6) / 1e9 if ms_steps else None
         per_step = None if not ms_steps else {"value": world * B * T * K / (ms_steps * 1e-3), "unit": UNIT, "avg_launch_us": step_launch_us, "launches": T * K,
                     "roofline_achieved_gbs": ach1, "roofline_frac": ach1 / peak,
@@ -397,11 +408,56 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (GF(2)) + f32 reward/obs", "data": "synthetic",
         "config": config_json(args, world, {"obs_buffers": nbuf, "cuda_graph": True}),
         "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "per_step_launch": per_step, "cpu_baseline": cpu_baseline,
-        "engine_error_flags": errs,
+        "synth": synth, "engine_error_flags": errs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_synth(args, dev, local, rank, world):
+    """Second BASELINE.json metric: synth rollouts/sec on configs[4] (PermutationGym 27q heavy-hex, num_searches = 1000 per GPU,
+    weak-scaled): policy-guided rollouts on the device (BasicPolicy-shaped MLP 729->512->256->{28,1}, torch.manual_seed(0) init, sampling),
+    every decision = policy forward + softmax + one fused qg_search_step, best rollout reduced on the GPU and across ranks (one int64
+    MAX all-reduce + broadcast of the winner).  Wall time of whole searches, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from qiskit_gym_b200 import workloads as W
+    from qiskit_gym_b200.search import BasicPolicy, RolloutSearch
+
+    kind, n, gateset, kw = W.baseline_configs()["C5_perm27_heavyhex"]
+    R = args.synth_rollouts
+    torch.manual_seed(0)
+    pol = BasicPolicy([n, n], len(gateset), embedding_size=512, common_layers=(256,))
+    rs = RolloutSearch(kind, n, gateset, pol, R, device=local, max_depth=128, add_inverts=False)
+    rng = np.random.Generator(np.random.PCG64(20261017 + 5))
+    targets = [rng.permutation(n).astype(np.int64).tolist() for _ in range(args.synth_searches + 1)]
+    shallow = list(range(n)); shallow[0], shallow[1] = shallow[1], shallow[0]      # one SWAP away: exercises the success / early-exit path
+    rs.solve(targets[0], deterministic=False, seed=0, first_rollout_id=rank * R)    # warm-up: graph capture, cuBLAS
+    res_sh = rs.solve(shallow, deterministic=False, seed=1, first_rollout_id=rank * R)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    its = 0
+    for i in range(args.synth_searches):
+        r = rs.solve(targets[1 + i], deterministic=False, seed=2 + i, first_rollout_id=rank * R)
+        its += r.iterations
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    total = world * R * args.synth_searches
+    return {"metric": "synth rollouts/sec (PermutationGym 27q heavy-hex, num_searches=1000 per GPU)", "value": total / sec, "unit": "rollouts/s",
+            "rollouts_per_search_per_gpu": R, "searches": args.synth_searches, "decisions_per_search": its / max(args.synth_searches, 1),
+            "us_per_decision": 1e6 * sec / max(its, 1), "ms_per_search": 1e3 * sec / max(args.synth_searches, 1),
+            "shallow_target": {"success": bool(res_sh.success), "circuit_len": None if res_sh.actions is None else len(res_sh.actions),
+                               "decisions": res_sh.iterations, "ms": 1e3 * res_sh.seconds},
+            "note": "uniform random 27-permutations, random-init policy (no checkpoint exists for this map): rollouts run to max_depth=128; "
+                    "time is host wall clock over whole solve() calls (set_state broadcast, CUDA-graph replays, on-GPU best reduction, "
+                    "cross-rank all-reduce), max over ranks"}
 
 
 def main():
