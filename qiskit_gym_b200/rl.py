@@ -1,0 +1,107 @@
+"""`RLSynthesis` over the device-resident search (reference src/qiskit_gym/rl/synthesis.py:32-147).
+
+The reference builds a twisterl algorithm object around the raw env and calls `algorithm.solve(state,
+deterministic, num_searches, num_mcts_searches, C, max_expand_depth)` (112-126).  Here `solve` is
+`search.RolloutSearch`: `num_searches` policy-guided rollouts stepped together on the GPU, the best one reduced on
+the device (and across ranks).  Config files and checkpoints are the reference's own formats: the `.json` written by
+`RLSynthesis.save` (79-93) and the policy `state_dict` `.pt` (examples/models/*), so models trained with the
+reference load unchanged.
+
+Out of scope here: `learn()` (PPO / AlphaZero training lives in twisterl) and MCTS (`num_mcts_searches > 0`).
+"""
+from __future__ import annotations
+
+import json
+
+import torch
+
+from . import gyms
+from .search import BasicPolicy, RolloutSearch
+
+_ENV_KINDS = {"PermutationEnv": 0, "LinearFunctionEnv": 1, "CliffordEnv": 2, "PauliNetworkEnv": 3}
+
+
+def gate_list_to_circuit(gate_list, num_qubits=None):
+    """rl/synthesis.py:141-147 (needs Qiskit)."""
+    if num_qubits is None:
+        num_qubits = max(max(gate_args) for _, gate_args in gate_list) + 1
+    from .wire import gates_to_circuit
+    return gates_to_circuit(gate_list, num_qubits)
+
+
+class RLSynthesis:
+    def __init__(self, env, rl_config: dict | None, model_config: dict | None, model_path: str | None = None, device=None,
+                 policy_cls: str = "twisterl.nn.BasicPolicy", algorithm_cls: str = "twisterl.rl.PPO"):
+        self.env = env
+        self.env_config = env.to_json()
+        self.rl_config = dict(rl_config or {})
+        self.model_config = dict(model_config or {})
+        self.policy_cls = policy_cls
+        self.algorithm_cls = algorithm_cls
+        if policy_cls.split(".")[-1] != "BasicPolicy":
+            raise NotImplementedError(f"policy class {policy_cls} is not supported (BasicPolicy only)")
+        self.device = device
+        self.policy = self._init_policy(model_path)
+        self._searches = {}
+
+    # ---- construction ---------------------------------------------------------------------------------
+    @classmethod
+    def from_config_json(cls, config_path, model_path=None, device=None):
+        """rl/synthesis.py:54-77: `{env_cls, env, policy_cls, policy, algorithm_cls, algorithm}`."""
+        full = json.load(open(config_path))
+        env_cls = full["env_cls"].split(".")[-1]
+        assert env_cls in gyms.SYNTH_ENVS, f"Synth env class {full['env_cls']} not supported, should be {list(gyms.SYNTH_ENVS.keys())}"
+        env = gyms.SYNTH_ENVS[env_cls].from_json(full["env"])
+        return cls(env, full.get("algorithm"), full.get("policy"), model_path, device=device,
+                   policy_cls=full.get("policy_cls", "twisterl.nn.BasicPolicy"), algorithm_cls=full.get("algorithm_cls", "twisterl.rl.PPO"))
+
+    def _init_policy(self, model_path):
+        """rl/synthesis.py:95-110: policy(obs_shape, num_actions, **model_config); checkpoint = plain state_dict."""
+        mc = self.model_config
+        pol = BasicPolicy(self.env.obs_shape(), self.env.num_actions(), embedding_size=mc.get("embedding_size", 512),
+                          common_layers=tuple(mc.get("common_layers", (256,))), policy_layers=tuple(mc.get("policy_layers", ())),
+                          value_layers=tuple(mc.get("value_layers", ())))
+        if model_path is not None:
+            pol.load_state_dict(torch.load(model_path, map_location="cpu", weights_only=True))
+        return pol.eval()
+
+    def to_json(self):
+        return {"env_cls": f"qiskit_gym.envs.synthesis.{self.env.cls_name}", "env": self.env_config, "policy_cls": self.policy_cls,
+                "policy": self.model_config, "algorithm_cls": self.algorithm_cls, "algorithm": self.rl_config}
+
+    def save(self, config_path, model_path=None):
+        with open(config_path, "w") as f:
+            json.dump(self.to_json(), f, indent=2)
+        if model_path is not None:
+            with open(model_path, "wb") as f:
+                torch.save(self.policy.state_dict(), f)
+
+    # ---- synthesis ------------------------------------------------------------------------------------
+    def _search(self, num_searches: int) -> RolloutSearch:
+        rs = self._searches.get(num_searches)
+        if rs is None:
+            cfg = dict(self.env_config)
+            kind = _ENV_KINDS[self.env.cls_name]
+            kw = {k: v for k, v in cfg.items() if k not in ("num_qubits", "gateset", "max_depth", "add_perms")}
+            rs = RolloutSearch(kind, cfg["num_qubits"], cfg["gateset"], self.policy, num_searches, device=self.device,
+                               max_depth=cfg.get("max_depth", 128), add_perms=False, **kw)
+            self._searches[num_searches] = rs
+        return rs
+
+    def solve(self, state, deterministic: bool = False, num_searches: int = 100, num_mcts_searches: int = 0, C: float = 2 ** 0.5,
+              max_expand_depth: int = 1, seed: int = 0):
+        """twisterl `Algorithm.solve`: the action list of the best successful rollout, or None."""
+        if num_mcts_searches:
+            raise NotImplementedError("MCTS search is not part of the engine (SURVEY.md §8f row 4)")
+        return self._search(int(num_searches)).solve(state, deterministic=deterministic, seed=seed).actions
+
+    def synth(self, input, deterministic: bool = False, num_searches: int = 100, num_mcts_searches: int = 0, C: float = 2 ** 0.5,
+              max_expand_depth: int = 1, seed: int = 0):
+        """rl/synthesis.py:112-126.  Returns the synthesised circuit (QuantumCircuit with Qiskit, else a gate list) or None."""
+        state = self.env.get_state(input)
+        actions = self.solve(state, deterministic, num_searches, num_mcts_searches, C, max_expand_depth, seed=seed)
+        if actions is not None:
+            return self.env.build_circuit_from_solution(actions, input)
+
+    def learn(self, initial_difficulty=1, num_iterations=int(1e10), tb_path=None):
+        raise NotImplementedError("training runs in twisterl (out of scope, DESIGN.md §7); use collector.RolloutCollector for on-device data collection")

@@ -80,3 +80,20 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def copy_model_fixtures():
+    """The reference's three trained BasicPolicy checkpoints + RLSynthesis config files (examples/models/*.pt, *.json) are data
+    fixtures of the synth path: tests/test_gyms.py loads them through RLSynthesis.from_config_json and checks that the
+    device-resident search synthesises valid circuits with them.  Copied verbatim (they are model data, not source)."""
+    import shutil
+    src = "/root/reference/examples/models"
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
+    os.makedirs(dst, exist_ok=True)
+    for f in sorted(os.listdir(src)):
+        if f.endswith((".pt", ".json")):
+            shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+
+
+if __name__ == "__main__" and os.path.isdir("/root/reference/examples/models"):
+    copy_model_fixtures()

@@ -1,0 +1,124 @@
+"""Gymnasium-facing wrappers (gyms.py) and RLSynthesis (rl.py) on the GPU, driven with the reference's own trained
+checkpoints (tests/golden/models = /root/reference/examples/models)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from qiskit_gym_b200 import wire
+from tests import helpers as H
+from tests.test_wire import random_gates, unitary
+
+pytestmark = pytest.mark.gpu
+MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models")
+
+
+def test_gym_wrapper_contract():
+    """adapters.py:36-105: spaces, dense int8 observation, (obs, reward, terminated, truncated, info), final-state assertion,
+    attribute forwarding and `difficulty` propagation — on the LinearFunction walk-through of the reference notebook."""
+    from qiskit_gym_b200 import gyms
+    k = json.load(open(os.path.join(os.path.dirname(MODELS), "notebook_kats.json")))
+    gs = [(g, tuple(q)) for g, q in k["lf3_gateset"]]
+    edges = sorted({q for _, q in gs})
+    env = gyms.LinearFunctionGym.from_coupling_map(edges, basis_gates=("CX", "SWAP"), add_inverts=False, add_perms=False)
+    assert type(env).__name__ == "LinearFunctionGym" and env.cls_name == "LinearFunctionEnv"
+    assert env.config["gateset"] == gs
+    assert env.observation_space.shape == (3, 3) and env.action_space.n == env.num_actions()
+    assert env.to_json()["num_qubits"] == 3
+    env.difficulty = 5
+    assert env._raw_env.difficulty == 5 and env.difficulty == 5
+    obs, info = env.reset(seed=1)
+    assert obs.shape == (3, 3) and obs.dtype == np.int8 and info == {}
+    ref = orc.OracleEnv(H.LF, 3, env.config["gateset"], add_inverts=False, add_perms=False)
+    start = [1, 1, 0, 0, 1, 0, 0, 1, 1]
+    env.set_state(start); ref.set_state(start)
+    for a in (0, 5, 2, 1, 7, 3):
+        if ref.is_final():
+            break
+        obs, r, term, trunc, info = env.step(a)
+        ref.step(a)
+        want = np.zeros(9, dtype=np.int8); want[ref.observe()] = 1
+        assert np.array_equal(obs.reshape(-1), want) and trunc is False and info == {}
+        assert np.float32(r).view(np.uint32) == np.float32(ref.reward()).view(np.uint32) and term == ref.is_final()
+    env.set_state([1, 0, 0, 0, 1, 0, 0, 0, 1])
+    assert env.is_final()
+    with pytest.raises(AssertionError):
+        env.step(0)
+    env2 = gyms.LinearFunctionGym.from_json(env.to_json())
+    assert env2.config == env.config
+
+
+@pytest.mark.parametrize("name", ["perm_square_3x3", "lf_5_line", "clifford_3q_custom"])
+def test_rlsynthesis_with_reference_checkpoints(name):
+    """RLSynthesis.from_config_json + synth (rl/synthesis.py:54-77, 112-126) with the reference's trained policies: the
+    device-resident search must return circuits that implement the target."""
+    from qiskit_gym_b200.rl import RLSynthesis
+    rls = RLSynthesis.from_config_json(os.path.join(MODELS, name + ".json"), os.path.join(MODELS, name + ".pt"))
+    saved = json.load(open(os.path.join(MODELS, name + ".json")))
+    assert all(rls.to_json()["env"][k] == v for k, v in saved["env"].items()) and rls.to_json()["policy"] == saved["policy"]
+    cfg = rls.env_config
+    n, gs = cfg["num_qubits"], [(g, tuple(q)) for g, q in cfg["gateset"]]
+    rng = np.random.default_rng(5)
+    solved, trials = 0, 12
+    for t in range(trials):
+        if name.startswith("perm"):
+            target = rng.permutation(n)
+            circ = rls.synth(target, deterministic=False, num_searches=64, seed=t)
+            if circ is None:
+                continue
+            # the SWAP list sorts the env state (argsort of the pattern) into the identity
+            st = np.argsort(target)
+            for g, (a, b) in circ:
+                assert g == "SWAP"
+                st[[a, b]] = st[[b, a]]
+            assert np.array_equal(st, np.arange(n))
+        elif name.startswith("lf"):
+            names = tuple(sorted({g.lower() for g, _ in gs}))
+            edges = [q for g, q in gs if g.lower() == "cx"]
+            tg = [("cx", edges[int(rng.integers(len(edges)))]) for _ in range(12)]
+            M = np.eye(n, dtype=np.uint8)
+            for _, (a, b) in tg:
+                M[b] ^= M[a]
+            circ = rls.synth(M, deterministic=False, num_searches=64, seed=t)
+            if circ is None:
+                continue
+            G = np.eye(n, dtype=np.uint8)
+            for g, (a, b) in circ:
+                if g.lower() == "cx":
+                    G[b] ^= G[a]
+                else:
+                    G[[a, b]] = G[[b, a]]
+            assert np.array_equal(G, M), names
+        else:
+            tg = [gs[int(rng.integers(len(gs)))] for _ in range(10)]
+            for _ in range(3):
+                tg.insert(int(rng.integers(len(tg))), (("x", "y", "z")[int(rng.integers(3))], (int(rng.integers(n)),)))
+            circ = rls.synth(tg, deterministic=False, num_searches=64, seed=t)
+            if circ is None:
+                continue
+            assert np.array_equal(wire.StabilizerTableau.from_gates(circ, n).to_array(), wire.StabilizerTableau.from_gates(tg, n).to_array())
+            U, V = unitary([(g.lower(), q) for g, q in circ], n), unitary([(g.lower(), q) for g, q in tg], n)
+            k = np.argmax(np.abs(V))
+            assert np.allclose(U, (U.flat[k] / V.flat[k]) * V, atol=1e-9)
+        solved += 1
+    assert solved >= trials - 2, f"{name}: only {solved}/{trials} targets synthesised"
+    # deterministic single rollout is reproducible
+    a = rls.solve(rls.env.get_state(np.arange(n)[::-1].copy()) if name.startswith("perm") else rls.env.get_state(np.eye(n, dtype=np.uint8)) if name.startswith("lf")
+                  else rls.env.get_state([("h", (0,))]), deterministic=True, num_searches=1)
+    b = rls.solve(rls.env.get_state(np.arange(n)[::-1].copy()) if name.startswith("perm") else rls.env.get_state(np.eye(n, dtype=np.uint8)) if name.startswith("lf")
+                  else rls.env.get_state([("h", (0,))]), deterministic=True, num_searches=1)
+    assert a == b
+
+
+def test_rlsynthesis_save_roundtrip(tmp_path):
+    from qiskit_gym_b200.rl import RLSynthesis
+    rls = RLSynthesis.from_config_json(os.path.join(MODELS, "lf_5_line.json"), os.path.join(MODELS, "lf_5_line.pt"))
+    rls.save(str(tmp_path / "c.json"), str(tmp_path / "m.pt"))
+    again = RLSynthesis.from_config_json(str(tmp_path / "c.json"), str(tmp_path / "m.pt"))
+    assert again.to_json() == rls.to_json()
+    for (k1, v1), (k2, v2) in zip(rls.policy.state_dict().items(), again.policy.state_dict().items()):
+        assert k1 == k2 and bool((v1 == v2).all())
+    with pytest.raises(NotImplementedError):
+        rls.solve([0] * 25, num_mcts_searches=4)
