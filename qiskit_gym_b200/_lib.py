@@ -12,7 +12,8 @@ import subprocess
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqg_engine.so")
+# QG_ENGINE_LIB: load another build of the same library (kernel A/B runs, tools/); the default is the in-tree build
+LIB_PATH = os.environ.get("QG_ENGINE_LIB") or os.path.join(_HERE, "libqg_engine.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 # every symbol include/qg_engine.h declares
@@ -29,10 +30,10 @@ SYMBOLS = [
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compiles the CUDA extension for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "qg_engine.h")]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))] + [os.path.join(_HERE, "..", "include", "qg_engine.h")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
-        cmd = ["make", "-C", CSRC] + (["-B"] if force else [])
+        cmd = ["make", "-C", CSRC, f"-j{min(os.cpu_count() or 1, 8)}"] + (["-B"] if force else [])
         subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     return LIB_PATH
 

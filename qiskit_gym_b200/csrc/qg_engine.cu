@@ -8,7 +8,8 @@
 #include <vector>
 
 #include "qg_host.hpp"
-#include "qg_kernels.cuh"
+#include "qg_aux_kernels.cuh"
+#include "qg_launch.hpp"
 
 using namespace qg;
 
@@ -37,6 +38,8 @@ struct qg_engine {
     int nperms = 0;
     int pdl_mode = 2;                // QG_PDL=0|1|2 in the environment: programmatic dependent launch variants (see StepArgs)
     int stagger_ns = 0, num_sms = 148;
+    bool all_symplectic = true;      // Clifford: every state loaded so far is symplectic (identity at construction, resets, checked set_state payloads)
+    bool inv_bucket_enabled = true;  // QG_INV_REG=0 in the environment forces the generic shared-memory Gauss-Jordan (A/B runs)
     // qg_replay_host pipeline (allocated on first use): two chunk buffers, copy-in / copy-out streams
     int rp_chunk = 0;
     int32_t* rp_actions[2] = {nullptr, nullptr}; uint8_t* rp_coins[2] = {nullptr, nullptr};
@@ -87,38 +90,17 @@ int pauli_perms(const qg_config* cfg, Twists& tw) {
     return compute_twists(cfg, true, tw);
 }
 
-template <int KIND>
-int prepare_kernels_k(qg_engine* e) {   // opt in to > 48 KB dynamic shared memory once, outside any stream capture
+int prepare_kernels(qg_engine* e) {   // opt in to > 48 KB dynamic shared memory once, outside any stream capture
     if (e->smem_bytes <= 48 * 1024) return QG_OK;
-    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CUDA_OK(cudaFuncSetAttribute(k_step<KIND, MODE_SEARCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    return QG_OK;
-}
-int prepare_kernels(qg_engine* e) {
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: return prepare_kernels_k<QG_ENV_PERMUTATION>(e);
-        case QG_ENV_LINEAR_FUNCTION: return prepare_kernels_k<QG_ENV_LINEAR_FUNCTION>(e);
-        case QG_ENV_CLIFFORD: return prepare_kernels_k<QG_ENV_CLIFFORD>(e);
-        default: return prepare_kernels_k<QG_ENV_PAULI_NETWORK>(e);
+        case QG_ENV_PERMUTATION: CUDA_OK(prepare_step_kind<QG_ENV_PERMUTATION>(e->smem_bytes)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(prepare_step_kind<QG_ENV_LINEAR_FUNCTION>(e->smem_bytes)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(prepare_step_kind<QG_ENV_CLIFFORD>(e->smem_bytes)); break;
+        default: CUDA_OK(prepare_step_kind<QG_ENV_PAULI_NETWORK>(e->smem_bytes)); break;
     }
-}
-template <int KIND, int MODE>
-int launch_step_k(qg_engine* e, const StepArgs& a, cudaStream_t st) {
-    const int64_t tiles = (e->B + 31) / 32;
-    const unsigned grid = (unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta);
-    // programmatic dependent launch: the grid may start while its predecessor in the stream drains; the kernel
-    // waits (griddepcontrol.wait) before it touches the records
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(grid); lc.blockDim = dim3(kWarpsPerCta * 32); lc.dynamicSmemBytes = e->smem_bytes; lc.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = a.pdl_mode ? 1 : 0;
-    CUDA_OK(cudaLaunchKernelEx(&lc, k_step<KIND, MODE>, e->dc, a));
     return QG_OK;
 }
-template <int MODE>
-int launch_step(qg_engine* e, StepArgs a, cudaStream_t st) {
+int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st) {
     if (e->B == 0) return QG_OK;
     int cur = -1;
     CUDA_OK(cudaGetDevice(&cur));
@@ -126,17 +108,26 @@ int launch_step(qg_engine* e, StepArgs a, cudaStream_t st) {
     if (a.nsteps <= 0) a.nsteps = 1;
     if (a.ring <= 0) a.ring = 1;
     a.pdl_mode = e->pdl_mode; a.num_sms = e->num_sms;
-    a.stagger_ns = (MODE == MODE_STEP && a.nsteps >= 8) ? e->stagger_ns : 0;
+    a.stagger_ns = (mode == MODE_STEP && a.nsteps >= 8) ? e->stagger_ns : 0;
     a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
+    { const uint32_t vpe = (uint32_t)e->L.obs_size / 4; a.exp_q = vpe ? 32u / vpe : 0u; a.exp_r = vpe ? 32u - a.exp_q * vpe : 0u; }
+    a.symplectic = e->all_symplectic ? 1 : 0;
     if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     if (a.mask && (reinterpret_cast<uintptr_t>(a.mask) & 15)) { set_error("mask_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
+    const int64_t tiles = (e->B + 31) / 32;
+    LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), e->smem_bytes, a.pdl_mode ? 1 : 0};
+    // register bucket of the add_inverts inverse (qg_gf2.cuh); 0 = generic shared-memory path (dimension > 32, or no inverts)
+    int inv = 0;
+    if (e->dc.add_inverts && e->inv_bucket_enabled && (e->L.kind == QG_ENV_LINEAR_FUNCTION || e->L.kind == QG_ENV_CLIFFORD))
+        inv = e->L.D <= 8 ? 8 : e->L.D <= 16 ? 16 : e->L.D <= 32 ? 32 : 0;
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: return launch_step_k<QG_ENV_PERMUTATION, MODE>(e, a, st);
-        case QG_ENV_LINEAR_FUNCTION: return launch_step_k<QG_ENV_LINEAR_FUNCTION, MODE>(e, a, st);
-        case QG_ENV_CLIFFORD: return launch_step_k<QG_ENV_CLIFFORD, MODE>(e, a, st);
-        default: return launch_step_k<QG_ENV_PAULI_NETWORK, MODE>(e, a, st);
+        case QG_ENV_PERMUTATION: CUDA_OK(launch_step_kind<QG_ENV_PERMUTATION>(mode, inv, e->dc, a, g, st)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_step_kind<QG_ENV_LINEAR_FUNCTION>(mode, inv, e->dc, a, g, st)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(launch_step_kind<QG_ENV_CLIFFORD>(mode, inv, e->dc, a, g, st)); break;
+        default: CUDA_OK(launch_step_kind<QG_ENV_PAULI_NETWORK>(mode, inv, e->dc, a, g, st)); break;
     }
+    return QG_OK;
 }
 
 int launch_load(qg_engine* e, int64_t first, int64_t count, int broadcast, uint32_t depth_init, cudaStream_t st) {
@@ -253,6 +244,8 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     e->L = L; e->device = device; e->B = batch; e->Bpad = align_up(std::max<int64_t>(batch, 1), 32);
     e->nperms = (int)tw.act_perms.size();
     if (const char* v = std::getenv("QG_PDL")) e->pdl_mode = std::atoi(v);
+    if (const char* v = std::getenv("QG_INV_REG")) e->inv_bucket_enabled = std::atoi(v) != 0;
+    if (const char* v = std::getenv("QG_INV_SYMPLECTIC")) e->all_symplectic = std::atoi(v) != 0;   // 0: never use the transpose shortcut
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
     {   // replay stagger: the time one warp's observation + mask slab takes at the SM's share of the write bandwidth
         const double slab = 32.0 * (4.0 * L.obs_size + L.A + 6.0), sm_bw = 6.6e12 / e->num_sms;
@@ -274,7 +267,7 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     // shared-memory plan: each warp owns [W | SCR | OW] words x kStride for its 32 envs
     const int words = L.W + L.SCR + L.OW;
     e->sm_warp_words = words * kStride; e->sm_scr = L.W * kStride; e->sm_obs = (L.W + L.SCR) * kStride;
-    e->smem_bytes = (size_t)e->sm_warp_words * kWarpsPerCta * 4;
+    e->smem_bytes = ((size_t)kLutWords + (size_t)e->sm_warp_words * kWarpsPerCta) * 4;
     if (e->smem_bytes > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
     e->magic_obs = magic40((uint32_t)L.obs_size); e->magic_A = magic40((uint32_t)L.A);
     auto magic32 = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
@@ -375,6 +368,7 @@ int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride, int64
         int64_t used = 0;
         rc = pack_state(&e->cfg, e->L, states_host + i * stride, stride, e->h_staged + i * e->L.PW, &used);
         if (rc != QG_OK) return rc;
+        if (e->L.kind == QG_ENV_CLIFFORD && e->all_symplectic && !is_symplectic(e->L, e->h_staged + i * e->L.PW)) e->all_symplectic = false;
     }
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(e->staged, e->h_staged, (size_t)payloads * e->L.PW * 4, cudaMemcpyHostToDevice, st));
@@ -426,7 +420,7 @@ int qg_step(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, 
     if (!e || !actions_dev) { set_error("null argument"); return QG_ERR_INVALID; }
     StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs = obs_dev; a.mask = mask_dev;
     a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
-    return launch_step<MODE_STEP>(e, a, (cudaStream_t)stream);
+    return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
 }
 
 int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev,
@@ -437,7 +431,7 @@ int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const
     StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs = obs_dev; a.mask = mask_dev;
     a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
     a.nsteps = num_steps; a.ring = ring; a.in_stride = e->B; a.out_stride = e->B;
-    return launch_step<MODE_STEP>(e, a, (cudaStream_t)stream);
+    return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
 }
 
 // Episode replay with HOST buffers, pipelined in chunks of steps over three streams: the copy-in stream uploads the
@@ -481,7 +475,7 @@ int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host,
         StepArgs a{}; a.actions = e->rp_actions[b]; a.coins = coins_host ? e->rp_coins[b] : nullptr; a.obs = obs_dev; a.mask = mask_dev;
         a.reward = reward_host ? e->rp_reward[b] : nullptr; a.done = done_host ? e->rp_done[b] : nullptr; a.success = success_host ? e->rp_success[b] : nullptr;
         a.nsteps = ns; a.ring = ring; a.slot0 = t0 % ring; a.in_stride = e->B; a.out_stride = e->B;
-        const int rc = launch_step<MODE_STEP>(e, a, st);
+        const int rc = launch_step(e, MODE_STEP, a, st);
         if (rc != QG_OK) return rc;
         CUDA_OK(cudaEventRecord(e->rp_ev_run[b], st));
         CUDA_OK(cudaStreamWaitEvent(e->rp_out, e->rp_ev_run[b], 0));
@@ -505,7 +499,7 @@ int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins
     if (coins_host) CUDA_OK(cudaMemcpyAsync(e->io_coins, coins_host, B, cudaMemcpyHostToDevice, st));
     StepArgs a{}; a.actions = e->io_actions; a.coins = coins_host ? e->io_coins : nullptr; a.obs = obs_dev; a.mask = mask_dev;
     a.reward = e->io_reward; a.done = e->io_done; a.success = e->io_success;
-    const int rc = launch_step<MODE_STEP>(e, a, st);
+    const int rc = launch_step(e, MODE_STEP, a, st);
     if (rc != QG_OK) return rc;
     if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host, e->io_reward, B * 4, cudaMemcpyDeviceToHost, st));
     if (done_host) CUDA_OK(cudaMemcpyAsync(done_host, e->io_done, B, cudaMemcpyDeviceToHost, st));
@@ -517,12 +511,12 @@ int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins
 int qg_observe(qg_engine* e, const uint32_t* perm_raw_dev, float* obs_dev, qg_stream stream) {
     if (!e || !obs_dev) { set_error("null argument"); return QG_ERR_INVALID; }
     StepArgs a{}; a.perm_raw = perm_raw_dev; a.obs = obs_dev;
-    return launch_step<MODE_OBSERVE>(e, a, (cudaStream_t)stream);
+    return launch_step(e, MODE_OBSERVE, a, (cudaStream_t)stream);
 }
 int qg_masks(qg_engine* e, uint8_t* mask_dev, qg_stream stream) {
     if (!e || !mask_dev) { set_error("null argument"); return QG_ERR_INVALID; }
     StepArgs a{}; a.mask = mask_dev;
-    return launch_step<MODE_OBSERVE>(e, a, (cudaStream_t)stream);
+    return launch_step(e, MODE_OBSERVE, a, (cudaStream_t)stream);
 }
 int qg_read_status(qg_engine* e, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, int32_t* depth_dev, qg_stream stream) {
     if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
@@ -596,7 +590,7 @@ int qg_search_step(qg_engine* e, const float* weights_dev, int32_t deterministic
     cudaStream_t st = (cudaStream_t)stream;
     if (num_active_dev) CUDA_OK(cudaMemsetAsync(num_active_dev, 0, 4, st));
     StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs = obs_dev; a.mask = mask_dev; a.chosen = chosen_dev; a.num_active = num_active_dev;
-    return launch_step<MODE_SEARCH>(e, a, st);
+    return launch_step(e, MODE_SEARCH, a, st);
 }
 
 int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream) {

@@ -327,6 +327,18 @@ int pack_state(const qg_config* cfg, const Layout& L, const int64_t* p, int64_t 
     *used = i; return QG_OK;
 }
 
+bool is_symplectic(const Layout& L, const uint32_t* packed) {
+    const int n = L.n, D = 2 * n;
+    auto bit = [&](int r, int c) { const int64_t b = (int64_t)r * D + c; return (packed[b >> 5] >> (b & 31)) & 1u; };
+    for (int i = 0; i < D; ++i)
+        for (int j = i; j < D; ++j) {
+            uint32_t s = 0;                      // sum_k M[i][k] M[j][k +- n]
+            for (int k = 0; k < n; ++k) s ^= (bit(i, k) & bit(j, k + n)) ^ (bit(i, k + n) & bit(j, k));
+            if (s != (uint32_t)(j == i + n ? 1 : 0)) return false;
+        }
+    return true;
+}
+
 int unpack_state(const Layout& L, const uint32_t* rec, uint8_t* out, int64_t cap, int64_t* len) {
     const uint32_t* S = rec + L.off_state;
     auto bit = [&](int64_t b) { return (uint8_t)((S[b >> 5] >> (b & 31)) & 1u); };

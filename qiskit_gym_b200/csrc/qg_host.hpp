@@ -42,6 +42,9 @@ void pauli_gen_tables(const qg_config* cfg, std::vector<uint32_t>& out);
 int pack_state(const qg_config* cfg, const Layout& L, const int64_t* payload, int64_t avail, uint32_t* out, int64_t* used);
 // identity payload words (constructor state)
 void pack_identity(const Layout& L, uint32_t* out);
+// Clifford: is the packed 2n x 2n matrix symplectic (M J M^T = J, J = [[0,I],[I,0]])?  Every state the gates can reach from the
+// identity is; a set_state payload need not be, and then the coin's inverse must not use the transpose shortcut (qg_gf2.cuh).
+bool is_symplectic(const Layout& L, const uint32_t* packed);
 // record column (W words) -> reference byte-per-entry layout
 int unpack_state(const Layout& L, const uint32_t* rec, uint8_t* out, int64_t cap, int64_t* len);
 

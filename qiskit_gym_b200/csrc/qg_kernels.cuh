@@ -10,6 +10,7 @@
 //       of the uint8 action-mask tensor is produced from the packed bits with 16-byte coalesced streaming stores.
 #pragma once
 #include "qg_common.cuh"
+#include "qg_gf2.cuh"
 
 namespace qg {
 
@@ -27,6 +28,7 @@ struct StepArgs {
     int32_t nsteps;              // steps played by this launch (MODE_STEP; 1 otherwise)
     int32_t ring;                // obs / mask hold `ring` step slots of [B][obs_size] / [B][A]; step t writes slot (slot0 + t) % ring
     int32_t slot0;
+    int32_t symplectic;          // Clifford: every loaded state is symplectic, the coin's inverse may use J M^T J (qg_gf2.cuh)
     int32_t pdl_mode;            // 0: plain launch; 1: dependents may launch right away; 2: only once this grid owns the records
     int32_t stagger_ns, num_sms; // replay: warp k of an SM starts k * stagger_ns late so that the warps of an SM do not all
                                  // alternate between the latency-bound step phase and the store-bound expansion in lock-step
@@ -35,6 +37,7 @@ struct StepArgs {
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
+    uint32_t exp_q, exp_r;            // 32 / VPE and 32 % VPE with VPE = obs_size / 4: how (env, float4-in-env) advances per warp store
 };
 
 enum { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_SEARCH = 2 };
@@ -287,10 +290,38 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
+// store flavour of the observation / mask slabs (compile-time switch for A/B runs): 0 = st.global.cs (streaming, evict first),
+// 1 = plain st.global, 2 = st.global.wt
+#ifndef QG_STORE
+#define QG_STORE 0
+#endif
+template <class V>
+__device__ __forceinline__ void st_slab(V* p, const V& v) {
+#if QG_STORE == 0
+    __stcs(p, v);
+#elif QG_STORE == 1
+    *p = v;
+#else
+    __stwt(p, v);
+#endif
+}
 __device__ __forceinline__ float4 nibble_to_float4(uint32_t nib) {
     float4 f;
     f.x = (nib & 1u) ? 1.0f : 0.0f; f.y = (nib & 2u) ? 1.0f : 0.0f; f.z = (nib & 4u) ? 1.0f : 0.0f; f.w = (nib & 8u) ? 1.0f : 0.0f;
     return f;
+}
+// nibble -> float4 table in shared memory: entry (nib, copy) at float4 index nib * 8 + copy, copy = lane & 7.  A quarter
+// warp (8 consecutive lanes, the unit a 128-bit shared load is served in) then touches 8 different 16-byte bank groups
+// whatever the nibbles are: conflict free.  Every warp writes the whole table itself before it reads it (the warps of a CTA
+// write identical values), so no block barrier is needed.
+constexpr int kLutWords = 16 * 8 * 4;
+__device__ __forceinline__ void lut_fill(uint32_t* lut, int lane) {
+#pragma unroll
+    for (int i = lane; i < 128; i += 32) reinterpret_cast<float4*>(lut)[i] = nibble_to_float4((uint32_t)i >> 3);
+    __syncwarp();
+}
+__device__ __forceinline__ float4 lut_get(const uint32_t* lut_lane /* lut + (lane & 7) * 4 */, uint32_t nib) {
+    return *reinterpret_cast<const float4*>(lut_lane + (nib << 5));
 }
 // 4 bits at bit offset `off` of environment e's observation bit stream (words at bits[w * kStride + e])
 __device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t e, uint32_t off) {
@@ -301,26 +332,48 @@ __device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t
 }
 
 // Phase 2a: bits -> floats.  The warp's slab out[0 .. cnt*obs_size) is contiguous in the [B][obs_size] tensor; lane l
-// stores the float4 number l, l+32, ... (512 contiguous bytes per warp instruction).  (e, off) of a lane's float4 is
-// tracked incrementally: advancing 32 float4s adds (q, r) with one conditional wrap, so the loop has no division.
+// stores the float4 number l, l+32, ... (512 contiguous bytes per warp instruction).  (e, v) = (environment, float4 within
+// the environment) of a lane's float4 is tracked incrementally: advancing 32 float4s adds (q, r) with one conditional wrap,
+// so the loop has no division; the four floats come from the shared-memory table with one 128-bit load.
 template <int MODE>
-__device__ __forceinline__ void expand_obs(const uint32_t* bits, float* out, uint32_t cnt, uint32_t obs, uint32_t en_bits, int lane,
-                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs) {
+__device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t* lut, float* out, uint32_t cnt, uint32_t obs, uint32_t en_bits, int lane,
+                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs, uint32_t q4, uint32_t r4) {
     // 16-byte stores need an aligned slab: always true for the engine's own [B][obs] tensors; a ring slot of an odd-sized
     // batch may start off the grid, then everything goes through the scalar tail loop
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-    if (vec_ok && (obs & 3u) == 0) {
+    const uint32_t* const lut_lane = lut + ((lane & 7) << 2);
+    float4* const out4 = reinterpret_cast<float4*>(out);
+    if (vec_ok && (obs & 31u) == 0) {
+        // whole words per environment: a lane's nibble position inside its word never changes (r4 is a multiple of 8)
+        const uint32_t VPE = obs >> 2, total = cnt * VPE, sh = ((uint32_t)lane & 7u) << 2;
+        uint32_t e = (VPE == 1) ? (uint32_t)lane : __umulhi((uint32_t)lane, magic_obs4), v = (uint32_t)lane - e * VPE;
+        const uint32_t* src = bits + (v >> 3) * kStride + e;
+        const int32_t dstep = (int32_t)(q4 + (r4 >> 3) * kStride), dwrap = 1 - (int32_t)(VPE >> 3) * kStride;
+        if (r4 == 0) {          // VPE divides 32: the lane keeps its word column and only walks the environments
+#pragma unroll 4
+            for (uint32_t j = lane; j < total; j += 32) {
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u));
+                src += dstep; e += q4;
+            }
+        } else {
+#pragma unroll 4
+            for (uint32_t j = lane; j < total; j += 32) {
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u));
+                src += dstep; e += q4; v += r4;
+                if (v >= VPE) { v -= VPE; src += dwrap; ++e; }
+            }
+        }
+    } else if (vec_ok && (obs & 3u) == 0) {
         // a float4 never straddles two environments
         const uint32_t VPE = obs >> 2, total = cnt * VPE;
         uint32_t e = (VPE == 1) ? (uint32_t)lane : __umulhi((uint32_t)lane, magic_obs4), v = (uint32_t)lane - e * VPE;
-        const uint32_t q = 32u / VPE, r = 32u - q * VPE;
 #pragma unroll 4
         for (uint32_t j = lane; j < total; j += 32) {
             if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) {
                 const uint32_t nib = bits[(v >> 3) * kStride + e] >> ((v & 7u) << 2);
-                __stcs(reinterpret_cast<float4*>(out) + j, nibble_to_float4(nib));
+                st_slab(out4 + j, lut_get(lut_lane, nib & 15u));
             }
-            e += q; v += r;
+            e += q4; v += r4;
             if (v >= VPE) { v -= VPE; ++e; }
         }
     } else {
@@ -334,7 +387,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, float* out, uin
                 const bool straddle = off + 4u > obs;                 // the float4 ends in environment e+1
                 if (straddle) { const uint32_t k = obs - off; nib = (nib & ((1u << k) - 1u)) | (bits[e + 1] << k); }
                 const bool on = (MODE != MODE_SEARCH) || (((en_bits >> e) & 1u) && (!straddle || ((en_bits >> (e + 1)) & 1u)));
-                if (on) __stcs(reinterpret_cast<float4*>(out) + j, nibble_to_float4(nib));
+                if (on) st_slab(out4 + j, lut_get(lut_lane, nib & 15u));
                 else {
                     uint32_t ee = e, oo = off;
                     for (int k = 0; k < 4; ++k) { if ((en_bits >> ee) & 1u) out[(j << 2) + k] = ((nib >> k) & 1u) ? 1.0f : 0.0f; if (++oo == obs) { oo = 0; ++ee; } }
@@ -356,6 +409,17 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, float* out, uin
 template <int MODE, int G>
 __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t A, uint32_t mask_bits, uint32_t en_bits, int lane, uint64_t magic_A) {
     const uint32_t total = cnt * A, nvec = (reinterpret_cast<uintptr_t>(out) & 15u) ? 0u : (total >> 4);   // whole 16-byte vectors of the (aligned) slab
+    if (MODE != MODE_SEARCH) {
+        // the usual case: the 32 environments agree (nobody solved yet, or all solved) -> a plain fill of the slab
+        const uint32_t live = cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+        if (mask_bits == live || mask_bits == 0u) {
+            const uint32_t w = mask_bits ? 0x01010101u : 0u;
+            const uint4 w4 = make_uint4(w, w, w, w);
+            for (uint32_t j = lane; j < nvec; j += 32) st_slab(reinterpret_cast<uint4*>(out) + j, w4);
+            for (uint32_t b = (nvec << 4) + lane; b < total; b += 32) out[b] = (uint8_t)(w & 1u);
+            return;
+        }
+    }
     const uint32_t P = A / G;                                     // granules per environment
     const uint32_t g0 = ((uint32_t)lane << 4) / G;                // first granule of this lane's first vector
     uint32_t e = fastdiv40(g0 * G, magic_A), off = g0 - e * P;
@@ -370,7 +434,7 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
             if (G == 4) w[k] = bit ? 0x01010101u : 0u; else w[k >> 2] |= bit << ((k & 3) * 8);
             if (++oo == P) { oo = 0; ++ee; }
         }
-        if (MODE != MODE_SEARCH || all_on) __stcs(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]));
+        if (MODE != MODE_SEARCH || all_on) st_slab(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]));
         else {
             uint32_t e2 = e, o2 = off;
             for (int k = 0; k < 16 / G; ++k) {
@@ -387,15 +451,19 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
     }
 }
 
-template <int KIND, int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
+// INV: register bucket of the add_inverts inverse (qg_gf2.cuh): 0 = generic shared-memory Gauss-Jordan (or no inverts),
+// 8 / 16 / 32 = matrix dimension bound of the register-resident versions.
+template <int KIND, int MODE, int INV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.pdl_mode == 1) pdl_launch_dependents();
     const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
     if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
     const int cnt = (int)min((int64_t)32, c.B - e0);
-    uint32_t* const wbase = smem + (size_t)warp * a.sm_warp_words;
+    uint32_t* const wbase = smem + kLutWords + (size_t)warp * a.sm_warp_words;
+    const uint32_t* const lut = smem;                // nibble -> float4 table, first kLutWords words of the CTA's shared memory
+    if (a.obs) lut_fill(smem, lane);
     typedef SmWords<kStride> Wd;
     const int64_t env = e0 + lane;
     const bool live = lane < cnt;
@@ -515,8 +583,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_step(const __grid_constan
                     else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
                     if (coin) {
                         if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; }
-                        else if (invert_matrix(c, S, SCR, SCR.at(c.SW))) flags ^= FL_INVERTED;
-                        else err |= QG_FLAG_SINGULAR;
+                        else {
+                            bool inverted;
+                            if constexpr (INV == 0) inverted = invert_matrix(c, S, SCR, SCR.at(c.SW));
+                            else if (KIND == QG_ENV_CLIFFORD && a.symplectic) { symplectic_invert_rows<INV>(S, c.n); inverted = true; }
+                            else inverted = gf2_invert_rows<INV>(S, c.D);
+                            if (inverted) flags ^= FL_INVERTED; else err |= QG_FLAG_SINGULAR;
+                        }
                     }
                 }
                 success = (KIND == QG_ENV_PAULI_NETWORK) ? pn_solved(c, S, pr) : solved_state<KIND>(c, S);
@@ -561,7 +634,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_step(const __grid_constan
         // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab --------
         if (a.obs) {
             float* out = a.obs + ((size_t)slot * c.B + (size_t)e0) * c.obs_size;
-            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs);
+            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r);
             else {
                 // large Permutation (no room for a bit stream in shared memory): one-hot test straight from the packed bytes
                 const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, n = (uint32_t)c.n;
@@ -752,54 +825,6 @@ __global__ void __launch_bounds__(EPC) k_reset_pauli(const __grid_constant__ Dev
     put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
     put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
     put(HD_TICK, 0);
-}
-
-// ---- small readers -----------------------------------------------------------------------------------
-__global__ void k_read_status(const __grid_constant__ DevCfg c, float* reward, uint8_t* done, uint8_t* success, int32_t* depth) {
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= c.B) return;
-    const uint32_t d = c.rec[(size_t)HD_DEPTH * c.Bpad + env], f = c.rec[(size_t)HD_FLAGS * c.Bpad + env];
-    if (reward) reward[env] = __uint_as_float(c.rec[(size_t)HD_REWARD * c.Bpad + env]);
-    if (done) done[env] = (d == 0 || (f & FL_SUCCESS)) ? 1 : 0;
-    if (success) success[env] = (f & FL_SUCCESS) ? 1 : 0;
-    if (depth) depth[env] = (int32_t)d;
-}
-__global__ void k_read_metrics(const __grid_constant__ DevCfg c, uint32_t* out) {
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= c.B) return;
-    const uint32_t l = c.rec[(size_t)HD_LAYERS * c.Bpad + env];
-    reinterpret_cast<uint4*>(out)[env] = make_uint4(c.rec[(size_t)HD_NCNOTS * c.Bpad + env], l >> 16, l & 0xFFFFu, c.rec[(size_t)HD_NGATES * c.Bpad + env]);
-}
-__global__ void k_read_errors(const __grid_constant__ DevCfg c, uint32_t* out) {
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= c.B) return;
-    out[env] = (c.rec[(size_t)HD_FLAGS * c.Bpad + env] >> FL_ERR_SHIFT) & 0xFFu;
-}
-__global__ void k_fill_f32(float* p, int64_t n, float v) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-__global__ void k_copy_f32(const float* src, float* dst, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[i];
-}
-
-// ---- best-rollout reduction (synth search): arg-max of a packed key ----------------------------------
-// key = success<<62 | orderable_u32(return)<<30 | (2^30-1 - global rollout id)
-__device__ __forceinline__ unsigned long long rollout_key(bool success, float ret, int64_t gid) {
-    uint32_t u = __float_as_uint(ret);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving map f32 -> u32
-    return ((unsigned long long)(success ? 1 : 0) << 62) | ((unsigned long long)u << 30) | (unsigned long long)((0x3FFFFFFFll - gid) & 0x3FFFFFFFll);
-}
-__global__ void k_best(const __grid_constant__ DevCfg c, unsigned long long* best) {
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long key = 0;
-    if (env < c.B) {
-        const uint32_t f = c.rec[(size_t)HD_FLAGS * c.Bpad + env];
-        key = rollout_key((f & FL_SUCCESS) != 0, c.ret[env], c.first_id + env);
-    }
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o); key = other > key ? other : key; }
-    if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
 }
 
 }  // namespace qg

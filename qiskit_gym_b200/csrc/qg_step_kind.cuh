@@ -1,0 +1,68 @@
+// qg_step_kind.cuh — definitions behind qg_launch.hpp; included by the per-kind translation units only.
+#pragma once
+#include "qg_launch.hpp"
+
+namespace qg {
+
+template <int KIND, int MODE, int INV>
+cudaError_t launch_one(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, cudaStream_t st) {
+    // programmatic dependent launch: the grid may start while its predecessor in the stream drains; the kernel
+    // waits (griddepcontrol.wait) before it touches the records
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(g.grid); lc.blockDim = dim3(kWarpsPerCta * 32); lc.dynamicSmemBytes = g.smem_bytes; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV>, c, a);
+}
+
+constexpr bool kind_has_matrix_inverse(int kind) { return kind == QG_ENV_LINEAR_FUNCTION || kind == QG_ENV_CLIFFORD; }
+
+template <int KIND, int MODE>
+cudaError_t launch_mode(int inv, const DevCfg& c, const StepArgs& a, const LaunchGeom& g, cudaStream_t st) {
+    if constexpr (kind_has_matrix_inverse(KIND) && MODE != MODE_OBSERVE) {
+        switch (inv) {
+            case 8: return launch_one<KIND, MODE, 8>(c, a, g, st);
+            case 16: return launch_one<KIND, MODE, 16>(c, a, g, st);
+            case 32: return launch_one<KIND, MODE, 32>(c, a, g, st);
+            default: break;
+        }
+    }
+    return launch_one<KIND, MODE, 0>(c, a, g, st);
+}
+
+template <int KIND>
+cudaError_t launch_step_kind(int mode, int inv, const DevCfg& c, const StepArgs& a, const LaunchGeom& g, cudaStream_t st) {
+    switch (mode) {
+        case MODE_STEP: return launch_mode<KIND, MODE_STEP>(inv, c, a, g, st);
+        case MODE_SEARCH: return launch_mode<KIND, MODE_SEARCH>(inv, c, a, g, st);
+        default: return launch_mode<KIND, MODE_OBSERVE>(0, c, a, g, st);
+    }
+}
+
+template <int KIND, int MODE, int INV>
+cudaError_t prepare_one(size_t smem_bytes) {
+    return cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+}
+
+template <int KIND>
+cudaError_t prepare_step_kind(size_t smem_bytes) {
+    cudaError_t e = prepare_one<KIND, MODE_STEP, 0>(smem_bytes);
+    if (e == cudaSuccess) e = prepare_one<KIND, MODE_OBSERVE, 0>(smem_bytes);
+    if (e == cudaSuccess) e = prepare_one<KIND, MODE_SEARCH, 0>(smem_bytes);
+    if constexpr (kind_has_matrix_inverse(KIND)) {
+        if (e == cudaSuccess) e = prepare_one<KIND, MODE_STEP, 8>(smem_bytes);
+        if (e == cudaSuccess) e = prepare_one<KIND, MODE_STEP, 16>(smem_bytes);
+        if (e == cudaSuccess) e = prepare_one<KIND, MODE_STEP, 32>(smem_bytes);
+        if (e == cudaSuccess) e = prepare_one<KIND, MODE_SEARCH, 8>(smem_bytes);
+        if (e == cudaSuccess) e = prepare_one<KIND, MODE_SEARCH, 16>(smem_bytes);
+        if (e == cudaSuccess) e = prepare_one<KIND, MODE_SEARCH, 32>(smem_bytes);
+    }
+    return e;
+}
+
+#define QG_INSTANTIATE_KIND(KIND)                                                                                              \
+    template cudaError_t launch_step_kind<KIND>(int, int, const DevCfg&, const StepArgs&, const LaunchGeom&, cudaStream_t);    \
+    template cudaError_t prepare_step_kind<KIND>(size_t);
+
+}  // namespace qg

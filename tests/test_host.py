@@ -137,3 +137,67 @@ def test_workload_generators_are_seeded_and_valid():
                 # scrambled matrices stay invertible: reachable from identity by gates
                 m = np.array(env.raw_state()).reshape(int(np.sqrt(len(env.raw_state()))), -1)
                 assert round(abs(np.linalg.det(m.astype(float)))) % 2 == 1
+
+
+def _gf2_probe():
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = os.path.join(here, "_gf2_probe.so")
+    srcs = [os.path.join(here, "gf2_probe.cpp"), os.path.join(here, "..", "qiskit_gym_b200", "csrc", "qg_gf2.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, srcs[0]])
+    return C.CDLL(out)
+
+
+def _pack_rows(M):
+    D = M.shape[0]
+    bits = M.reshape(-1).astype(np.uint8)
+    words = np.zeros((D * D + 31) // 32 + 1, dtype=np.uint32)
+    for i in np.nonzero(bits)[0]:
+        words[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    return words
+
+
+def _unpack_rows(words, D):
+    return np.array([(int(words[i >> 5]) >> (i & 31)) & 1 for i in range(D * D)], dtype=np.uint8).reshape(D, D)
+
+
+def test_register_gauss_jordan_and_symplectic_inverse_match_numpy():
+    """csrc/qg_gf2.cuh (the add_inverts inverse of LinearFunction / Clifford, linear_function.rs:124-146, clifford.rs:147-170)
+    compiled for the host: equal to an independent numpy Gauss-Jordan for every size a bucket covers; singular matrices are
+    reported and left untouched."""
+    from qiskit_gym_b200 import wire
+    P = _gf2_probe()
+    rng = np.random.default_rng(2)
+    for dmax, sizes in ((8, (1, 2, 5, 8)), (16, (3, 9, 12, 16)), (32, (7, 17, 24, 31, 32))):
+        for D in sizes:
+            done = 0
+            while done < 12:
+                M = rng.integers(0, 2, size=(D, D), dtype=np.uint8)
+                w = _pack_rows(M); w0 = w.copy()
+                rc = P.probe_gauss_jordan(dmax, D, w.ctypes.data_as(C.c_void_p))
+                try:
+                    want = wire.gf2_inverse(M)
+                except ValueError:
+                    assert rc == 0 and np.array_equal(w, w0)
+                    if D > 4:
+                        continue
+                    done += 1
+                    continue
+                assert rc == 1 and np.array_equal(_unpack_rows(w, D), want), (dmax, D)
+                done += 1
+    for dmax, ns in ((8, (1, 2, 4)), (16, (3, 5, 8)), (32, (6, 11, 16))):
+        for n in ns:
+            for _ in range(8):
+                gates = []
+                for _k in range(6 * n):
+                    g = ("h", "s", "cx")[int(rng.integers(3))]
+                    if g == "cx" and n > 1:
+                        a, b = rng.choice(n, size=2, replace=False)
+                        gates.append((g, (int(a), int(b))))
+                    elif g != "cx":
+                        gates.append((g, (int(rng.integers(n)),)))
+                F = wire.StabilizerTableau.from_gates(gates, n).symplectic()
+                w = _pack_rows(F)
+                assert P.probe_symplectic(dmax, n, w.ctypes.data_as(C.c_void_p)) == 1
+                assert np.array_equal(_unpack_rows(w, 2 * n), wire.gf2_inverse(F)), (dmax, n)
