@@ -134,6 +134,12 @@ QG_API int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride
  * draws the same stream as an unsharded one. */
 QG_API int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream);
 
+/* Env::reset restricted to some envs: select_dev uint8[B] (non-zero = reset this env) or NULL = every env whose
+ * is_final() holds (depth == 0 or success), which is what a rollout collector does between episodes (twisterl's
+ * collectors clone + reset one env per episode; rl/configs.py:133-137 sizes them).  Same Philox streams as qg_reset,
+ * so a collector passes a fresh seed per call.  Untouched envs keep their state. */
+QG_API int qg_reset_select(qg_engine* e, uint64_t seed, int64_t first_env_id, const uint8_t* select_dev, qg_stream stream);
+
 /* `Clone` of the whole batch (the reference clones one prototype env per episode / rollout,
  * permutation.rs:29, linear_function.rs:154, clifford.rs:179, pauli.rs:307-337): qg_snapshot keeps a
  * device copy of every env record; qg_restore puts it back (solutions restart at the snapshot's length). */
@@ -206,6 +212,27 @@ QG_API int qg_search_step(qg_engine* e, const float* weights_dev, int32_t determ
  * *best_key_host and the winner's local env index to *best_env_host (-1 if B == 0). */
 QG_API int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream);
 QG_API int qg_read_returns(qg_engine* e, float* returns_dev, qg_stream stream);
+
+/* ---- rollout collector pieces (the data-collection half of twisterl's PPO loop) ------------- */
+/* qg_search_step that also reports the step's reward / is_final / success per env (entries of envs that were already
+ * final, chosen = -1, are left untouched) and takes the Philox seed of this decision explicitly: the action sample of
+ * env i is drawn from (seed; first_env_id + i, env's step counter, sample stream). */
+QG_API int qg_collect_step(qg_engine* e, uint64_t seed, const float* weights_dev, int32_t deterministic,
+                           float* obs_dev, uint8_t* mask_dev, int32_t* chosen_dev,
+                           float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
+/* Generalised advantage estimation over a rollout laid out [num_steps][batch] (value_dev has num_steps + 1 rows, the
+ * last one bootstraps the truncated episodes):  nd = !done[t];  delta = (reward[t] + (gamma*value[t+1])*nd) - value[t];
+ * adv[t] = delta + ((gamma*lambda)*nd)*adv[t+1];  ret[t] = adv[t] + value[t]  — f32, every operation rounded on its
+ * own in that order.  valid_dev (uint8, may be NULL): 0 marks a slot where the env was not stepped (adv = ret = 0).
+ * Needs no engine: plain device pointers. */
+QG_API int qg_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, const uint8_t* valid_dev,
+                  int32_t num_steps, int64_t batch, float gamma, float lambda, float* adv_dev, float* ret_dev, qg_stream stream);
+/* Twists on the device (Env::twists, symmetry.rs:297-361): out[b][j] = in[b][table[index[b]][j]] for an int32 table
+ * [K][len] and a per-env twist index int32[B] (NULL = twist 0).  With the inverse of obs_perms[k] this is the twisted
+ * observation (entry i moves to obs_perms[k][i]); with act_perms[k] it brings the policy's action weights back into
+ * the env's action order. */
+QG_API int qg_twist_gather(const float* in_dev, float* out_dev, const int32_t* table_dev, const int32_t* index_dev,
+                           int64_t batch, int32_t len, qg_stream stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ SYMBOLS = [
     "qg_batch", "qg_num_actions", "qg_obs_size", "qg_obs_shape", "qg_set_difficulty", "qg_get_difficulty",
     "qg_set_state", "qg_reset", "qg_snapshot", "qg_restore", "qg_step", "qg_replay", "qg_replay_host", "qg_step_host", "qg_observe", "qg_masks", "qg_read_status",
     "qg_read_metrics", "qg_read_errors", "qg_get_state_host", "qg_solution_host", "qg_search_begin",
-    "qg_search_step", "qg_search_best", "qg_read_returns",
+    "qg_search_step", "qg_search_best", "qg_read_returns", "qg_reset_select", "qg_collect_step", "qg_gae", "qg_twist_gather",
 ]
 
 
@@ -100,6 +100,10 @@ def lib():
     L.qg_search_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.qg_search_best.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp]
     L.qg_read_returns.argtypes = [vp, vp, vp]
+    L.qg_reset_select.argtypes = [vp, u64, i64, vp, vp]
+    L.qg_collect_step.argtypes = [vp, u64, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.qg_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
+    L.qg_twist_gather.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     _lib = L
     return L
 

@@ -52,4 +52,47 @@ __global__ void k_best(const __grid_constant__ DevCfg c, unsigned long long* bes
     if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
 }
 
+// ---- rollout-collector helpers ------------------------------------------------------------------------
+// Generalised advantage estimation over a [T][B] rollout, one thread per environment walking its column backwards
+// (every load / store of a warp is one coalesced row segment).  Each product and sum is rounded on its own, in the
+// order written, so the CPU restatement matches bit for bit:
+//     nd      = done[t] ? 0 : 1
+//     delta   = (reward[t] + (gamma * value[t+1]) * nd) - value[t]
+//     adv[t]  = delta + ((gamma * lambda) * nd) * adv[t+1]          (adv[T] = 0)
+//     ret[t]  = adv[t] + value[t]
+// A step with valid[t] == 0 (the env was already final at decision time and was not stepped) yields adv = ret = 0 and
+// cuts the recursion like an episode end.
+__global__ void k_gae(const float* __restrict__ reward, const float* __restrict__ value, const uint8_t* __restrict__ done,
+                      const uint8_t* __restrict__ valid, int T, int64_t B, float gamma, float lambda, float* __restrict__ adv, float* __restrict__ ret) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float gl = __fmul_rn(gamma, lambda);
+    float next_v = value[(size_t)T * B + b], next_adv = 0.0f;
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t k = (size_t)t * B + b;
+        const float v = value[k];
+        if (valid && !valid[k]) { adv[k] = 0.0f; if (ret) ret[k] = 0.0f; next_adv = 0.0f; next_v = v; continue; }
+        const float nd = done[k] ? 0.0f : 1.0f;
+        const float delta = __fsub_rn(__fadd_rn(reward[k], __fmul_rn(__fmul_rn(gamma, next_v), nd)), v);
+        const float a = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nd), next_adv));
+        adv[k] = a;
+        if (ret) ret[k] = __fadd_rn(a, v);
+        next_adv = a; next_v = v;
+    }
+}
+
+// Twists (symmetry.rs:297-361) applied on the device: out[b][j] = in[b][table[k[b]][j]] for a [K][len] index table.
+// With the inverse of obs_perms it produces the twisted observation (index i of the observation moves to
+// obs_perms[k][i]); with act_perms it maps the policy's action weights back to the environment's action order.
+__global__ void k_twist_gather(const float* __restrict__ in, float* __restrict__ out, const int32_t* __restrict__ table,
+                               const int32_t* __restrict__ kidx, int64_t B, int len, uint64_t magic_len) {
+    const int64_t total = B * (int64_t)len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = magic_len ? (int64_t)__umul64hi((uint64_t)i, magic_len) : i;   // magic_len = ceil(2^64 / len), 0 for len == 1
+        const int j = (int)(i - b * len);
+        const int32_t k = kidx ? kidx[b] : 0;
+        out[i] = in[b * len + table[(size_t)k * len + j]];
+    }
+}
+
 }  // namespace qg

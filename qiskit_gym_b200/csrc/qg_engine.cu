@@ -378,28 +378,39 @@ int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride, int64
     return QG_OK;
 }
 
-int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream) {
-    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+namespace {
+int launch_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, int which, const uint8_t* select_dev, cudaStream_t st) {
     CUDA_OK(cudaSetDevice(e->device));
     e->dc.seed = seed; e->dc.first_id = first_env_id;
     if (e->B == 0) return QG_OK;
-    cudaStream_t st = (cudaStream_t)stream;
     if (e->L.kind == QG_ENV_PAULI_NETWORK) {
         const int words = e->L.SW + e->L.XW + 3 * e->L.Rtot;
         const int fl = e->cfg.final_pauli_layers >= 0 ? e->cfg.final_pauli_layers : e->cfg.max_rotations + 2;
-        k_reset_pauli<32><<<(unsigned)((e->B + 31) / 32), 32, (size_t)words * 32 * 4, st>>>(e->dc, std::max(e->cfg.pauli_diff_scale, 1), e->cfg.num_qubits_decay, fl);
+        k_reset_pauli<32><<<(unsigned)((e->B + 31) / 32), 32, (size_t)words * 32 * 4, st>>>(e->dc, std::max(e->cfg.pauli_diff_scale, 1), e->cfg.num_qubits_decay, fl,
+                                                                                              which, select_dev);
         CUDA_OK(cudaGetLastError());
         return QG_OK;
     }
     const unsigned grid = (unsigned)((e->B + 63) / 64);
     const size_t sm = (size_t)e->L.SW * 64 * 4;
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: k_reset<QG_ENV_PERMUTATION, 64><<<grid, 64, sm, st>>>(e->dc); break;
-        case QG_ENV_LINEAR_FUNCTION: k_reset<QG_ENV_LINEAR_FUNCTION, 64><<<grid, 64, sm, st>>>(e->dc); break;
-        default: k_reset<QG_ENV_CLIFFORD, 64><<<grid, 64, sm, st>>>(e->dc); break;
+        case QG_ENV_PERMUTATION: k_reset<QG_ENV_PERMUTATION, 64><<<grid, 64, sm, st>>>(e->dc, which, select_dev); break;
+        case QG_ENV_LINEAR_FUNCTION: k_reset<QG_ENV_LINEAR_FUNCTION, 64><<<grid, 64, sm, st>>>(e->dc, which, select_dev); break;
+        default: k_reset<QG_ENV_CLIFFORD, 64><<<grid, 64, sm, st>>>(e->dc, which, select_dev); break;
     }
     CUDA_OK(cudaGetLastError());
     return QG_OK;
+}
+}  // namespace
+
+int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    return launch_reset(e, seed, first_env_id, RESET_ALL, nullptr, (cudaStream_t)stream);
+}
+
+int qg_reset_select(qg_engine* e, uint64_t seed, int64_t first_env_id, const uint8_t* select_dev, qg_stream stream) {
+    if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
+    return launch_reset(e, seed, first_env_id, select_dev ? RESET_SELECT : RESET_FINAL, select_dev, (cudaStream_t)stream);
 }
 
 int qg_snapshot(qg_engine* e, qg_stream stream) {
@@ -591,6 +602,38 @@ int qg_search_step(qg_engine* e, const float* weights_dev, int32_t deterministic
     if (num_active_dev) CUDA_OK(cudaMemsetAsync(num_active_dev, 0, 4, st));
     StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs = obs_dev; a.mask = mask_dev; a.chosen = chosen_dev; a.num_active = num_active_dev;
     return launch_step(e, MODE_SEARCH, a, st);
+}
+
+int qg_collect_step(qg_engine* e, uint64_t seed, const float* weights_dev, int32_t deterministic, float* obs_dev, uint8_t* mask_dev, int32_t* chosen_dev,
+                    float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !weights_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    e->dc.seed = seed;
+    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs = obs_dev; a.mask = mask_dev; a.chosen = chosen_dev;
+    a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    return launch_step(e, MODE_SEARCH, a, (cudaStream_t)stream);
+}
+
+int qg_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, const uint8_t* valid_dev, int32_t num_steps, int64_t batch,
+           float gamma, float lambda, float* adv_dev, float* ret_dev, qg_stream stream) {
+    if (!reward_dev || !value_dev || !done_dev || !adv_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (num_steps < 0 || batch < 0) { set_error("qg_gae: negative size"); return QG_ERR_INVALID; }
+    if (num_steps == 0 || batch == 0) return QG_OK;
+    k_gae<<<(unsigned)((batch + 127) / 128), 128, 0, (cudaStream_t)stream>>>(reward_dev, value_dev, done_dev, valid_dev, num_steps, batch, gamma, lambda, adv_dev, ret_dev);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
+}
+
+int qg_twist_gather(const float* in_dev, float* out_dev, const int32_t* table_dev, const int32_t* index_dev, int64_t batch, int32_t len, qg_stream stream) {
+    if (!in_dev || !out_dev || !table_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (batch < 0 || len <= 0) { set_error("qg_twist_gather: bad size"); return QG_ERR_INVALID; }
+    if (in_dev == out_dev) { set_error("qg_twist_gather cannot run in place"); return QG_ERR_INVALID; }
+    if (batch == 0) return QG_OK;
+    const uint64_t magic = len == 1 ? 0ull : (~0ull / (uint64_t)len) + 1ull;   // ceil(2^64 / len) for len that is not a power of two, exact enough: see k_twist_gather
+    const int64_t total = batch * (int64_t)len;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    k_twist_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(in_dev, out_dev, table_dev, index_dev, batch, len, magic);
+    CUDA_OK(cudaGetLastError());
+    return QG_OK;
 }
 
 int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream) {

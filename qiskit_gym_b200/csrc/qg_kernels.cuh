@@ -343,7 +343,28 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     const uint32_t* const lut_lane = lut + ((lane & 7) << 2);
     float4* const out4 = reinterpret_cast<float4*>(out);
-    if (vec_ok && (obs & 31u) == 0) {
+    if (vec_ok && (obs & 127u) == 0) {
+        // whole 512-byte warp stores per environment: lane l always holds nibble (l & 7) of words (l >> 3) + 4k of the current
+        // environment, so the loop is one LDS (broadcast within a quarter warp) + shift + table load + store per 512 bytes
+        const uint32_t K = obs >> 7, VPE = obs >> 2, sh = ((uint32_t)lane & 7u) << 2;
+        const uint32_t* src = bits + ((uint32_t)lane >> 3) * kStride;
+        float4* o = out4 + lane;
+        if (K == 2) {
+#pragma unroll 4
+            for (uint32_t e = 0; e < cnt; ++e, o += 64) {
+                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+                const uint32_t w0 = src[e], w1 = src[4 * kStride + e];
+                st_slab(o, lut_get(lut_lane, (w0 >> sh) & 15u));
+                st_slab(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u));
+            }
+        } else {
+            for (uint32_t e = 0; e < cnt; ++e, o += VPE) {
+                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+#pragma unroll 4
+                for (uint32_t k = 0; k < K; ++k) st_slab(o + (k << 5), lut_get(lut_lane, (src[(k << 2) * kStride + e] >> sh) & 15u));
+            }
+        }
+    } else if (vec_ok && (obs & 31u) == 0) {
         // whole words per environment: a lane's nibble position inside its word never changes (r4 is a multiple of 8)
         const uint32_t VPE = obs >> 2, total = cnt * VPE, sh = ((uint32_t)lane & 7u) << 2;
         uint32_t e = (VPE == 1) ? (uint32_t)lane : __umulhi((uint32_t)lane, magic_obs4), v = (uint32_t)lane - e * VPE;
@@ -501,11 +522,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
     bool dirty = false;                              // records changed: write them back at the end
     int slot = a.slot0;                              // observation / mask ring slot of this step
 
+    // replay: the next step's action (and coin) is requested before this step's expansion, so its DRAM latency is hidden
+    int next_action = -1; uint32_t next_coin = 0;
+    if (MODE == MODE_STEP && live) {
+        next_action = a.actions[env];
+        if (a.coins) next_coin = a.coins[env];
+    }
     for (int t = 0; t < a.nsteps; ++t) {
         bool success = (flags & FL_SUCCESS) != 0, enabled = live;
+        const uint32_t coin_in = next_coin;
         if (live) {
             int action = -1;
-            if (MODE == MODE_STEP) action = a.actions[(size_t)t * a.in_stride + env];
+            if (MODE == MODE_STEP) {
+                action = next_action;
+                if (t + 1 < a.nsteps) {
+                    next_action = a.actions[(size_t)(t + 1) * a.in_stride + env];
+                    if (a.coins) next_coin = a.coins[(size_t)(t + 1) * a.in_stride + env];
+                }
+            }
             if (MODE == MODE_SEARCH) {
                 // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
                 enabled = !(depth == 0 || success);
@@ -579,7 +613,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
                 depth = depth > 0 ? depth - 1 : 0;              // saturating_sub
                 if (KIND != QG_ENV_PAULI_NETWORK && c.add_inverts) {
                     bool coin;
-                    if (a.coins) coin = a.coins[(size_t)t * a.in_stride + env] != 0;
+                    if (a.coins) coin = (MODE == MODE_STEP) ? (coin_in != 0) : (a.coins[(size_t)t * a.in_stride + env] != 0);
                     else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
                     if (coin) {
                         if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; }
@@ -700,12 +734,22 @@ __global__ void k_load(const __grid_constant__ DevCfg c, const uint32_t* __restr
 
 // ---- reset (Permutation / LinearFunction / Clifford): identity scrambled by `difficulty` Philox-drawn gates
 // (permutation.rs:175-192, linear_function.rs:285-300, clifford.rs:306-319) --------------------------
+// which environments a reset touches: RESET_ALL, RESET_FINAL (those whose is_final() holds: what a collector does between
+// episodes) or RESET_SELECT (select[env] != 0)
+enum { RESET_ALL = 0, RESET_FINAL = 1, RESET_SELECT = 2 };
+__device__ __forceinline__ bool reset_wanted(const DevCfg& c, int64_t env, int which, const uint8_t* select) {
+    if (which == RESET_SELECT) return select[env] != 0;
+    if (which == RESET_FINAL) return c.rec[(size_t)HD_DEPTH * c.Bpad + env] == 0 || (c.rec[(size_t)HD_FLAGS * c.Bpad + env] & FL_SUCCESS) != 0;
+    return true;
+}
+
 template <int KIND, int EPC>
-__global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c) {
+__global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c, int which, const uint8_t* __restrict__ select) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x;
     const int64_t env = (int64_t)blockIdx.x * EPC + tid;
     if (env >= c.B) return;
+    if (!reset_wanted(c, env, which, select)) return;
     typedef SmWords<EPC> Wd;
     const Wd S{smem + tid};
     if (KIND == QG_ENV_PERMUTATION) { for (int w = 0; w < c.SW; ++w) S[w] = 0; for (int q = 0; q < c.n; ++q) set8(S, q, (uint32_t)q); }
@@ -726,6 +770,7 @@ __global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c)
     put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
     put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
     put(HD_TICK, 0);
+    c.ret[env] = 0.0f;
 }
 
 // ---- PauliNetwork reset (pauli.rs:554-586): rotations from generate_paulis_with_difficulty (115-213), tableau from
@@ -733,11 +778,13 @@ __global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c)
 // (draw index = running counter), in the order the reference code makes them.
 // gen tables (c.pgen): [0]=ND, [1]=NP, [2]=NCX, dists[ND] ascending, pair_off[ND+1], pairs[NP] (q1 | q2<<8, q1<q2), cx[NCX] (q0 | q1<<8)
 template <int EPC>
-__global__ void __launch_bounds__(EPC) k_reset_pauli(const __grid_constant__ DevCfg c, int pauli_diff_scale, float decay, int final_layers) {
+__global__ void __launch_bounds__(EPC) k_reset_pauli(const __grid_constant__ DevCfg c, int pauli_diff_scale, float decay, int final_layers, int which,
+                                                      const uint8_t* __restrict__ select) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x;
     const int64_t env = (int64_t)blockIdx.x * EPC + tid;
     if (env >= c.B) return;
+    if (!reset_wanted(c, env, which, select)) return;
     typedef SmWords<EPC> Wd;
     const Wd S{smem + tid}, X = S.at(c.SW), RX = X.at(c.W - c.off_extra), RZ = RX.at(c.Rtot), HV = RZ.at(c.Rtot);
     const int n = c.n, D = 2 * n;
@@ -825,6 +872,7 @@ __global__ void __launch_bounds__(EPC) k_reset_pauli(const __grid_constant__ Dev
     put(HD_NCNOTS, 0); put(HD_NGATES, 0); put(HD_LAYERS, 0);
     put(HD_REWARD, __float_as_uint(ok ? 1.0f : 0.0f));
     put(HD_TICK, 0);
+    c.ret[env] = 0.0f;
 }
 
 }  // namespace qg

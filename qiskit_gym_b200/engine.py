@@ -124,6 +124,11 @@ class BatchedEnv:
     def reset(self, seed: int = 0, first_env_id: int = 0):
         check(lib().qg_reset(self._h, C.c_uint64(seed & (2**64 - 1)), first_env_id, self._stream()))
 
+    def reset_select(self, seed: int = 0, first_env_id: int = 0, select: torch.Tensor | None = None):
+        """Env::reset for the envs flagged in `select` (bool/uint8 [B]) or, with select=None, for every env that is final."""
+        assert select is None or (select.is_cuda and select.numel() == self.batch and select.element_size() == 1)
+        check(lib().qg_reset_select(self._h, C.c_uint64(seed & (2**64 - 1)), first_env_id, _dptr(select), self._stream()))
+
     def snapshot(self):
         """Clone of the whole batch (device copy of every env record)."""
         check(lib().qg_snapshot(self._h, self._stream()))
@@ -243,6 +248,19 @@ class BatchedEnv:
         obs_t = self.obs if obs is True else (None if obs is False else obs)
         check(lib().qg_search_step(self._h, _dptr(weights), 1 if deterministic else 0, _dptr(obs_t), None, _dptr(chosen),
                                    _dptr(num_active), self._stream()))
+        return obs_t
+
+    def collect_step(self, weights: torch.Tensor, seed: int, deterministic: bool = False, obs: torch.Tensor | None | bool = True,
+                     mask: torch.Tensor | None | bool = None, chosen: torch.Tensor | None = None, reward: torch.Tensor | None = None,
+                     done: torch.Tensor | None = None, success: torch.Tensor | None = None):
+        """Collector decision step (qg_collect_step): sample / arg-max from the action weights, fused env step, and the step's
+        reward / is_final / success written per env (untouched for envs that were already final: chosen = -1)."""
+        assert weights.dtype == torch.float32 and weights.is_cuda and weights.is_contiguous()
+        obs_t = self.obs if obs is True else (None if obs is False else obs)
+        mask_t = self.mask if mask is True else (None if mask is False else mask)
+        check(lib().qg_collect_step(self._h, C.c_uint64(seed & (2**64 - 1)), _dptr(weights), 1 if deterministic else 0, _dptr(obs_t), _dptr(mask_t),
+                                    _dptr(chosen), _dptr(self.reward if reward is None else reward), _dptr(self.done if done is None else done),
+                                    _dptr(self.success if success is None else success), self._stream()))
         return obs_t
 
     def search_best(self):
