@@ -14,9 +14,10 @@
 //   Permutation     n bytes, 4 per word                               (permutation.rs:30  Vec<usize>)
 //   LinearFunction  dense bit stream, entry (r,c) at bit r*n+c         (linear_function.rs:29-33, one byte per bit there)
 //   Clifford        dense bit stream, entry (r,c) at bit r*2n+c        (clifford.rs:28-31)
-//   PauliNetwork    dense bit stream of 2n rows x CW bits, CW = 2n+Rtot; columns 2n.. hold the rotations'
-//                   (x|z) vectors, which keep evolving after a rotation is harvested exactly like
-//                   PauliNetwork::rotation_qk does (pauli_network.rs:189-223); `alive` masks them.
+//   PauliNetwork    2n rows of CW bits, CW = 2n+Rtot rounded up to whole words (a row operation is one word
+//                   operation per row word); columns 2n.. hold the rotations' (x|z) vectors, which keep evolving
+//                   after a rotation is harvested exactly like PauliNetwork::rotation_qk does
+//                   (pauli_network.rs:189-223); `alive` masks them.
 // For LinearFunction/Clifford the state bit stream IS the observation bit stream (observe() lists the
 // set bits in row-major order, clifford.rs:361-368), so the observation expander reads it directly.
 #pragma once

@@ -73,7 +73,7 @@ int make_layout(const qg_config* cfg, Layout& L) {
             L.max_rot = std::max(cfg->max_rotations, 1);                                     // pauli.rs:388
             const int fl = cfg->final_pauli_layers >= 0 ? cfg->final_pauli_layers : cfg->max_rotations + 2;
             L.Rtot = std::max(L.max_rot, fl);
-            L.D = 2 * n; L.CW = 2 * n + L.Rtot;
+            L.D = 2 * n; L.CW = (2 * n + L.Rtot + 31) / 32 * 32;     // row stride in bits: rows are padded to whole words
             L.obs_rows = 2 * n; L.obs_cols = 2 * n + L.max_rot;
             L.SW = (2 * n * L.CW + 31) / 32;
             L.XW = PX_ANTI + (L.Rtot + 1) / 2;

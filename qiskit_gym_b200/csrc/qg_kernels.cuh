@@ -151,6 +151,9 @@ __device__ void invert_perm(const DevCfg& c, const Wd& S, const Wd& T) {
 }
 
 // ---- PauliNetwork ----------------------------------------------------------------------------------
+// Rows of the 2n x (2n + Rtot) matrix are padded to whole 32-bit words (c.CW = row stride in bits, a multiple of 32), so a
+// row operation is one load / xor / store per row word, and the rotation part of a row (columns 2n .. 2n+Rtot) is one
+// shifted word (two when it straddles a word, which depends on the configuration only: warp-uniform).
 struct PauliRegs { uint32_t plo, phi, alive, ord0, ord1, misc; };
 __device__ __forceinline__ uint32_t ord_get(const PauliRegs& p, int i) { return ((i < 8 ? p.ord0 : p.ord1) >> ((i & 7) * 4)) & 0xFu; }
 __device__ __forceinline__ void ord_set(PauliRegs& p, int i, uint32_t v) {
@@ -159,27 +162,35 @@ __device__ __forceinline__ void ord_set(PauliRegs& p, int i, uint32_t v) {
 }
 __device__ __forceinline__ void phase_add(PauliRegs& p, uint32_t m) { const uint32_t carry = p.plo & m; p.plo ^= m; p.phi ^= carry; }
 template <class Wd>
-__device__ __forceinline__ uint32_t rot_bits(const DevCfg& c, const Wd& S, int row) { return get_bits(S, row * c.CW + 2 * c.n, c.Rtot); }
+__device__ __forceinline__ uint32_t rot_bits(const DevCfg& c, const Wd& S, int row) {
+    const int D = 2 * c.n, idx = row * (c.CW >> 5) + (D >> 5), sh = D & 31;
+    uint32_t v = S[idx] >> sh;
+    if (sh + c.Rtot > 32) v |= S[idx + 1] << (32 - sh);
+    return c.Rtot >= 32 ? v : (v & ((1u << c.Rtot) - 1u));
+}
+template <class Wd>
+__device__ __forceinline__ void pn_row_xor(const DevCfg& c, const Wd& S, int dst, int src) {
+    const int RW = c.CW >> 5;
+    for (int w = 0; w < RW; ++w) S[dst * RW + w] ^= S[src * RW + w];
+}
 
-// pauli_network.rs:189-194 (+ pauli.rs:83-90)
+// One-qubit gates as one routine with selects instead of branches, so that a warp whose lanes hold different gates runs it
+// once: H (pauli_network.rs:189-194, pauli.rs:83-90): swap rows i, n+i, phase += 2(x & z);  S / Sdg = S^3 (209-215, 229-233;
+// pauli.rs:92-97): row n+i ^= row i, phase += x or 3x;  SX / SXdg = SX^3 (217-223, 235-241; pauli.rs:105-110: H,S,H adds
+// 2xz + z + 2z(1-x) = 3z, and 9z = z): row i ^= row n+i, phase += 3z or z.
+__device__ __forceinline__ int pn_type_1q(int kind) { return kind + 1; }      // QG_H..QG_SXDG -> 1..5, 0 = none
 template <class Wd>
-__device__ __forceinline__ void pn_h(const DevCfg& c, const Wd& S, PauliRegs& p, int i) {
-    p.phi ^= rot_bits(c, S, i) & rot_bits(c, S, c.n + i);
-    row_swap(S, c.CW, i, c.n + i);
-}
-// pauli_network.rs:209-215 (+ pauli.rs:92-97); times = 1 (S) or 3 (Sdg = S^3, pauli_network.rs:229-233)
-template <class Wd>
-__device__ __forceinline__ void pn_s(const DevCfg& c, const Wd& S, PauliRegs& p, int i, bool thrice) {
-    const uint32_t x = rot_bits(c, S, i);
-    phase_add(p, x); if (thrice) p.phi ^= x;          // +x or +3x (mod 4)
-    row_xor(S, c.CW, c.n + i, i);                      // xor applied once or three times is the same matrix
-}
-// pauli_network.rs:217-223 (+ pauli.rs:105-110: H,S,H adds 2xz + z + 2z(1-x) = 3z); SXdg = SX^3 adds 9z = z
-template <class Wd>
-__device__ __forceinline__ void pn_sx(const DevCfg& c, const Wd& S, PauliRegs& p, int i, bool thrice) {
-    const uint32_t z = rot_bits(c, S, c.n + i);
-    phase_add(p, z); if (!thrice) p.phi ^= z;
-    row_xor(S, c.CW, i, c.n + i);
+__device__ __forceinline__ void pn_1q(const DevCfg& c, const Wd& S, PauliRegs& p, int type, int i) {
+    const bool isH = type == 1, isS = type == 2 || type == 3, isSX = type == 4 || type == 5;
+    const uint32_t x = rot_bits(c, S, i), z = rot_bits(c, S, c.n + i);
+    phase_add(p, isS ? x : (isSX ? z : 0u));
+    p.phi ^= isH ? (x & z) : (type == 3 ? x : (type == 4 ? z : 0u));
+    const int RW = c.CW >> 5;
+    for (int w = 0; w < RW; ++w) {
+        const uint32_t a = S[i * RW + w], b = S[(c.n + i) * RW + w];
+        S[i * RW + w] = isH ? b : (isSX ? (a ^ b) : a);
+        S[(c.n + i) * RW + w] = isH ? a : (isS ? (a ^ b) : b);
+    }
 }
 // pauli_network.rs:139-165 with the petgraph 0.6.5 retain_nodes/swap-remove node order.
 // Harvested (axis, qubit, idx) triples are appended to hv[] as axis<<21 | qubit<<11 | idx<<1.
@@ -195,9 +206,9 @@ __device__ void pn_clean(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p
         uint32_t marked = 0;                        // node positions to remove
         for (int pos = 0; pos < m; ++pos) {
             const uint32_t r = ord_get(p, pos);
+            if ((ge2 >> r) & 1u) continue;          // weight >= 2: not trivial (pauli_network.rs:83-97)
             const uint32_t anti = (X[PX_ANTI + (r >> 1)] >> ((r & 1) * 16)) & 0xFFFFu;   // earlier rotations that anticommute
             if ((anti & alive0) != 0) continue;     // has an outgoing edge: not in the front layer (pauli_dag.rs:47-57)
-            if ((ge2 >> r) & 1u) continue;          // weight >= 2: not trivial (pauli_network.rs:83-97)
             marked |= 1u << pos;
             p.alive &= ~(1u << r);                  // set_column(zeros) (pauli_network.rs:153-156)
             if (!((ones >> r) & 1u)) { err |= QG_FLAG_BAD_ROTATION; continue; }   // which_qubit().unwrap() panic in the reference
@@ -215,60 +226,82 @@ __device__ void pn_clean(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p
 // pauli_network.rs:196-207
 template <class Wd>
 __device__ __forceinline__ void pn_cnot(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p, int i, int j, const Wd& hv, int& nh, uint32_t& err) {
-    row_xor(S, c.CW, i, j);
-    row_xor(S, c.CW, c.n + j, c.n + i);
+    pn_row_xor(c, S, i, j);
+    pn_row_xor(c, S, c.n + j, c.n + i);
     pn_clean(c, S, X, p, hv, nh, err);
 }
-// pauli_network.rs:225-260
+// pauli_network.rs:225-260 as a fixed schedule  [one-qubit op] [up to three CNOTs] [one-qubit op]  instead of a switch over the
+// eight gate kinds: the lanes of a warp hold different gates, and this way the warp runs the one-qubit routine at most twice
+// and the CNOT + clean routine at most three times per step, whatever mix of gates its 32 environments drew.
+//   H/S/Sdg/SX/SXdg(q0): pre            CX(q0,q1): cnot(q0,q1)
+//   CZ(q0,q1) = h(q1), cnot(q0,q1), h(q1) (243-249)        SWAP(q0,q1) = cnot(q0,q1), cnot(q1,q0), cnot(q0,q1) (250-257)
 template <class Wd>
 __device__ void pn_act(const DevCfg& c, const Wd& S, const Wd& X, PauliRegs& p, int kind, int q0, int q1, const Wd& hv, int& nh, uint32_t& err) {
-    switch (kind) {
-        case QG_H: pn_h(c, S, p, q0); break;
-        case QG_S: pn_s(c, S, p, q0, false); break;
-        case QG_SDG: pn_s(c, S, p, q0, true); break;
-        case QG_SX: pn_sx(c, S, p, q0, false); break;
-        case QG_SXDG: pn_sx(c, S, p, q0, true); break;
-        case QG_CX: pn_cnot(c, S, X, p, q0, q1, hv, nh, err); break;
-        case QG_CZ: pn_h(c, S, p, q1); pn_cnot(c, S, X, p, q0, q1, hv, nh, err); pn_h(c, S, p, q1); break;
-        case QG_SWAP: pn_cnot(c, S, X, p, q0, q1, hv, nh, err); pn_cnot(c, S, X, p, q1, q0, hv, nh, err); pn_cnot(c, S, X, p, q0, q1, hv, nh, err); break;
+    const int pre = kind <= QG_SXDG ? pn_type_1q(kind) : (kind == QG_CZ ? 1 : 0);
+    const int pre_q = kind == QG_CZ ? q1 : q0;
+    const int ncnot = kind == QG_SWAP ? 3 : (kind == QG_CX || kind == QG_CZ ? 1 : 0);
+    if (pre) pn_1q(c, S, p, pre, pre_q);
+    for (int k = 0; k < ncnot; ++k) {
+        const bool flip = k == 1;
+        pn_cnot(c, S, X, p, flip ? q1 : q0, flip ? q0 : q1, hv, nh, err);
     }
+    if (kind == QG_CZ) pn_1q(c, S, p, 1, q1);
 }
 // pauli_network.rs:167-173
 template <class Wd>
 __device__ __forceinline__ bool pn_solved(const DevCfg& c, const Wd& S, const PauliRegs& p) {
     if ((p.misc >> 24) != 0) return false;
-    const int D = 2 * c.n;
-    for (int r = 0; r < D; ++r)
-        for (int c0 = 0; c0 < D; c0 += 32) {
-            const int len = min(32, D - c0);
-            const uint32_t want = (r >= c0 && r < c0 + len) ? (1u << (r - c0)) : 0u;
-            if (get_bits(S, r * c.CW + c0, len) != want) return false;
+    const int D = 2 * c.n, RW = c.CW >> 5;
+    uint32_t diff = 0;
+    for (int r = 0; r < D; ++r) {
+        const uint32_t lo = S[r * RW];
+        if (D <= 32) diff |= (D == 32 ? lo : (lo & ((1u << D) - 1u))) ^ (1u << r);
+        else {
+            const uint32_t hi = S[r * RW + 1] & ((1u << (D - 32)) - 1u);      // D <= 62 (2n + rotations <= 64)
+            diff |= (lo ^ (r < 32 ? (1u << r) : 0u)) | (hi ^ (r >= 32 ? (1u << (r - 32)) : 0u));
         }
-    return true;
+    }
+    return diff == 0;
 }
-// observe(): pad_and_collect (pauli.rs:411-437) + apply_perm_to_obs (445-485) -> obs bit stream O
+// observe(): pad_and_collect (pauli.rs:411-437) + apply_perm_to_obs (445-485) -> obs bit stream O, rows of obs_cols =
+// 2n + max_rotations bits written one after the other through a 64-bit accumulator.
 template <class Wd>
 __device__ void pn_build_obs(const DevCfg& c, const Wd& S, const PauliRegs& p, const Wd& O, int perm_idx) {
-    const int n = c.n, D = 2 * n, OC = c.obs_cols;
-    for (int w = 0; w < c.OW; ++w) O[w] = 0;
+    const int n = c.n, D = 2 * n, RW = c.CW >> 5;
     const int m = min((int)(p.misc >> 24), c.max_rot);
     const uint8_t* perm = (c.nperms > 0) ? (c.qperms + (size_t)perm_idx * n) : nullptr;
+    unsigned long long acc = 0; int fill = 0, ow = 0;
+    auto append = [&](uint32_t v, int len) {       // len in 1..32, v has no bits above len
+        acc |= (unsigned long long)v << fill; fill += len;
+        if (fill >= 32) { O[ow++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+    };
     for (int r = 0; r < D; ++r) {
         int src = r;
         if (perm) src = (r < n) ? (int)perm[r] : n + (int)perm[r - n];
-        const uint32_t rb = rot_bits(c, S, src);
-        uint32_t rot = 0;
-        for (int i = 0; i < m; ++i) rot |= ((rb >> ord_get(p, i)) & 1u) << i;
-        if (!perm) {
-            for (int c0 = 0; c0 < D; c0 += 32) { const int len = min(32, D - c0); xor_bits(O, r * OC + c0, len, get_bits(S, src * c.CW + c0, len)); }
-        } else {
+        const uint32_t lo = S[src * RW], hi = D > 32 ? S[src * RW + 1] : 0u;
+        uint32_t l0 = lo, l1 = hi;
+        if (perm) {                                  // tableau columns move with the qubits too (pauli.rs:470-480)
+            const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+            unsigned long long o = 0;
             for (int col = 0; col < D; ++col) {
                 const int sc = (col < n) ? (int)perm[col] : n + (int)perm[col - n];
-                if (get_bit(S, src * c.CW + sc)) xor_bits(O, r * OC + col, 1, 1u);
+                o |= ((bits >> sc) & 1ull) << col;
             }
+            l0 = (uint32_t)o; l1 = (uint32_t)(o >> 32);
         }
-        if (m > 0) xor_bits(O, r * OC + D, m, rot);
+        if (D <= 32) append(D == 32 ? l0 : (l0 & ((1u << D) - 1u)), D);
+        else { append(l0, 32); append(l1 & ((1u << (D - 32)) - 1u), D - 32); }
+        const uint32_t rb = rot_bits(c, S, src);
+        uint32_t rot = 0, ow0 = p.ord0;
+        for (int i = 0; i < m; ++i) {                // active rotations in DAG node order (pauli.rs:411-437)
+            if (i == 8) ow0 = p.ord1;
+            rot |= ((rb >> (ow0 & 15u)) & 1u) << i;
+            ow0 >>= 4;
+        }
+        append(rot, c.max_rot);
     }
+    if (fill > 0) O[ow++] = (uint32_t)acc;
+    for (; ow < c.OW; ++ow) O[ow] = 0;
 }
 
 // ---- the fused kernel ----------------------------------------------------------------------------------
