@@ -46,37 +46,37 @@ __device__ __forceinline__ uint32_t fastdiv40(uint32_t x, uint64_t magic) { retu
 
 struct Counts { uint32_t nc, ng, nl, nlc; };
 
-// metrics.rs:84-96
-template <class Wd>
-__device__ __forceinline__ void met_single(const Wd& lg, int n, int t, Counts& c, uint32_t& err) {
-    if ((unsigned)t >= (unsigned)n) return;
-    c.ng += 1;
-    int L = get16(lg, t) + 1;
-    if (L > 32767) { L = 32767; err |= QG_FLAG_LAYER_OVERFLOW; }
-    set16(lg, t, L);
-    c.nl = max(c.nl, (uint32_t)(L + 1));   // layers is always {0..max} so len() == max+1
-}
-// metrics.rs:98-123
-template <class Wd>
-__device__ __forceinline__ void met_cx(const Wd& lg, const Wd& lc, int n, int ctl, int tgt, Counts& c, uint32_t& err) {
-    if (ctl == tgt || (unsigned)ctl >= (unsigned)n || (unsigned)tgt >= (unsigned)n) return;
-    c.nc += 1; c.ng += 1;
-    int L = max(get16(lg, ctl), get16(lg, tgt)) + 1;
-    if (L > 32767) { L = 32767; err |= QG_FLAG_LAYER_OVERFLOW; }
-    set16(lg, ctl, L); set16(lg, tgt, L);
-    c.nl = max(c.nl, (uint32_t)(L + 1));
-    int Lc = max(get16(lc, ctl), get16(lc, tgt)) + 1;
-    if (Lc > 32767) { Lc = 32767; err |= QG_FLAG_LAYER_OVERFLOW; }
-    set16(lc, ctl, Lc); set16(lc, tgt, Lc);
-    c.nlc = max(c.nlc, (uint32_t)(Lc + 1));
-}
-// metrics.rs:64-82
+// MetricsTracker::apply_gate (metrics.rs:64-123) in closed form, one select-based routine for every gate kind so that a warp
+// whose lanes hold different gates runs it once.  The reference expands  CX -> cx(c,t);  SWAP -> cx(c,t), cx(t,c), cx(c,t);
+// CZ -> single(t), cx(c,t), single(t);  one-qubit gate -> single(q)  (77-80), with
+//   single(t): n_gates++, L = last_gates[t]+1 -> last_gates[t], layers                                  (84-96)
+//   cx(c,t)  : ignored if c == t; n_cnots++, n_gates++, L = max(last_gates[c], last_gates[t])+1 -> both, same on last_cxs (98-123)
+// k chained cx on the same pair raise both qubits to max+k, so the whole gate is
+//   [pre single on t] -> [cx raising by k] -> [post single on t]   with (pre, k, post) = 1q (1,0,0), CX (0,1,0), SWAP (0,3,0), CZ (1,1,1).
+// `layers` is always {0..max} (tests/test_oracle.py::test_layer_sets_are_prefixes), so len() is the running maximum + 1; the
+// last value written to t is the largest of the chain.  Counters saturate at 32767 with a flag, stage by stage like the
+// one-by-one updates would.
 template <class Wd>
 __device__ __forceinline__ void met_gate(const Wd& lg, const Wd& lc, int n, int kind, int q0, int q1, Counts& c, uint32_t& err) {
-    if (kind == QG_CX) met_cx(lg, lc, n, q0, q1, c, err);
-    else if (kind == QG_SWAP) { met_cx(lg, lc, n, q0, q1, c, err); met_cx(lg, lc, n, q1, q0, c, err); met_cx(lg, lc, n, q0, q1, c, err); }
-    else if (kind == QG_CZ) { met_single(lg, n, q1, c, err); met_cx(lg, lc, n, q0, q1, c, err); met_single(lg, n, q1, c, err); }
-    else met_single(lg, n, q0, c, err);
+    (void)n;                                              // qubit indices were range-checked at construction (qg_config_validate)
+    const bool two = kind >= QG_CX;
+    const int t = two ? q1 : q0;
+    const int pre = (!two || kind == QG_CZ) ? 1 : 0, post = (kind == QG_CZ) ? 1 : 0;
+    const int k = (two && q0 != q1) ? (kind == QG_SWAP ? 3 : 1) : 0;
+    auto sat = [&](int v) { if (v > 32767) { v = 32767; err |= QG_FLAG_LAYER_OVERFLOW; } return v; };
+    int lt = sat(get16(lg, t) + pre);
+    if (k) {
+        lt = sat(max(get16(lg, q0), lt) + k);
+        set16(lg, q0, lt);
+        const int Lc = sat(max(get16(lc, q0), get16(lc, t)) + k);
+        set16(lc, q0, Lc); set16(lc, t, Lc);
+        c.nlc = max(c.nlc, (uint32_t)(Lc + 1));
+        c.nc += (uint32_t)k;
+    }
+    lt = sat(lt + post);
+    set16(lg, t, lt);
+    c.nl = max(c.nl, (uint32_t)(lt + 1));
+    c.ng += (uint32_t)(pre + k + post);
 }
 // metrics.rs:135-146: ((w0*dc + w1*dlc) + w2*dl) + w3*dg, every product and sum rounded on its own.
 __device__ __forceinline__ float weighted_delta(const DevCfg& c, const Counts& now, const Counts& prev) {
