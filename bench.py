@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-per-step", action="store_true", help="skip the one-launch-per-env-step leg (profiling runs)")
     ap.add_argument("--no-synth", action="store_true", help="skip the synth-search leg (BASELINE.json configs[4])")
+    ap.add_argument("--no-packed", action="store_true", help="skip the packed-bit observation leg (qg_replay_bits)")
     ap.add_argument("--synth-rollouts", type=int, default=1000, help="num_searches per GPU of the synth leg")
     ap.add_argument("--synth-searches", type=int, default=5, help="timed searches of the synth leg")
     return ap.parse_args()
@@ -300,6 +301,22 @@ def run_ours(args):
                 g_replay.replay()
             stream.synchronize()
     ms_steps = timed(g_steps)[0] if g_steps is not None else None
+    packed = None
+    if not args.no_packed and not (kind == W.PERM and n > 64):
+        # the same episode with the observation delivered as packed bits: 1 bit per entry instead of an f32,
+        # no mask tensor (masks() is [!success; A], the success flag carries it)
+        ow = env.obs_words()
+        bits_ring = env.new_obs_bits(ring=nbuf)
+
+        def episode_replay_bits():
+            env.restore()
+            env.replay_bits(actions, obs_bits=bits_ring, coins=coins, reward=rew_tb, done=done_tb, success=succ_tb)
+
+        ms_bits = timed(capture(episode_replay_bits))[0]
+        packed = {"value": world * B * T * K / (ms_bits * 1e-3), "unit": UNIT, "ms_per_step": ms_bits / K,
+                  "bytes_per_env_step": 4 * ow + 4 + 4 + 1 + 1,
+                  "note": "qg_replay_bits: observation as uint32 bit words [B][ceil(obs/32)] for the fused policy kernel (qg_policy_forward_bits); "
+                          "outputs per env-step: packed obs + f32 reward + u8 done + u8 success, input int32 action"}
     ms, clocks = timed(g_replay, sample_clocks=True)
     total_env_steps = world * B * T * K
     value = total_env_steps / (ms * 1e-3)
@@ -408,7 +425,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (GF(2)) + f32 reward/obs", "data": "synthetic",
         "config": config_json(args, world, {"obs_buffers": nbuf, "cuda_graph": True}),
         "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "per_step_launch": per_step, "cpu_baseline": cpu_baseline,
-        "synth": synth, "engine_error_flags": errs,
+        "packed_obs": packed, "synth": synth, "engine_error_flags": errs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -427,37 +444,46 @@ def run_synth(args, dev, local, rank, world):
 
     kind, n, gateset, kw = W.baseline_configs()["C5_perm27_heavyhex"]
     R = args.synth_rollouts
-    torch.manual_seed(0)
-    pol = BasicPolicy([n, n], len(gateset), embedding_size=512, common_layers=(256,))
-    rs = RolloutSearch(kind, n, gateset, pol, R, device=local, max_depth=128, add_inverts=False)
     rng = np.random.Generator(np.random.PCG64(20261017 + 5))
     targets = [rng.permutation(n).astype(np.int64).tolist() for _ in range(args.synth_searches + 1)]
     shallow = list(range(n)); shallow[0], shallow[1] = shallow[1], shallow[0]      # one SWAP away: exercises the success / early-exit path
-    rs.solve(targets[0], deterministic=False, seed=0, first_rollout_id=rank * R)    # warm-up: graph capture, cuBLAS
-    res_sh = rs.solve(shallow, deterministic=False, seed=1, first_rollout_id=rank * R)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    its = 0
-    for i in range(args.synth_searches):
-        r = rs.solve(targets[1 + i], deterministic=False, seed=2 + i, first_rollout_id=rank * R)
-        its += r.iterations
-    torch.cuda.synchronize()
-    sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([sec], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sec = float(t.item())
-    total = world * R * args.synth_searches
-    return {"metric": "synth rollouts/sec (PermutationGym 27q heavy-hex, num_searches=1000 per GPU)", "value": total / sec, "unit": "rollouts/s",
-            "rollouts_per_search_per_gpu": R, "searches": args.synth_searches, "decisions_per_search": its / max(args.synth_searches, 1),
-            "us_per_decision": 1e6 * sec / max(its, 1), "ms_per_search": 1e3 * sec / max(args.synth_searches, 1),
-            "shallow_target": {"success": bool(res_sh.success), "circuit_len": None if res_sh.actions is None else len(res_sh.actions),
-                               "decisions": res_sh.iterations, "ms": 1e3 * res_sh.seconds},
-            "note": "uniform random 27-permutations, random-init policy (no checkpoint exists for this map): rollouts run to max_depth=128; "
-                    "time is host wall clock over whole solve() calls (set_state broadcast, CUDA-graph replays, on-GPU best reduction, "
-                    "cross-rank all-reduce), max over ranks"}
+
+    def leg(backend):
+        torch.manual_seed(0)
+        pol = BasicPolicy([n, n], len(gateset), embedding_size=512, common_layers=(256,))
+        rs = RolloutSearch(kind, n, gateset, pol, R, device=local, max_depth=128, add_inverts=False, policy_backend=backend)
+        rs.solve(targets[0], deterministic=False, seed=0, first_rollout_id=rank * R)    # warm-up: graph capture, cuBLAS
+        res_sh = rs.solve(shallow, deterministic=False, seed=1, first_rollout_id=rank * R)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        its = 0
+        for i in range(args.synth_searches):
+            r = rs.solve(targets[1 + i], deterministic=False, seed=2 + i, first_rollout_id=rank * R)
+            its += r.iterations
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        total = world * R * args.synth_searches
+        return {"value": total / sec, "unit": "rollouts/s", "decisions_per_search": its / max(args.synth_searches, 1),
+                "us_per_decision": 1e6 * sec / max(its, 1), "ms_per_search": 1e3 * sec / max(args.synth_searches, 1),
+                "shallow_target": {"success": bool(res_sh.success), "circuit_len": None if res_sh.actions is None else len(res_sh.actions),
+                                   "decisions": res_sh.iterations, "ms": 1e3 * res_sh.seconds}}
+
+    fused = leg("fused")
+    torch_leg = leg("torch")
+    out = {"metric": "synth rollouts/sec (PermutationGym 27q heavy-hex, num_searches=1000 per GPU)", "rollouts_per_search_per_gpu": R, "searches": args.synth_searches}
+    out.update(fused)
+    out["policy_backend"] = "fused: packed-bit observations -> qg_policy_forward_bits (gather-sum first layer + MLP + softmax in one kernel) -> qg_search_step_bits; 2 launches per decision"
+    out["torch_policy"] = dict(torch_leg, note="same search with the PyTorch BasicPolicy on dense f32 observations (cuBLAS GEMMs + softmax + qg_search_step)")
+    out["note"] = ("uniform random 27-permutations, random-init policy (no checkpoint exists for this map): rollouts run to max_depth=128; "
+                   "time is host wall clock over whole solve() calls (set_state broadcast, CUDA-graph replays, on-GPU best reduction, "
+                   "cross-rank all-reduce), max over ranks")
+    return out
 
 
 def main():

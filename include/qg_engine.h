@@ -234,6 +234,35 @@ QG_API int qg_gae(const float* reward_dev, const float* value_dev, const uint8_t
 QG_API int qg_twist_gather(const float* in_dev, float* out_dev, const int32_t* table_dev, const int32_t* index_dev,
                            int64_t batch, int32_t len, qg_stream stream);
 
+/* ---- packed-bit observations + fused policy network ------------------------------------------
+ * Env::observe returns the indices of the non-zero entries (e.g. clifford.rs:361-368) because twisterl's policy sums
+ * first-layer weight columns over them.  The *_bits entry points deliver the same information as one bit per entry:
+ * obs_bits_dev uint32[B][qg_obs_words] (bit i%32 of word i/32 = entry i of the row-major observation), 32x smaller
+ * than the dense f32 tensor; everything else is identical to the entry point of the same name without the suffix. */
+typedef struct qg_policy qg_policy;
+QG_API int32_t qg_obs_words(const qg_engine* e);            /* ceil(obs_size / 32) */
+QG_API int qg_step_bits(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev,
+                        uint32_t* obs_bits_dev, uint8_t* mask_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev,
+                        qg_stream stream);
+QG_API int qg_replay_bits(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const uint8_t* coins_dev,
+                          const uint32_t* perm_raw_dev, uint32_t* obs_bits_dev, uint8_t* mask_dev, int32_t ring,
+                          float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
+QG_API int qg_observe_bits(qg_engine* e, const uint32_t* perm_raw_dev, uint32_t* obs_bits_dev, qg_stream stream);
+QG_API int qg_search_step_bits(qg_engine* e, const float* weights_dev, int32_t deterministic, uint32_t* obs_bits_dev,
+                               int32_t* chosen_dev, int32_t* num_active_dev, qg_stream stream);
+/* The action network of a twisterl BasicPolicy (the .pt files under examples/models: embeddings -> ReLU -> common[i] -> ReLU ... ->
+ * action head) evaluated from packed observations in one kernel: first layer = bias + sum of the weight columns of the
+ * set bits, then the Linear/ReLU chain and a softmax.  Layer l has out_features[l] outputs and consumes the
+ * observation (l = 0) or layer l-1; weights_host[l] is torch's Linear.weight layout [out][in] row-major, f32; ReLU
+ * follows every layer but the last.  Limits: 1..8 layers, widths <= 1024. */
+QG_API int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features,
+                            const float* const* weights_host, const float* const* biases_host, qg_policy** out);
+QG_API void qg_policy_destroy(qg_policy* p);
+QG_API int32_t qg_policy_num_actions(const qg_policy* p);
+/* probs_dev float[B][num_actions] (softmax) and / or logits_dev float[B][num_actions]; either may be NULL. */
+QG_API int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev,
+                                  float* logits_dev, qg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

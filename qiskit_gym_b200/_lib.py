@@ -25,6 +25,8 @@ SYMBOLS = [
     "qg_set_state", "qg_reset", "qg_snapshot", "qg_restore", "qg_step", "qg_replay", "qg_replay_host", "qg_step_host", "qg_observe", "qg_masks", "qg_read_status",
     "qg_read_metrics", "qg_read_errors", "qg_get_state_host", "qg_solution_host", "qg_search_begin",
     "qg_search_step", "qg_search_best", "qg_read_returns", "qg_reset_select", "qg_collect_step", "qg_gae", "qg_twist_gather",
+    "qg_obs_words", "qg_step_bits", "qg_replay_bits", "qg_observe_bits", "qg_search_step_bits",
+    "qg_policy_create", "qg_policy_destroy", "qg_policy_num_actions", "qg_policy_forward_bits",
 ]
 
 
@@ -104,6 +106,16 @@ def lib():
     L.qg_collect_step.argtypes = [vp, u64, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.qg_gae.argtypes = [vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp]
     L.qg_twist_gather.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+    L.qg_obs_words.argtypes = [vp]
+    L.qg_step_bits.argtypes = [vp] + [vp] * 8 + [vp]
+    L.qg_replay_bits.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.qg_observe_bits.argtypes = [vp, vp, vp, vp]
+    L.qg_search_step_bits.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.qg_policy_create.argtypes = [i32, i32, i32, vp, vp, vp, C.POINTER(vp)]
+    L.qg_policy_destroy.argtypes = [vp]
+    L.qg_policy_destroy.restype = None
+    L.qg_policy_num_actions.argtypes = [vp]
+    L.qg_policy_forward_bits.argtypes = [vp, vp, i64, vp, vp, vp]
     _lib = L
     return L
 

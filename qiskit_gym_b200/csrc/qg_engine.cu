@@ -90,8 +90,7 @@ int pauli_perms(const qg_config* cfg, Twists& tw) {
     return compute_twists(cfg, true, tw);
 }
 
-int prepare_kernels(qg_engine* e) {   // opt in to > 48 KB dynamic shared memory once, outside any stream capture
-    if (e->smem_bytes <= 48 * 1024) return QG_OK;
+int prepare_kernels(qg_engine* e) {   // kernel attributes (shared-memory carve-out, > 48 KB opt-in) once, outside any stream capture
     switch (e->L.kind) {
         case QG_ENV_PERMUTATION: CUDA_OK(prepare_step_kind<QG_ENV_PERMUTATION>(e->smem_bytes)); break;
         case QG_ENV_LINEAR_FUNCTION: CUDA_OK(prepare_step_kind<QG_ENV_LINEAR_FUNCTION>(e->smem_bytes)); break;
@@ -113,6 +112,8 @@ int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st) {
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     { const uint32_t vpe = (uint32_t)e->L.obs_size / 4; a.exp_q = vpe ? 32u / vpe : 0u; a.exp_r = vpe ? 32u - a.exp_q * vpe : 0u; }
     a.symplectic = e->all_symplectic ? 1 : 0;
+    a.magic_ow = magic40(((uint32_t)e->L.obs_size + 31u) / 32u);
+    if (a.obs_bits && e->L.kind == QG_ENV_PERMUTATION && e->L.OW == 0) { set_error("packed observations need num_qubits <= 64 for Permutation"); return QG_ERR_UNSUPPORTED; }
     if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     if (a.mask && (reinterpret_cast<uintptr_t>(a.mask) & 15)) { set_error("mask_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     const int64_t tiles = (e->B + 31) / 32;
@@ -634,6 +635,43 @@ int qg_twist_gather(const float* in_dev, float* out_dev, const int32_t* table_de
     k_twist_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(in_dev, out_dev, table_dev, index_dev, batch, len, magic);
     CUDA_OK(cudaGetLastError());
     return QG_OK;
+}
+
+// ---- packed-bit observation variants ------------------------------------------------------------
+int32_t qg_obs_words(const qg_engine* e) { return e ? (e->L.obs_size + 31) / 32 : 0; }
+
+int qg_step_bits(qg_engine* e, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev, uint32_t* obs_bits_dev, uint8_t* mask_dev,
+                 float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !actions_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs_bits = obs_bits_dev; a.mask = mask_dev;
+    a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
+}
+
+int qg_replay_bits(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const uint8_t* coins_dev, const uint32_t* perm_raw_dev,
+                   uint32_t* obs_bits_dev, uint8_t* mask_dev, int32_t ring, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !actions_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (num_steps < 0 || ring < 1) { set_error("qg_replay_bits: num_steps must be >= 0 and ring >= 1"); return QG_ERR_INVALID; }
+    if (num_steps == 0) return QG_OK;
+    StepArgs a{}; a.actions = actions_dev; a.coins = coins_dev; a.perm_raw = perm_raw_dev; a.obs_bits = obs_bits_dev; a.mask = mask_dev;
+    a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    a.nsteps = num_steps; a.ring = ring; a.in_stride = e->B; a.out_stride = e->B;
+    return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
+}
+
+int qg_observe_bits(qg_engine* e, const uint32_t* perm_raw_dev, uint32_t* obs_bits_dev, qg_stream stream) {
+    if (!e || !obs_bits_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    StepArgs a{}; a.perm_raw = perm_raw_dev; a.obs_bits = obs_bits_dev;
+    return launch_step(e, MODE_OBSERVE, a, (cudaStream_t)stream);
+}
+
+int qg_search_step_bits(qg_engine* e, const float* weights_dev, int32_t deterministic, uint32_t* obs_bits_dev, int32_t* chosen_dev,
+                        int32_t* num_active_dev, qg_stream stream) {
+    if (!e || !weights_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (num_active_dev) CUDA_OK(cudaMemsetAsync(num_active_dev, 0, 4, st));
+    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs_bits = obs_bits_dev; a.chosen = chosen_dev; a.num_active = num_active_dev;
+    return launch_step(e, MODE_SEARCH, a, st);
 }
 
 int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream) {

@@ -21,6 +21,7 @@ struct StepArgs {
     const float* weights;        // [B][A]         (MODE_SEARCH)
     int32_t deterministic;
     float* obs;                  // [B][obs_size] or null
+    uint32_t* obs_bits;          // [B][ceil(obs_size/32)] or null: the observation as packed bits (bit i of an env = entry i), env-major
     uint8_t* mask;               // [B][A] or null
     float* reward; uint8_t* done; uint8_t* success;   // [B] or null
     int32_t* chosen;             // [B] or null    (MODE_SEARCH)
@@ -36,6 +37,7 @@ struct StepArgs {
     int64_t out_stride;          // elements between consecutive steps of reward / done / success
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
+    uint64_t magic_ow;                // ceil(2^40/ceil(obs_size/32))        (packed observation)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
     uint32_t exp_q, exp_r;            // 32 / VPE and 32 % VPE with VPE = obs_size / 4: how (env, float4-in-env) advances per warp store
 };
@@ -679,15 +681,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
             if (KIND == QG_ENV_PAULI_NETWORK && enabled) {
                 // PauliNetwork picks its qubit permutation here (pauli.rs:653-665)
                 int perm_idx = 0;
-                if (c.nperms > 0 && a.obs) {
+                if (c.nperms > 0 && (a.obs || a.obs_bits)) {
                     const uint32_t raw = a.perm_raw ? a.perm_raw[(size_t)t * a.in_stride + env] : philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_PERM);
                     perm_idx = (int)__umulhi(raw, (uint32_t)c.nperms);
                     pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
                     dirty = true;
                 }
-                if (a.obs) pn_build_obs(c, S, pr, O, perm_idx);
+                if (a.obs || a.obs_bits) pn_build_obs(c, S, pr, O, perm_idx);
             }
-            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && enabled && a.obs) {
+            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && enabled && (a.obs || a.obs_bits)) {
                 // one-hot rows: bit i*n + state[i] (permutation.rs:241-243)
                 for (int w = 0; w < c.OW; ++w) O[w] = 0;
                 for (int i = 0, b = 0; i < c.n; ++i, b += c.n) { const int bit = b + (int)get8(S, i); O[bit >> 5] |= 1u << (bit & 31); }
@@ -711,6 +713,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
                     const uint32_t i = __umulhi(off, c.magic_n), col = off - i * n;
                     if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[f] = (((st[(i >> 2) * kStride + e] >> ((i & 3u) * 8u)) & 0xFFu) == col) ? 1.0f : 0.0f;
                 }
+            }
+        }
+        if (a.obs_bits) {
+            // packed observation: the warp's 32 x OWp words are contiguous in the [B][OWp] tensor; transposed out of the
+            // [word][env] shared-memory stream with coalesced stores
+            const uint32_t OWp = ((uint32_t)c.obs_size + 31u) >> 5, total = (uint32_t)cnt * OWp;
+            uint32_t* out = a.obs_bits + ((size_t)slot * c.B + (size_t)e0) * OWp;
+            for (uint32_t i = lane; i < total; i += 32) {
+                const uint32_t e = fastdiv40(i, a.magic_ow), w = i - e * OWp;
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) out[i] = obs_bits[w * kStride + e];
             }
         }
         if (a.mask) {

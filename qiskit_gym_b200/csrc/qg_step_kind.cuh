@@ -42,7 +42,11 @@ cudaError_t launch_step_kind(int mode, int inv, const DevCfg& c, const StepArgs&
 
 template <int KIND, int MODE, int INV>
 cudaError_t prepare_one(size_t smem_bytes) {
-    return cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    // same shared-memory carve-out as the policy kernel (qg_policy.cu): alternating launches of the two in a search do not make
+    // the SMs reconfigure their L1 / shared-memory split in between
+    cudaError_t e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    return e;
 }
 
 template <int KIND>

@@ -263,6 +263,51 @@ class BatchedEnv:
                                     _dptr(self.success if success is None else success), self._stream()))
         return obs_t
 
+    # ------------------------------------------------------------------ packed-bit observations
+    def obs_words(self) -> int:
+        return int(lib().qg_obs_words(self._h))
+
+    def new_obs_bits(self, ring: int | None = None) -> torch.Tensor:
+        shape = (self.batch, self.obs_words()) if ring is None else (ring, self.batch, self.obs_words())
+        return torch.zeros(shape, dtype=torch.int32, device=self.device)
+
+    def observe_bits(self, out: torch.Tensor, perm_raw: torch.Tensor | None = None):
+        """Env::observe as packed bits: int32 [B, obs_words], bit i%32 of word i//32 = entry i of the flattened observation."""
+        assert out.is_cuda and out.element_size() == 4 and out.numel() == self.batch * self.obs_words() and out.is_contiguous()
+        check(lib().qg_observe_bits(self._h, _dptr(perm_raw), _dptr(out), self._stream()))
+        return out
+
+    def step_bits(self, actions: torch.Tensor, obs_bits: torch.Tensor | None, coins: torch.Tensor | None = None,
+                  perm_raw: torch.Tensor | None = None, mask: torch.Tensor | None | bool = None):
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.numel() == self.batch
+        mask_t = self.mask if mask is True else (None if mask is False else mask)
+        check(lib().qg_step_bits(self._h, _dptr(actions), _dptr(coins), _dptr(perm_raw), _dptr(obs_bits), _dptr(mask_t),
+                                 _dptr(self.reward), _dptr(self.done), _dptr(self.success), self._stream()))
+        return obs_bits, self.reward, self.done
+
+    def replay_bits(self, actions: torch.Tensor, obs_bits: torch.Tensor | None = None, mask: torch.Tensor | None = None,
+                    coins: torch.Tensor | None = None, perm_raw: torch.Tensor | None = None, reward: torch.Tensor | None = None,
+                    done: torch.Tensor | None = None, success: torch.Tensor | None = None):
+        """qg_replay with packed observations: obs_bits int32 [ring, B, obs_words]."""
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous() and actions.shape[-1] == self.batch
+        T = int(actions.shape[0]) if actions.dim() == 2 else 1
+        ring = 1
+        if obs_bits is not None:
+            ring = obs_bits.numel() // (self.batch * self.obs_words())
+        if mask is not None:
+            mring = mask.numel() // (self.batch * self._A)
+            assert obs_bits is None or mring == ring, "obs and mask rings differ"
+            ring = mring
+        check(lib().qg_replay_bits(self._h, T, _dptr(actions), _dptr(coins), _dptr(perm_raw), _dptr(obs_bits), _dptr(mask), ring,
+                                   _dptr(reward), _dptr(done), _dptr(success), self._stream()))
+
+    def search_step_bits(self, weights: torch.Tensor, obs_bits: torch.Tensor | None, deterministic: bool = False,
+                         chosen: torch.Tensor | None = None, num_active: torch.Tensor | None = None):
+        assert weights.dtype == torch.float32 and weights.is_cuda and weights.is_contiguous()
+        check(lib().qg_search_step_bits(self._h, _dptr(weights), 1 if deterministic else 0, _dptr(obs_bits), _dptr(chosen),
+                                        _dptr(num_active), self._stream()))
+        return obs_bits
+
     def search_best(self):
         key, env = C.c_int64(), C.c_int64()
         check(lib().qg_search_best(self._h, C.byref(key), C.byref(env), self._stream()))

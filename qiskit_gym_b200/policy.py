@@ -1,0 +1,81 @@
+"""FusedPolicy — the action network of a twisterl `BasicPolicy` evaluated from packed-bit observations by one CUDA kernel
+(`qg_policy_forward_bits`, csrc/qg_policy.cu).
+
+twisterl's policy consumes `Env::observe()`'s sparse indices with a gather-sum first layer; the PyTorch `BasicPolicy` in
+search.py consumes the dense f32 tensor instead.  `FusedPolicy` takes the weights of such a module (or of a checkpoint in
+the reference's `.pt` format) and evaluates  obs bits -> Linear -> ReLU -> ... -> Linear -> softmax  in a single launch,
+which is what makes a synth-search decision two launches long.  Its output matches the PyTorch module to f32 rounding
+(sums run in a different order than cuBLAS'); tests/test_policy.py states the tolerance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .engine import _dptr
+
+
+def action_layers(policy: torch.nn.Module):
+    """The Linear layers on the observation -> action-logits path of a BasicPolicy-shaped module, in order."""
+    layers = [policy.embeddings]
+    layers += [m for m in policy.common if isinstance(m, torch.nn.Linear)]
+    layers += [m for m in policy.action if isinstance(m, torch.nn.Linear)]
+    return layers
+
+
+class FusedPolicy:
+    def __init__(self, policy: torch.nn.Module, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("qiskit_gym_b200 needs a CUDA device (no CPU fallback)")
+        self.device_index = torch.cuda.current_device() if device is None else (device.index if isinstance(device, torch.device) else int(device))
+        self.device = torch.device("cuda", self.device_index)
+        layers = action_layers(policy)
+        ws = [np.ascontiguousarray(l.weight.detach().cpu().numpy(), dtype=np.float32) for l in layers]
+        bs = [np.ascontiguousarray(l.bias.detach().cpu().numpy(), dtype=np.float32) for l in layers]
+        for a, b in zip(ws[:-1], ws[1:]):
+            assert b.shape[1] == a.shape[0], "layers do not chain"
+        self.obs_size = int(ws[0].shape[1])
+        self.obs_words = (self.obs_size + 31) // 32
+        self.num_actions = int(ws[-1].shape[0])
+        n = len(ws)
+        widths = (C.c_int32 * n)(*[int(w.shape[0]) for w in ws])
+        wp = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
+        bp = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
+        h = C.c_void_p()
+        check(lib().qg_policy_create(self.device_index, self.obs_size, n, widths, wp, bp, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().qg_policy_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward_bits(self, obs_bits: torch.Tensor, probs: torch.Tensor | None = None, logits: torch.Tensor | None = None):
+        """obs_bits int32 [B, obs_words] (BatchedEnv.observe_bits / step_bits) -> softmax action weights f32 [B, A]."""
+        assert obs_bits.is_cuda and obs_bits.element_size() == 4 and obs_bits.is_contiguous() and obs_bits.shape[-1] == self.obs_words
+        B = obs_bits.numel() // self.obs_words
+        if probs is None and logits is None:
+            probs = torch.empty((B, self.num_actions), dtype=torch.float32, device=obs_bits.device)
+        for t in (probs, logits):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == B * self.num_actions)
+        st = C.c_void_p(torch.cuda.current_stream(obs_bits.device).cuda_stream)
+        check(lib().qg_policy_forward_bits(self._h, _dptr(obs_bits), B, _dptr(probs), _dptr(logits), st))
+        return probs if probs is not None else logits
+
+
+def pack_obs_bits(obs: torch.Tensor) -> torch.Tensor:
+    """Dense 0/1 observation [B, ...] -> packed int32 [B, ceil(obs/32)] (host-side helper for tests and tools)."""
+    flat = (obs.reshape(obs.shape[0], -1) != 0).cpu().numpy()
+    B, n = flat.shape
+    words = (n + 31) // 32
+    pad = np.zeros((B, words * 32), dtype=bool)
+    pad[:, :n] = flat
+    packed = np.packbits(pad.reshape(B, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(B, words)
+    return torch.from_numpy(packed.view(np.int32).copy())

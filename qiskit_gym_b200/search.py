@@ -105,10 +105,18 @@ class RolloutSearch:
     """Device-resident `solve`: owns a BatchedEnv of `num_rollouts` rollouts on one GPU."""
 
     def __init__(self, env_kind, num_qubits, gateset, policy: torch.nn.Module, num_rollouts: int, device=None,
-                 max_depth: int = 128, use_cuda_graph: bool = True, **env_kwargs):
+                 max_depth: int = 128, use_cuda_graph: bool = True, policy_backend: str = "fused", **env_kwargs):
+        """policy_backend: "fused" = packed-bit observations + the one-kernel action network (policy.FusedPolicy);
+        "torch" = dense f32 observations + the PyTorch module (cuBLAS GEMMs, softmax)."""
         env_kwargs.setdefault("add_perms", False)
         self.env = BatchedEnv(env_kind, num_qubits, gateset, num_rollouts, device=device, max_depth=max_depth, **env_kwargs)
         self.policy = policy.to(self.env.device).eval()
+        assert policy_backend in ("fused", "torch")
+        self.backend = policy_backend
+        if policy_backend == "fused":
+            from .policy import FusedPolicy
+            self.fused = FusedPolicy(self.policy, device=self.env.device)
+            self.obs_bits = self.env.new_obs_bits()
         self.max_depth = max_depth
         self.B = num_rollouts
         dev = self.env.device
@@ -119,10 +127,20 @@ class RolloutSearch:
         self._stream = torch.cuda.Stream(device=dev)
 
     def _iteration(self, deterministic):
+        if self.backend == "fused":
+            self.fused.forward_bits(self.obs_bits, probs=self.probs)
+            self.env.search_step_bits(self.probs, self.obs_bits, deterministic=deterministic, num_active=self.num_active)
+            return
         with torch.no_grad():
             logits, _ = self.policy(self.env.obs)
             torch.softmax(logits.float(), dim=-1, out=self.probs)
         self.env.search_step(self.probs, deterministic=deterministic, obs=True, num_active=self.num_active)
+
+    def _observe(self):
+        if self.backend == "fused":
+            self.env.observe_bits(self.obs_bits)
+        else:
+            self.env.observe()
 
     def _graph(self, deterministic):
         g = self._graphs.get(deterministic)
@@ -150,7 +168,7 @@ class RolloutSearch:
                 g = self._graph(deterministic)
                 env.set_state(state)
             env.search_begin(seed, first_rollout_id)
-            env.observe()
+            self._observe()
             its = 0
             while its < self.max_depth:
                 if self.use_graph:

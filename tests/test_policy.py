@@ -1,0 +1,127 @@
+"""Packed-bit observations (qg_*_bits) against the dense observation and the oracle, and the fused action network
+(qg_policy_forward_bits) against the PyTorch BasicPolicy it was built from."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests import helpers as H
+
+
+def unpack_bits(bits, n):
+    """int32/uint32 [B, words] -> uint8 [B, n]"""
+    b = np.ascontiguousarray(bits).view(np.uint32)
+    out = np.unpackbits(b.view(np.uint8).reshape(b.shape[0], -1), axis=1, bitorder="little")
+    return out[:, :n]
+
+
+def test_pack_obs_bits_helper():
+    from qiskit_gym_b200.policy import pack_obs_bits
+    rng = np.random.Generator(np.random.PCG64(1))
+    for B, n in ((1, 1), (3, 31), (5, 32), (4, 33), (7, 81), (2, 729)):
+        dense = (rng.random((B, n)) < 0.4).astype(np.float32)
+        packed = pack_obs_bits(torch.from_numpy(dense)).numpy()
+        assert packed.shape == (B, (n + 31) // 32)
+        assert np.array_equal(unpack_bits(packed, n), dense.astype(np.uint8))
+        # bits beyond n are zero
+        assert np.array_equal(unpack_bits(packed, packed.shape[1] * 32)[:, n:], np.zeros((B, packed.shape[1] * 32 - n), np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C1_perm_grid3", "C2_lf8_line", "C3_clifford8_full", "C4_pauli10_line", "C5_perm27_heavyhex", "lf11_line", "clifford5_allgates", "pauli6_line"])
+@pytest.mark.parametrize("B", [1, 33, 100])
+def test_packed_observation_equals_dense_and_oracle(name, B):
+    from qiskit_gym_b200 import BatchedEnv
+    kind, n, gs, kw = H.config_table()[name]
+    kw = dict(kw, add_perms=False)
+    if kind != H.PAULI:
+        kw["add_inverts"] = False
+    T = 6
+    rng = np.random.Generator(np.random.PCG64(17))
+    cfg = H.make_cfg(kind, n, gs, **kw)
+    tarr = H.random_targets(kind, n, gs, B, 5, scramble=12)
+    lens = H.payload_lengths(kind, n, tarr)
+    actions = H.random_actions(rng, T, B, len(gs))
+    ref = orc.run_batch(cfg, tarr, lens, actions)
+    env = BatchedEnv(kind, n, gs, B, **kw)
+    env.set_state(tarr)
+    size = env._obs_size
+    bits = env.new_obs_bits()
+    env.observe_bits(bits)
+    assert np.array_equal(unpack_bits(bits.cpu().numpy(), size), ref["obs0"])
+    for t in range(T):
+        env.step_bits(torch.from_numpy(actions[t]).to(env.device), bits, mask=True)
+        got = bits.cpu().numpy()
+        assert np.array_equal(unpack_bits(got, size), ref["obs"][t]), (name, t)
+        assert np.array_equal(unpack_bits(got, got.shape[1] * 32)[:, size:].sum(), 0)          # padding bits stay clear
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), ref["reward"][t].view(np.uint32))
+        assert np.array_equal(env.done.cpu().numpy().astype(np.uint8), ref["done"][t])
+    # the same episode in one launch, packed ring of 2 slots
+    env.set_state(tarr)
+    ring = env.new_obs_bits(ring=2)
+    env.replay_bits(torch.from_numpy(actions).to(env.device), obs_bits=ring)
+    got = ring.cpu().numpy()
+    assert np.array_equal(unpack_bits(got[(T - 1) % 2], size), ref["obs"][T - 1])
+    assert np.array_equal(unpack_bits(got[(T - 2) % 2], size), ref["obs"][T - 2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obs_shape,A,emb,common,pol_layers,density", [
+    ((9, 9), 12, 64, (32,), (), 0.12),
+    ((27, 27), 28, 512, (256,), (), 0.04),
+    ((16, 16), 72, 512, (256,), (), 0.5),
+    ((20, 25), 104, 300, (200, 100), (50,), 0.3),
+    ((3, 3), 2, 1024, (), (), 0.5),
+])
+def test_fused_policy_matches_torch(obs_shape, A, emb, common, pol_layers, density):
+    from qiskit_gym_b200.policy import FusedPolicy, pack_obs_bits
+    from qiskit_gym_b200.search import BasicPolicy
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    pol = BasicPolicy(list(obs_shape), A, embedding_size=emb, common_layers=common, policy_layers=pol_layers).to(dev).eval()
+    fused = FusedPolicy(pol, device=dev)
+    rng = np.random.Generator(np.random.PCG64(9))
+    for B in (1, 7, 8, 9, 1000):
+        dense = torch.from_numpy((rng.random((B,) + tuple(obs_shape)) < density).astype(np.float32))
+        if B > 2:
+            dense[0] = 0.0                                          # an empty observation and a full one
+            dense[1] = 1.0
+        bits = pack_obs_bits(dense).to(dev)
+        probs = torch.empty((B, A), dtype=torch.float32, device=dev)
+        logits = torch.empty((B, A), dtype=torch.float32, device=dev)
+        fused.forward_bits(bits, probs=probs, logits=logits)
+        with torch.no_grad():
+            # reference in float64 so the comparison is not limited by cuBLAS' own f32 rounding / TF32 settings
+            ref_logits, _ = pol.double()(dense.to(dev).double())
+            pol.float()
+        ref_probs = torch.softmax(ref_logits, dim=-1)
+        # tolerance: f32 accumulation over <= 1024-term sums
+        assert torch.allclose(logits.double(), ref_logits, rtol=1e-4, atol=2e-5), (B, (logits.double() - ref_logits).abs().max())
+        assert torch.allclose(probs.double(), ref_probs, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(probs.sum(dim=1), torch.ones(B, device=dev), atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_rollout_search_fused_backend_solves_shallow_targets():
+    from qiskit_gym_b200.search import BasicPolicy, RolloutSearch
+    kind, n, gs, kw = H.config_table()["C1_perm_grid3"]
+    torch.manual_seed(0)
+    pol = BasicPolicy([n, n], len(gs), embedding_size=64, common_layers=(32,))
+    results = {}
+    for backend in ("torch", "fused"):
+        rs = RolloutSearch(kind, n, gs, pol, 2048, max_depth=6, policy_backend=backend, add_inverts=False)
+        tgt = orc.OracleEnv(kind, n, gs, difficulty=2, add_inverts=False, add_perms=False)
+        solved = 0
+        for trial in range(4):
+            tgt.reset(seed=trial, env_id=0)
+            state = tgt.raw_state().astype(np.int64).tolist()
+            res = rs.solve(state, deterministic=False, seed=trial)
+            if res.actions is not None:
+                solved += 1
+                chk = orc.OracleEnv(kind, n, gs, add_inverts=False, add_perms=False)
+                chk.set_state(state)
+                for a in res.actions:
+                    chk.step(a)
+                assert chk.success()
+        results[backend] = solved
+        assert solved >= 3
