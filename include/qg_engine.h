@@ -263,6 +263,46 @@ QG_API int32_t qg_policy_num_actions(const qg_policy* p);
 QG_API int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev,
                                   float* logits_dev, qg_stream stream);
 
+/* ---- tree search (num_mcts_searches > 0, rl/synthesis.py:122-124, rl/configs.py:30-42) ----------------
+ * Clone + step through record slots: the engine's batch is a pool of record slots; logical env i (i < count) reads the
+ * record in slot src_slot_dev[i], plays actions_dev[i] and writes the result to slot dst_slot_dev[i] (a tree-search child
+ * node = clone of the parent's env + one step, the reference's `Clone` + `step`).  A negative action leaves slot and outputs
+ * of env i untouched.  Outputs (each may be NULL) are indexed by i like qg_step's. */
+QG_API int qg_step_slots(qg_engine* e, int64_t count, const int32_t* src_slot_dev, const int32_t* dst_slot_dev,
+                         const int32_t* actions_dev, float* obs_dev, uint32_t* obs_bits_dev, uint8_t* mask_dev,
+                         float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
+/* Copies the records of envs 0..count-1 of `src` into the slots dst_slot_dev[i] of `dst` (same env kind, qubits and gateset;
+ * batch and track_solution may differ: the copies restart their solution log). */
+QG_API int qg_copy_records(qg_engine* dst, const int32_t* dst_slot_dev, qg_engine* src, int64_t count, qg_stream stream);
+
+/* Device arrays of num_trees PUCT trees with node_cap nodes each (caller-owned, see csrc/qg_mcts.cu for the protocol);
+ * node j of tree i lives in record slot i * node_cap + j of the slot-pool engine. */
+typedef struct qg_mcts_tree {
+    int32_t num_trees, node_cap, num_actions;
+    float* prior;          /* [num_trees][node_cap][num_actions] */
+    int32_t* visits;       /* [num_trees][node_cap][num_actions] */
+    float* value_sum;      /* [num_trees][node_cap][num_actions] */
+    int32_t* child;        /* [num_trees][node_cap][num_actions] node index or -1 */
+    float* node_reward;    /* [num_trees][node_cap] reward of the step that created the node */
+    uint8_t* node_final;   /* [num_trees][node_cap] */
+    int32_t* node_count;   /* [num_trees] */
+    int32_t* path_node;    /* [num_trees][node_cap] */
+    int32_t* path_action;  /* [num_trees][node_cap] */
+    int32_t* path_len;     /* [num_trees] */
+    int32_t* new_node;     /* [num_trees] node created by the last select, -1 if none */
+} qg_mcts_tree;
+/* New decision: node 0 of every tree gets root_prior_dev float[num_trees][num_actions] and root_final_dev uint8[num_trees]. */
+QG_API int qg_mcts_begin(const qg_mcts_tree* t, const float* root_prior_dev, const uint8_t* root_final_dev, qg_stream stream);
+/* One simulation's descent per tree; writes the slots / action of the expansion for qg_step_slots (action -1: none). */
+QG_API int qg_mcts_select(const qg_mcts_tree* t, float c_puct, int32_t* src_slot_dev, int32_t* dst_slot_dev,
+                          int32_t* action_dev, qg_stream stream);
+/* Finishes the simulation: the new node gets prior_dev float[num_trees][num_actions], reward_dev / done_dev of its step and
+ * value_dev float[num_trees] (ignored if final); returns are backed up along the recorded path. */
+QG_API int qg_mcts_backup(const qg_mcts_tree* t, const float* prior_dev, const float* value_dev, const float* reward_dev,
+                          const uint8_t* done_dev, qg_stream stream);
+/* weights_dev float[num_trees][num_actions] = root visit counts / their sum (all zero for a tree without simulations). */
+QG_API int qg_mcts_root_weights(const qg_mcts_tree* t, float* weights_dev, qg_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,13 @@ class OracleEnv:
             lib().qgo_destroy(self._h)
             self._h = None
 
+    def clone(self):
+        """`Clone` of the env (the reference clones one env per rollout / tree node)."""
+        o = object.__new__(OracleEnv)
+        o.cfg, o._shape = self.cfg, self._shape
+        o._h = lib().qgo_clone(self._h)
+        return o
+
     def _chk(self, rc):
         if rc < 0:
             raise RuntimeError(lib().qgo_last_error().decode())

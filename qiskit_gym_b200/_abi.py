@@ -48,6 +48,16 @@ class QgConfig(C.Structure):
     ]
 
 
+class QgMctsTree(C.Structure):
+    """qg_mcts_tree: device arrays of the PUCT trees (include/qg_engine.h)."""
+    _fields_ = [
+        ("num_trees", C.c_int32), ("node_cap", C.c_int32), ("num_actions", C.c_int32),
+        ("prior", C.c_void_p), ("visits", C.c_void_p), ("value_sum", C.c_void_p), ("child", C.c_void_p),
+        ("node_reward", C.c_void_p), ("node_final", C.c_void_p), ("node_count", C.c_void_p),
+        ("path_node", C.c_void_p), ("path_action", C.c_void_p), ("path_len", C.c_void_p), ("new_node", C.c_void_p),
+    ]
+
+
 def parse_gateset(gateset: Iterable, kind_from_name) -> "C.Array[QgGate]":
     """(name, indices) pairs -> qg_gate[]; error behaviour of common.rs:46-100
     (TypeError for malformed items, ValueError for unknown names / wrong arity)."""

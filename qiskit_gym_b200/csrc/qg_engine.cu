@@ -99,8 +99,10 @@ int prepare_kernels(qg_engine* e) {   // kernel attributes (shared-memory carve-
     }
     return QG_OK;
 }
-int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st) {
-    if (e->B == 0) return QG_OK;
+int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t logical_batch = -1) {
+    // logical_batch >= 0: the launch covers that many logical envs addressed through a.src_slot / a.dst_slot (qg_step_slots)
+    const int64_t LB = logical_batch >= 0 ? logical_batch : e->B;
+    if (LB == 0) return QG_OK;
     int cur = -1;
     CUDA_OK(cudaGetDevice(&cur));
     if (cur != e->device) CUDA_OK(cudaSetDevice(e->device));
@@ -116,17 +118,19 @@ int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st) {
     if (a.obs_bits && e->L.kind == QG_ENV_PERMUTATION && e->L.OW == 0) { set_error("packed observations need num_qubits <= 64 for Permutation"); return QG_ERR_UNSUPPORTED; }
     if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     if (a.mask && (reinterpret_cast<uintptr_t>(a.mask) & 15)) { set_error("mask_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
-    const int64_t tiles = (e->B + 31) / 32;
+    const int64_t tiles = (LB + 31) / 32;
+    DevCfg dc = e->dc;
+    dc.B = LB;
     LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), e->smem_bytes, a.pdl_mode ? 1 : 0};
     // register bucket of the add_inverts inverse (qg_gf2.cuh); 0 = generic shared-memory path (dimension > 32, or no inverts)
     int inv = 0;
     if (e->dc.add_inverts && e->inv_bucket_enabled && (e->L.kind == QG_ENV_LINEAR_FUNCTION || e->L.kind == QG_ENV_CLIFFORD))
         inv = e->L.D <= 8 ? 8 : e->L.D <= 16 ? 16 : e->L.D <= 32 ? 32 : 0;
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: CUDA_OK(launch_step_kind<QG_ENV_PERMUTATION>(mode, inv, e->dc, a, g, st)); break;
-        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_step_kind<QG_ENV_LINEAR_FUNCTION>(mode, inv, e->dc, a, g, st)); break;
-        case QG_ENV_CLIFFORD: CUDA_OK(launch_step_kind<QG_ENV_CLIFFORD>(mode, inv, e->dc, a, g, st)); break;
-        default: CUDA_OK(launch_step_kind<QG_ENV_PAULI_NETWORK>(mode, inv, e->dc, a, g, st)); break;
+        case QG_ENV_PERMUTATION: CUDA_OK(launch_step_kind<QG_ENV_PERMUTATION>(mode, inv, dc, a, g, st)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_step_kind<QG_ENV_LINEAR_FUNCTION>(mode, inv, dc, a, g, st)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(launch_step_kind<QG_ENV_CLIFFORD>(mode, inv, dc, a, g, st)); break;
+        default: CUDA_OK(launch_step_kind<QG_ENV_PAULI_NETWORK>(mode, inv, dc, a, g, st)); break;
     }
     return QG_OK;
 }
@@ -672,6 +676,43 @@ int qg_search_step_bits(qg_engine* e, const float* weights_dev, int32_t determin
     if (num_active_dev) CUDA_OK(cudaMemsetAsync(num_active_dev, 0, 4, st));
     StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs_bits = obs_bits_dev; a.chosen = chosen_dev; a.num_active = num_active_dev;
     return launch_step(e, MODE_SEARCH, a, st);
+}
+
+// ---- tree-search support: clone + step through record slots, cross-engine record copies -----------------------------------
+namespace qg {
+__global__ void k_copy_records(DevCfg dst, const int32_t* __restrict__ dst_slot, const uint32_t* __restrict__ src_rec, int64_t src_bpad, int W, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t slot = dst_slot ? (int64_t)dst_slot[i] : i;
+    for (int w = 0; w < W; ++w) {
+        uint32_t v = src_rec[(size_t)w * src_bpad + i];
+        if (w == HD_FLAGS) v &= (1u << FL_LEN_SHIFT) - 1u;       // the copy restarts its solution log
+        dst.rec[(size_t)w * dst.Bpad + slot] = v;
+    }
+}
+}  // namespace qg
+
+int qg_step_slots(qg_engine* e, int64_t count, const int32_t* src_slot_dev, const int32_t* dst_slot_dev, const int32_t* actions_dev, float* obs_dev,
+                  uint32_t* obs_bits_dev, uint8_t* mask_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !src_slot_dev || !dst_slot_dev || !actions_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (count < 0 || count > e->B) { set_error("qg_step_slots: count must be within the slot pool"); return QG_ERR_INVALID; }
+    StepArgs a{}; a.actions = actions_dev; a.src_slot = src_slot_dev; a.dst_slot = dst_slot_dev; a.skip_negative = 1;
+    a.obs = obs_dev; a.obs_bits = obs_bits_dev; a.mask = mask_dev; a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    return launch_step(e, MODE_STEP, a, (cudaStream_t)stream, count);
+}
+
+int qg_copy_records(qg_engine* dst, const int32_t* dst_slot_dev, qg_engine* src, int64_t count, qg_stream stream) {
+    if (!dst || !src) { set_error("null engine"); return QG_ERR_INVALID; }
+    if (dst->L.kind != src->L.kind || dst->L.n != src->L.n || dst->L.W != src->L.W || dst->L.A != src->L.A || dst->device != src->device) {
+        set_error("qg_copy_records: the engines must share env kind, qubits, gateset size and device"); return QG_ERR_INVALID;
+    }
+    if (count < 0 || count > src->B || (!dst_slot_dev && count > dst->B)) { set_error("qg_copy_records: count outside the batch"); return QG_ERR_INVALID; }
+    if (count == 0) return QG_OK;
+    CUDA_OK(cudaSetDevice(dst->device));
+    k_copy_records<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst->dc, dst_slot_dev, src->dc.rec, src->Bpad, dst->L.W, count);
+    CUDA_OK(cudaGetLastError());
+    if (dst->L.kind == QG_ENV_CLIFFORD && !src->all_symplectic) dst->all_symplectic = false;
+    return QG_OK;
 }
 
 int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream) {

@@ -22,6 +22,9 @@ struct StepArgs {
     int32_t deterministic;
     float* obs;                  // [B][obs_size] or null
     uint32_t* obs_bits;          // [B][ceil(obs_size/32)] or null: the observation as packed bits (bit i of an env = entry i), env-major
+    const int32_t* src_slot;     // [B] or null: logical env i reads its record from record slot src_slot[i] ...
+    const int32_t* dst_slot;     // [B] or null: ... and writes it to slot dst_slot[i] (clone + step in one pass: tree search nodes)
+    int32_t skip_negative;       // MODE_STEP: a negative action leaves the env untouched (no step, no outputs) instead of flagging it
     uint8_t* mask;               // [B][A] or null
     float* reward; uint8_t* done; uint8_t* success;   // [B] or null
     int32_t* chosen;             // [B] or null    (MODE_SEARCH)
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
         }
     }
     if (live) {
-        const uint32_t* src = c.rec + env;
+        const uint32_t* src = c.rec + (a.src_slot ? (int64_t)a.src_slot[env] : env);
 #pragma unroll 4
         for (int w = 0; w < c.W; ++w, src += c.Bpad) cp_async_4(&R[w], src);       // all W loads in flight at once
         cp_async_wait_all();
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
             int action = -1;
             if (MODE == MODE_STEP) {
                 action = next_action;
+                if (a.skip_negative && action < 0) enabled = false;
                 if (t + 1 < a.nsteps) {
                     next_action = a.actions[(size_t)(t + 1) * a.in_stride + env];
                     if (a.coins) next_coin = a.coins[(size_t)(t + 1) * a.in_stride + env];
@@ -738,7 +742,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
         R[HD_DEPTH] = depth; R[HD_FLAGS] = flags; R[HD_TICK] = tick;
         if (KIND == QG_ENV_PAULI_NETWORK) { X[PX_PLO] = pr.plo; X[PX_PHI] = pr.phi; X[PX_ALIVE] = pr.alive; X[PX_ORD0] = pr.ord0; X[PX_ORD1] = pr.ord1; X[PX_MISC] = pr.misc; }
         if (MODE != MODE_OBSERVE) {
-            uint32_t* dst = c.rec + env;
+            uint32_t* dst = c.rec + (a.dst_slot ? (int64_t)a.dst_slot[env] : env);
 #pragma unroll 4
             for (int w = 0; w < c.W; ++w, dst += c.Bpad) *dst = R[w];
         } else if (KIND == QG_ENV_PAULI_NETWORK) {

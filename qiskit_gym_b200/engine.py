@@ -308,6 +308,24 @@ class BatchedEnv:
                                         _dptr(num_active), self._stream()))
         return obs_bits
 
+    # ------------------------------------------------------------------ record slots (tree search)
+    def step_slots(self, src_slot: torch.Tensor, dst_slot: torch.Tensor, actions: torch.Tensor, obs: torch.Tensor | None = None,
+                   obs_bits: torch.Tensor | None = None, reward: torch.Tensor | None = None, done: torch.Tensor | None = None,
+                   success: torch.Tensor | None = None):
+        """Clone + step through record slots (qg_step_slots): logical env i reads slot src_slot[i], plays actions[i] (negative =
+        skip) and writes slot dst_slot[i]; outputs are indexed by i.  The engine's batch is the slot pool."""
+        count = int(actions.numel())
+        for t in (src_slot, dst_slot, actions):
+            assert t.dtype == torch.int32 and t.is_cuda and t.is_contiguous() and t.numel() == count
+        check(lib().qg_step_slots(self._h, count, _dptr(src_slot), _dptr(dst_slot), _dptr(actions), _dptr(obs), _dptr(obs_bits), None,
+                                  _dptr(reward), _dptr(done), _dptr(success), self._stream()))
+
+    def copy_records_from(self, src: "BatchedEnv", dst_slot: torch.Tensor | None = None, count: int | None = None):
+        """Copies the records of envs 0..count-1 of `src` into this engine's slots dst_slot[i] (qg_copy_records)."""
+        count = src.batch if count is None else int(count)
+        assert dst_slot is None or (dst_slot.dtype == torch.int32 and dst_slot.is_cuda and dst_slot.numel() >= count)
+        check(lib().qg_copy_records(self._h, _dptr(dst_slot), src._h, count, self._stream()))
+
     def search_best(self):
         key, env = C.c_int64(), C.c_int64()
         check(lib().qg_search_best(self._h, C.byref(key), C.byref(env), self._stream()))

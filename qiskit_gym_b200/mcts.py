@@ -1,0 +1,131 @@
+"""Batched PUCT tree search on the device: the `num_mcts_searches > 0` branch of the reference's
+`algorithm.solve(state, deterministic, num_searches, num_mcts_searches, C, max_expand_depth)` (rl/synthesis.py:122-124;
+rl/configs.py:30-42 documents the knobs).
+
+`num_searches` rollouts run side by side as in search.RolloutSearch; before each decision every rollout grows its own tree
+of `num_mcts_searches` simulations from its current env state, and the decision is drawn from the root's visit counts
+instead of the raw policy output.  The tree bookkeeping (PUCT descent, node creation, return back-up) is csrc/qg_mcts.cu;
+a child node's env is the parent's record cloned and stepped in one pass through a pool of record slots
+(`qg_step_slots`); the policy evaluates all new leaves of a simulation round in one batch.
+
+twisterl's own tree search is not in the reference tree: the protocol (stated in csrc/qg_mcts.cu) is this engine's, and
+`max_expand_depth` — whose exact meaning cannot be recovered from the reference — is accepted and must be 1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import torch
+
+from . import _abi
+from ._lib import check, lib
+from .engine import BatchedEnv, _dptr
+from .search import SearchResult, decode_key, reduce_best
+
+
+class TreeArrays:
+    """Device arrays of `num_trees` trees with `node_cap` nodes (qg_mcts_tree)."""
+
+    def __init__(self, num_trees: int, node_cap: int, num_actions: int, device):
+        R, NC, A = num_trees, node_cap, num_actions
+        f32, i32 = torch.float32, torch.int32
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        self.prior, self.visits, self.value_sum, self.child = z((R, NC, A), f32), z((R, NC, A), i32), z((R, NC, A), f32), z((R, NC, A), i32)
+        self.node_reward, self.node_final, self.node_count = z((R, NC), f32), z((R, NC), torch.uint8), z((R,), i32)
+        self.path_node, self.path_action, self.path_len, self.new_node = z((R, NC), i32), z((R, NC), i32), z((R,), i32), z((R,), i32)
+        self.c = _abi.QgMctsTree(R, NC, A, *[t.data_ptr() for t in (self.prior, self.visits, self.value_sum, self.child, self.node_reward, self.node_final,
+                                                                     self.node_count, self.path_node, self.path_action, self.path_len, self.new_node)])
+        self.device = device
+
+    def _st(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def begin(self, root_prior, root_final):
+        check(lib().qg_mcts_begin(C.byref(self.c), _dptr(root_prior), _dptr(root_final), self._st()))
+
+    def select(self, c_puct, src_slot, dst_slot, action):
+        check(lib().qg_mcts_select(C.byref(self.c), C.c_float(c_puct), _dptr(src_slot), _dptr(dst_slot), _dptr(action), self._st()))
+
+    def backup(self, prior, value, reward, done):
+        check(lib().qg_mcts_backup(C.byref(self.c), _dptr(prior), _dptr(value), _dptr(reward), _dptr(done), self._st()))
+
+    def root_weights(self, out):
+        check(lib().qg_mcts_root_weights(C.byref(self.c), _dptr(out), self._st()))
+        return out
+
+
+class MCTSSearch:
+    """`solve` with a tree search per decision.  Owns the rollout engine (R envs, solutions tracked) and a slot-pool engine of
+    R * (num_mcts_searches + 1) records for the tree nodes."""
+
+    def __init__(self, env_kind, num_qubits, gateset, policy: torch.nn.Module, num_rollouts: int, num_mcts_searches: int, C: float = 2 ** 0.5,
+                 device=None, max_depth: int = 128, **env_kwargs):
+        assert num_mcts_searches >= 1
+        env_kwargs.setdefault("add_perms", False)
+        self.env = BatchedEnv(env_kind, num_qubits, gateset, num_rollouts, device=device, max_depth=max_depth, **env_kwargs)
+        pool_kwargs = dict(env_kwargs, track_solution=False)
+        self.S, self.NC, self.R = int(num_mcts_searches), int(num_mcts_searches) + 1, int(num_rollouts)
+        self.pool = BatchedEnv(env_kind, num_qubits, gateset, self.R * self.NC, device=self.env.device_index, max_depth=max_depth, **pool_kwargs)
+        self.policy = policy.to(self.env.device).eval()
+        self.c_puct, self.max_depth = float(C), int(max_depth)
+        dev = self.env.device
+        A = self.env.num_actions()
+        self.tree = TreeArrays(self.R, self.NC, A, dev)
+        i32 = torch.int32
+        self.root_slots = (torch.arange(self.R, device=dev, dtype=torch.int64) * self.NC).to(i32)
+        self.src, self.dst, self.act = (torch.zeros(self.R, dtype=i32, device=dev) for _ in range(3))
+        self.leaf_obs = torch.zeros((self.R,) + tuple(self.env.obs_shape()), dtype=torch.float32, device=dev)
+        self.leaf_reward = torch.zeros(self.R, dtype=torch.float32, device=dev)
+        self.leaf_done = torch.zeros(self.R, dtype=torch.bool, device=dev)
+        self.weights = torch.zeros((self.R, A), dtype=torch.float32, device=dev)
+        self.num_active = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hook = None            # tests: hook(kind, decision, simulation, tensors...) sees the policy outputs the trees consumed
+
+    def _policy(self, obs):
+        with torch.no_grad():
+            logits, value = self.policy(obs)
+            return torch.softmax(logits.float(), dim=-1).contiguous(), value.float().reshape(-1).contiguous()
+
+    def decide(self, decision: int = 0):
+        """One decision's tree search for every rollout; leaves the root visit weights in self.weights."""
+        env, pool, tree = self.env, self.pool, self.tree
+        env.observe()
+        _, done, _, _ = env.status()
+        prior, _ = self._policy(env.obs)
+        if self.hook:
+            self.hook("root", decision, -1, prior, None)
+        pool.copy_records_from(env, self.root_slots)
+        tree.begin(prior, done)
+        for s in range(self.S):
+            tree.select(self.c_puct, self.src, self.dst, self.act)
+            pool.step_slots(self.src, self.dst, self.act, obs=self.leaf_obs, reward=self.leaf_reward, done=self.leaf_done)
+            p, v = self._policy(self.leaf_obs)
+            if self.hook:
+                self.hook("leaf", decision, s, p, v)
+            tree.backup(p, v, self.leaf_reward, self.leaf_done)
+        return tree.root_weights(self.weights)
+
+    def solve(self, state, deterministic: bool = False, seed: int = 0, first_rollout_id: int = 0, check_every: int = 4, group=None) -> SearchResult:
+        env = self.env
+        t0 = time.perf_counter()
+        env.set_state(state)
+        env.search_begin(seed, first_rollout_id)
+        its = 0
+        while its < self.max_depth:
+            self.decide(its)
+            env.search_step(self.weights, deterministic=deterministic, obs=False, num_active=self.num_active)
+            its += 1
+            if its % check_every == 0 and int(self.num_active.item()) == 0:
+                break
+        key, idx = env.search_best()
+        ok, rid = decode_key(key)
+        sol = env.solution(idx) if (ok and idx >= 0) else None
+        world = 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(group)
+            key, sol = reduce_best(key, sol, group=group, device=env.device if dist.get_backend(group) == "nccl" else None)
+            ok, rid = decode_key(key)
+        return SearchResult(actions=sol if ok else None, key=key, rollout_id=rid, success=ok, iterations=its,
+                            seconds=time.perf_counter() - t0, rollouts=self.R * world)

@@ -7,7 +7,8 @@ the device (and across ranks).  Config files and checkpoints are the reference's
 `RLSynthesis.save` (79-93) and the policy `state_dict` `.pt` (examples/models/*), so models trained with the
 reference load unchanged.
 
-Out of scope here: `learn()` (PPO / AlphaZero training lives in twisterl) and MCTS (`num_mcts_searches > 0`).
+`num_mcts_searches > 0` runs the device tree search of mcts.py.  Out of scope here: `learn()` (the PPO / AlphaZero optimisation loop
+lives in twisterl; collector.RolloutCollector is the data-collection half).
 """
 from __future__ import annotations
 
@@ -88,11 +89,26 @@ class RLSynthesis:
             self._searches[num_searches] = rs
         return rs
 
+    def _mcts(self, num_searches: int, num_mcts_searches: int, C: float):
+        from .mcts import MCTSSearch
+        key = ("mcts", num_searches, num_mcts_searches, C)
+        ms = self._searches.get(key)
+        if ms is None:
+            cfg = dict(self.env_config)
+            kind = _ENV_KINDS[self.env.cls_name]
+            kw = {k: v for k, v in cfg.items() if k not in ("num_qubits", "gateset", "max_depth", "add_perms")}
+            ms = MCTSSearch(kind, cfg["num_qubits"], cfg["gateset"], self.policy, num_searches, num_mcts_searches, C=C, device=self.device,
+                            max_depth=cfg.get("max_depth", 128), add_perms=False, **kw)
+            self._searches[key] = ms
+        return ms
+
     def solve(self, state, deterministic: bool = False, num_searches: int = 100, num_mcts_searches: int = 0, C: float = 2 ** 0.5,
               max_expand_depth: int = 1, seed: int = 0):
         """twisterl `Algorithm.solve`: the action list of the best successful rollout, or None."""
         if num_mcts_searches:
-            raise NotImplementedError("MCTS search is not part of the engine (SURVEY.md §8f row 4)")
+            if max_expand_depth != 1:
+                raise NotImplementedError("max_expand_depth != 1 is not supported by the device tree search (mcts.py)")
+            return self._mcts(int(num_searches), int(num_mcts_searches), float(C)).solve(state, deterministic=deterministic, seed=seed).actions
         return self._search(int(num_searches)).solve(state, deterministic=deterministic, seed=seed).actions
 
     def synth(self, input, deterministic: bool = False, num_searches: int = 100, num_mcts_searches: int = 0, C: float = 2 ** 0.5,
