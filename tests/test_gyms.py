@@ -121,4 +121,61 @@ def test_rlsynthesis_save_roundtrip(tmp_path):
     for (k1, v1), (k2, v2) in zip(rls.policy.state_dict().items(), again.policy.state_dict().items()):
         assert k1 == k2 and bool((v1 == v2).all())
     with pytest.raises(NotImplementedError):
-        rls.solve([0] * 25, num_mcts_searches=4)
+        rls.solve([0] * 25, num_mcts_searches=4, max_expand_depth=2)
+
+
+def _random_target_state(rls, name, rng, n, gs):
+    if name.startswith("perm"):
+        return rls.env.get_state(rng.permutation(n))
+    if name.startswith("lf"):
+        edges = [q for g, q in gs if g.lower() == "cx"]
+        M = np.eye(n, dtype=np.uint8)
+        for _ in range(12):
+            a, b = edges[int(rng.integers(len(edges)))]
+            M[b] ^= M[a]
+        return rls.env.get_state(M)
+    return rls.env.get_state([gs[int(rng.integers(len(gs)))] for _ in range(10)])
+
+
+@pytest.mark.parametrize("name", ["perm_square_3x3", "lf_5_line", "clifford_3q_custom"])
+def test_reference_checkpoints_pin_the_observation_and_action_encoding(name):
+    """The reference's trained policies were trained against the reference's Rust envs.  Driven greedily (one deterministic
+    rollout, no search to paper over mistakes) on this engine they still solve most random targets, while the same network
+    with fresh random weights does not: the observation encoding, the action order and the dynamics the checkpoints learned
+    are the ones implemented here.  This is the only reference-produced artefact that exercises Permutation and Clifford."""
+    import torch
+    from qiskit_gym_b200.rl import RLSynthesis
+    rls = RLSynthesis.from_config_json(os.path.join(MODELS, name + ".json"), os.path.join(MODELS, name + ".pt"))
+    blank = RLSynthesis.from_config_json(os.path.join(MODELS, name + ".json"), None)
+    torch.manual_seed(0)
+    for m in blank.policy.modules():
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.normal_(m.weight, std=0.05)
+    cfg = rls.env_config
+    n, gs = cfg["num_qubits"], [(g, tuple(q)) for g, q in cfg["gateset"]]
+    rng = np.random.default_rng(11)
+    trials, ok_trained, ok_blank = 40, 0, 0
+    for _ in range(trials):
+        state = _random_target_state(rls, name, rng, n, gs)
+        ok_trained += rls.solve(state, deterministic=True, num_searches=1) is not None
+        ok_blank += blank.solve(state, deterministic=True, num_searches=1) is not None
+    assert ok_trained >= 0.8 * trials, f"{name}: trained policy solved {ok_trained}/{trials} greedily"
+    assert ok_blank <= 0.5 * ok_trained, f"{name}: untrained policy solved {ok_blank}/{trials}, trained {ok_trained}"
+
+
+def test_rlsynthesis_tree_search_returns_valid_circuits():
+    from qiskit_gym_b200.rl import RLSynthesis
+    rls = RLSynthesis.from_config_json(os.path.join(MODELS, "perm_square_3x3.json"), os.path.join(MODELS, "perm_square_3x3.pt"))
+    rng = np.random.default_rng(2)
+    solved = 0
+    for t in range(3):
+        target = rng.permutation(9)
+        circ = rls.synth(target, deterministic=True, num_searches=4, num_mcts_searches=8, seed=t)
+        if circ is None:
+            continue
+        st = np.argsort(target)
+        for g, (a, b) in circ:
+            st[[a, b]] = st[[b, a]]
+        assert np.array_equal(st, np.arange(9))
+        solved += 1
+    assert solved >= 2
