@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-per-step", action="store_true", help="skip the one-launch-per-env-step leg (profiling runs)")
     ap.add_argument("--no-synth", action="store_true", help="skip the synth-search leg (BASELINE.json configs[4])")
     ap.add_argument("--no-packed", action="store_true", help="skip the packed-bit observation leg (qg_replay_bits)")
+    ap.add_argument("--no-collector", action="store_true", help="skip the policy-in-the-loop collector leg (collector.RolloutCollector)")
     ap.add_argument("--synth-rollouts", type=int, default=1000, help="num_searches per GPU of the synth leg")
     ap.add_argument("--synth-searches", type=int, default=5, help="timed searches of the synth leg")
     return ap.parse_args()
@@ -384,6 +385,7 @@ def run_ours(args):
                                  "note": "qg_step_host: one synchronous H2D + launch + D2H round trip per env-step (host-side collector)"}}
 
     synth = None if args.no_synth else run_synth(args, dev, local, rank, world)
+    collector = None if args.no_collector else run_collector(args, dev, local, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -430,11 +432,52 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (GF(2)) + f32 reward/obs", "data": "synthetic",
         "config": config_json(args, world, {"obs_buffers": nbuf, "cuda_graph": True}),
         "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "per_step_launch": per_step, "cpu_baseline": cpu_baseline,
-        "packed_obs": packed, "synth": synth, "engine_error_flags": errs,
+        "packed_obs": packed, "synth": synth, "collector": collector, "engine_error_flags": errs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_collector(args, dev, local, rank, world):
+    """Policy-in-the-loop data collection on the bench config (what twisterl's PPO collector does on CPU cores, rl/configs.py:133-137):
+    every decision = selective reset + observe + PyTorch BasicPolicy forward + Philox sample + fused step, then GAE on the device.
+    Reported as env-steps/s including the policy; the env-only numbers above are its upper bound."""
+    import torch
+    import torch.distributed as dist
+    from qiskit_gym_b200 import BatchedEnv
+    from qiskit_gym_b200 import workloads as W
+    from qiskit_gym_b200.collector import RolloutCollector
+    from qiskit_gym_b200.search import BasicPolicy
+
+    kind, n, gateset, kw = workload(args)
+    B, T = min(args.envs, 65536), 32
+    pk = dict(kw)
+    if kind != W.PAULI:
+        pk["add_inverts"] = False
+    env = BatchedEnv(kind, n, gateset, B, device=local, difficulty=64, depth_slope=2, max_depth=128, add_perms=False, **pk)
+    torch.manual_seed(0)
+    pol = BasicPolicy(env.obs_shape(), len(gateset), embedding_size=512, common_layers=(256,))
+    col = RolloutCollector(env, pol, use_twists=False, seed=rank)
+    col.collect(4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ro = col.collect(T)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    episodes, success = ro.episode_stats()
+    return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "envs_per_gpu": B, "decisions": T, "ms_per_decision": ms / T,
+            "episodes_finished": episodes,
+            "note": "RolloutCollector.collect: reset_select + observe (dense f32) + PyTorch BasicPolicy 512/256 forward (f32 cuBLAS) + softmax + "
+                    "qg_collect_step + log-prob gather per decision, qg_gae at the end; difficulty 64, random-init policy"}
 
 
 def run_synth(args, dev, local, rank, world):
@@ -479,11 +522,14 @@ def run_synth(args, dev, local, rank, world):
                 "shallow_target": {"success": bool(res_sh.success), "circuit_len": None if res_sh.actions is None else len(res_sh.actions),
                                    "decisions": res_sh.iterations, "ms": 1e3 * res_sh.seconds}}
 
+    persistent = leg("persistent")
     fused = leg("fused")
     torch_leg = leg("torch")
     out = {"metric": "synth rollouts/sec (PermutationGym 27q heavy-hex, num_searches=1000 per GPU)", "rollouts_per_search_per_gpu": R, "searches": args.synth_searches}
-    out.update(fused)
-    out["policy_backend"] = "fused: packed-bit observations -> qg_policy_forward_bits (gather-sum first layer + MLP + softmax in one kernel) -> qg_search_step_bits; 2 launches per decision"
+    out.update(persistent)
+    out["policy_backend"] = ("persistent: the whole search is ONE launch of qg_search_run (each CTA owns 8 rollouts and loops packed observation -> "
+                             "fused policy network -> Philox sample + env step); identical decisions to the two-kernel path")
+    out["two_kernel"] = dict(fused, note="qg_policy_forward_bits + qg_search_step_bits per decision, CUDA graph, PDL")
     out["torch_policy"] = dict(torch_leg, note="same search with the PyTorch BasicPolicy on dense f32 observations (cuBLAS GEMMs + softmax + qg_search_step)")
     out["note"] = ("uniform random 27-permutations, random-init policy (no checkpoint exists for this map): rollouts run to max_depth=128; "
                    "time is host wall clock over whole solve() calls (set_state broadcast, CUDA-graph replays, on-GPU best reduction, "

@@ -263,6 +263,15 @@ QG_API int32_t qg_policy_num_actions(const qg_policy* p);
 QG_API int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev,
                                   float* logits_dev, qg_stream stream);
 
+/* The whole rollout search in ONE launch: every CTA owns 8 rollouts and loops  policy (packed observation -> action weights) ->
+ * sample / arg-max + fused step -> next packed observation  until its rollouts are final or max_decisions decisions were taken;
+ * equivalent to max_decisions rounds of qg_policy_forward_bits + qg_search_step_bits (same bits), without launch gaps or host
+ * round trips.  Call qg_set_state (broadcast), qg_search_begin and qg_observe_bits first; obs_bits_dev uint32[B][qg_obs_words]
+ * and weights_dev float[B][num_actions] are the working buffers; decisions_dev int32[ceil(B/8)] (or NULL) receives the number of
+ * decisions each CTA took.  Then qg_search_best / qg_solution_host as usual. */
+QG_API int qg_search_run(qg_engine* e, qg_policy* policy, int32_t deterministic, int32_t max_decisions, uint32_t* obs_bits_dev,
+                         float* weights_dev, int32_t* decisions_dev, qg_stream stream);
+
 /* ---- tree search (num_mcts_searches > 0, rl/synthesis.py:122-124, rl/configs.py:30-42) ----------------
  * Clone + step through record slots: the engine's batch is a pool of record slots; logical env i (i < count) reads the
  * record in slot src_slot_dev[i], plays actions_dev[i] and writes the result to slot dst_slot_dev[i] (a tree-search child

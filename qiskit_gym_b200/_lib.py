@@ -27,7 +27,7 @@ SYMBOLS = [
     "qg_search_step", "qg_search_best", "qg_read_returns", "qg_reset_select", "qg_collect_step", "qg_gae", "qg_twist_gather",
     "qg_obs_words", "qg_step_bits", "qg_replay_bits", "qg_observe_bits", "qg_search_step_bits",
     "qg_policy_create", "qg_policy_destroy", "qg_policy_num_actions", "qg_policy_forward_bits",
-    "qg_step_slots", "qg_copy_records", "qg_mcts_begin", "qg_mcts_select", "qg_mcts_backup", "qg_mcts_root_weights",
+    "qg_step_slots", "qg_copy_records", "qg_mcts_begin", "qg_mcts_select", "qg_mcts_backup", "qg_mcts_root_weights", "qg_search_run",
 ]
 
 
@@ -124,6 +124,7 @@ def lib():
     L.qg_mcts_select.argtypes = [treep, C.c_float, vp, vp, vp, vp]
     L.qg_mcts_backup.argtypes = [treep, vp, vp, vp, vp, vp]
     L.qg_mcts_root_weights.argtypes = [treep, vp, vp]
+    L.qg_search_run.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -10,6 +10,7 @@
 #include "qg_host.hpp"
 #include "qg_aux_kernels.cuh"
 #include "qg_launch.hpp"
+#include "qg_policy_host.hpp"
 
 using namespace qg;
 
@@ -712,6 +713,32 @@ int qg_copy_records(qg_engine* dst, const int32_t* dst_slot_dev, qg_engine* src,
     k_copy_records<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst->dc, dst_slot_dev, src->dc.rec, src->Bpad, dst->L.W, count);
     CUDA_OK(cudaGetLastError());
     if (dst->L.kind == QG_ENV_CLIFFORD && !src->all_symplectic) dst->all_symplectic = false;
+    return QG_OK;
+}
+
+int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t max_decisions, uint32_t* obs_bits_dev, float* weights_dev,
+                  int32_t* decisions_dev, qg_stream stream) {
+    if (!e || !pol || !obs_bits_dev || !weights_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (pol->device != e->device) { set_error("qg_search_run: policy and engine live on different devices"); return QG_ERR_INVALID; }
+    if (pol->d.obs_size != e->L.obs_size || pol->d.width[pol->d.num_layers - 1] != e->L.A) { set_error("qg_search_run: the policy's observation size / action count do not match the env"); return QG_ERR_INVALID; }
+    if (e->L.kind == QG_ENV_PERMUTATION && e->L.OW == 0) { set_error("packed observations need num_qubits <= 64 for Permutation"); return QG_ERR_UNSUPPORTED; }
+    if (max_decisions < 0) { set_error("qg_search_run: negative decision budget"); return QG_ERR_INVALID; }
+    if (e->B == 0 || max_decisions == 0) return QG_OK;
+    CUDA_OK(cudaSetDevice(e->device));
+    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs_bits = obs_bits_dev;
+    a.nsteps = 1; a.ring = 1; a.pdl_mode = 0; a.num_sms = e->num_sms;
+    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4; a.symplectic = e->all_symplectic ? 1 : 0;
+    a.magic_ow = magic40(((uint32_t)e->L.obs_size + 31u) / 32u);
+    const size_t step_smem = (size_t)e->sm_warp_words * 4 + 16;
+    if (policy_smem_bytes(pol->d) + step_smem > 220 * 1024) { set_error("qg_search_run: policy + env do not fit one SM's shared memory"); return QG_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (e->L.kind) {
+        case QG_ENV_PERMUTATION: CUDA_OK(launch_search_fused<QG_ENV_PERMUTATION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_search_fused<QG_ENV_LINEAR_FUNCTION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(launch_search_fused<QG_ENV_CLIFFORD>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
+        default: CUDA_OK(launch_search_fused<QG_ENV_PAULI_NETWORK>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
+    }
     return QG_OK;
 }
 

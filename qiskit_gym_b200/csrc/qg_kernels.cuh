@@ -510,19 +510,17 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
     }
 }
 
-// INV: register bucket of the add_inverts inverse (qg_gf2.cuh): 0 = generic shared-memory Gauss-Jordan (or no inverts),
-// 8 / 16 / 32 = matrix dimension bound of the register-resident versions.
+// The work of ONE warp on its tile of `cnt` (<= 32) consecutive environments starting at e0: record load, `a.nsteps` steps
+// (phase 1 + phase 2 each), record write-back.  wbase: the warp's private shared-memory region (a.sm_warp_words words), lut: the
+// CTA's nibble -> float4 table (only read when a.obs is set).  Returns the ballot of the environments that were stepped in the
+// last step (MODE_SEARCH: rollouts that were not final).  k_step calls it once per warp; the fused search kernel
+// (qg_search_fused.cuh) calls it once per decision for the rollouts its CTA owns.
+// resident: the warp's shared-memory region still holds the tile's records from its previous call (the fused search kernel calls
+// it once per decision for the same environments): skip the load.  weights_tile: MODE_SEARCH action weights of the tile's
+// environments, [cnt][A] starting at environment e0 (may point to shared memory), or null to read a.weights[env * A].
 template <int KIND, int MODE, int INV>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (a.pdl_mode == 1) pdl_launch_dependents();
-    const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
-    if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
-    const int cnt = (int)min((int64_t)32, c.B - e0);
-    uint32_t* const wbase = smem + kLutWords + (size_t)warp * a.sm_warp_words;
-    const uint32_t* const lut = smem;                // nibble -> float4 table, first kLutWords words of the CTA's shared memory
-    if (a.obs) lut_fill(smem, lane);
+__device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a, uint32_t* const wbase, const uint32_t* const lut, const int lane,
+                                              const int64_t e0, const int cnt, const bool resident = false, const float* const weights_tile = nullptr) {
     typedef SmWords<kStride> Wd;
     const int64_t env = e0 + lane;
     const bool live = lane < cnt;
@@ -531,21 +529,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
     const Wd SCR{wbase + a.sm_scr + lane}, O{wbase + a.sm_obs + lane};
     const bool obs_from_O = (KIND == QG_ENV_PAULI_NETWORK) || (KIND == QG_ENV_PERMUTATION && c.OW > 0);
     const uint32_t* const obs_bits = wbase + (obs_from_O ? a.sm_obs : c.off_state * kStride);
-
-    if (a.pdl_mode) pdl_wait();                      // the previous grid of the stream wrote the records
-    if (a.pdl_mode == 2) pdl_launch_dependents();
-    if (a.stagger_ns > 0) {
-        const long long wait_ns = (long long)(((int)blockIdx.x / a.num_sms) * kWarpsPerCta + warp) * a.stagger_ns;
-        long long t0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 >= wait_ns) break;
-            __nanosleep(200);
-        }
-    }
-    if (live) {
+    uint32_t last_en_bits = 0;
+    if (live && !resident) {
         const uint32_t* src = c.rec + (a.src_slot ? (int64_t)a.src_slot[env] : env);
 #pragma unroll 4
         for (int w = 0; w < c.W; ++w, src += c.Bpad) cp_async_4(&R[w], src);       // all W loads in flight at once
@@ -583,7 +568,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
                 // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
                 enabled = !(depth == 0 || success);
                 if (enabled) {
-                    const float* wt = a.weights + (size_t)env * c.A;
+                    const float* wt = weights_tile ? weights_tile + (size_t)lane * c.A : a.weights + (size_t)env * c.A;
                     if (a.deterministic) {
                         float best = wt[0]; action = 0;
                         for (int k = 1; k < c.A; ++k) { const float v = wt[k]; if (v > best) { best = v; action = k; } }
@@ -735,6 +720,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
             else expand_mask<MODE, 1>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
         }
         if (++slot == a.ring) slot = 0;
+        last_en_bits = en_bits;
         __syncwarp();                                 // the next step's phase 1 rewrites the bits phase 2 just read
     }
 
@@ -749,6 +735,36 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
             c.rec[(size_t)(c.off_extra + PX_MISC) * c.Bpad + env] = pr.misc;
         }
     }
+    return last_en_bits;
+}
+
+// INV: register bucket of the add_inverts inverse (qg_gf2.cuh): 0 = generic shared-memory Gauss-Jordan (or no inverts),
+// 8 / 16 / 32 = matrix dimension bound of the register-resident versions.
+template <int KIND, int MODE, int INV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.pdl_mode == 1) pdl_launch_dependents();
+    const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
+    if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
+    const int cnt = (int)min((int64_t)32, c.B - e0);
+    uint32_t* const wbase = smem + kLutWords + (size_t)warp * a.sm_warp_words;
+    const uint32_t* const lut = smem;                // nibble -> float4 table, first kLutWords words of the CTA's shared memory
+    if (a.obs) lut_fill(smem, lane);
+    if (a.pdl_mode) pdl_wait();                      // the previous grid of the stream wrote the records
+    if (a.pdl_mode == 2) pdl_launch_dependents();
+    if (a.stagger_ns > 0) {
+        const long long wait_ns = (long long)(((int)blockIdx.x / a.num_sms) * kWarpsPerCta + warp) * a.stagger_ns;
+        long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 >= wait_ns) break;
+            __nanosleep(200);
+        }
+    }
+    step_tile<KIND, MODE, INV>(c, a, wbase, lut, lane, e0, cnt);
 }
 
 // ---- load (set_state / constructor) --------------------------------------------------------------

@@ -1,0 +1,402 @@
+// qg_policy_kernels.cuh — device code of the fused policy network (see qg_policy.cu for the design notes); shared by the
+// stand-alone kernel k_policy_mlp and the fused search kernel (qg_search_fused.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qg {
+
+
+constexpr int kPolRows = 8;          // batch rows per CTA
+constexpr int kPolHalf = 256;         // threads that together own all output features of a layer (feature j = thread + i * 256)
+constexpr int kPolHalves = 2;         // the inputs of a layer are split over this many such groups (partial sums combined in shared memory)
+constexpr int kPolConsumers = kPolHalf * kPolHalves;   // 16 compute warps
+constexpr int kPolMaxWidth = 1024;    // widest layer (4 features per thread)
+constexpr int kPolThreads = kPolConsumers + 32;   // + 1 producer warp
+constexpr int kPolMaxLayers = 8;
+constexpr int kPolStages = 4;        // weight tiles in flight
+constexpr int kPolTileFloats = 4096; // 16 KB per weight tile
+constexpr int kPolPartFloats = kPolMaxWidth * 8;   // partial sums handed between the thread groups: 1024 features (or 16 warps x 64 features) x 8 rows
+
+struct PolicyDev {
+    int32_t num_layers, obs_size, obs_words;
+    int32_t width[kPolMaxLayers];        // output features of layer l (layer 0 consumes the observation)
+    int32_t stride[kPolMaxLayers];       // width rounded up to a multiple of 4 floats: row stride of the transposed weights
+    const float* wt[kPolMaxLayers];      // transposed weights [in][stride]
+    const float* bias[kPolMaxLayers];
+    int32_t act0_floats, act1_floats;    // activation buffers ([feature][row]); act1 also holds the first layer's 0/1 inputs
+};
+
+// ---- mbarrier / bulk-copy primitives (weights stream L2 -> shared memory with cp.async.bulk, no register staging) ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE;\n"
+        " bra WAIT_LOOP;\n"
+        "DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes),
+                 "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kPolConsumers) : "memory"); }
+
+// Rows of layer l's transposed weights consumed per tile
+__device__ __forceinline__ int tile_rows(const PolicyDev& p, int l) { return max(1, kPolTileFloats / p.stride[l]); }
+__device__ __forceinline__ int layer_tiles(const PolicyDev& p, int l, int U) {
+    const int K = l == 0 ? U : p.width[l - 1], kt = tile_rows(p, l);
+    return (K + kt - 1) / kt;
+}
+
+__device__ __forceinline__ void cp_async_16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// acc[i][r] += tile[u][j_i] * h[u][r] over the weight rows u = u0, u0 + ustep, .. of one tile (h: [u][8] activations, one 32-byte
+// broadcast per u)
+template <int NI>
+__device__ __forceinline__ void fma_tile(float (&acc)[NI][kPolRows], const float* __restrict__ tile, const float4* __restrict__ h, int rows, int ostr, const int (&jc)[NI],
+                                         int u0, int ustep) {
+#pragma unroll 4
+    for (int u = u0; u < rows; u += ustep) {
+        const float4 h0 = h[2 * u], h1 = h[2 * u + 1];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const float w = tile[u * ostr + jc[i]];
+            acc[i][0] = fmaf(w, h0.x, acc[i][0]); acc[i][1] = fmaf(w, h0.y, acc[i][1]);
+            acc[i][2] = fmaf(w, h0.z, acc[i][2]); acc[i][3] = fmaf(w, h0.w, acc[i][3]);
+            acc[i][4] = fmaf(w, h1.x, acc[i][4]); acc[i][5] = fmaf(w, h1.y, acc[i][5]);
+            acc[i][6] = fmaf(w, h1.z, acc[i][6]); acc[i][7] = fmaf(w, h1.w, acc[i][7]);
+        }
+    }
+}
+__device__ __forceinline__ void store_features(float* __restrict__ dst, int j, const float (&v)[kPolRows], bool relu) {
+    float4 lo, hi;
+    lo.x = v[0]; lo.y = v[1]; lo.z = v[2]; lo.w = v[3];
+    hi.x = v[4]; hi.y = v[5]; hi.z = v[6]; hi.w = v[7];
+    if (relu) {
+        lo.x = fmaxf(lo.x, 0.f); lo.y = fmaxf(lo.y, 0.f); lo.z = fmaxf(lo.z, 0.f); lo.w = fmaxf(lo.w, 0.f);
+        hi.x = fmaxf(hi.x, 0.f); hi.y = fmaxf(hi.y, 0.f); hi.z = fmaxf(hi.z, 0.f); hi.w = fmaxf(hi.w, 0.f);
+    }
+    reinterpret_cast<float4*>(dst + (size_t)j * kPolRows)[0] = lo;
+    reinterpret_cast<float4*>(dst + (size_t)j * kPolRows)[1] = hi;
+}
+
+// One layer for the consumer warps: the 512 compute threads are two halves of 256; within a half, thread ht owns the output
+// features ht + i * 256 (NI of them) for all 8 rows, and half h takes the inputs u = h, h + 2, .. of every tile; half 1 hands its
+// partial sums to half 0 through shared memory.
+//   GATHER (the first layer): the layer's K inputs are the listed observation entries uidx[0..K) and its weight rows are scattered;
+//     the consumers fetch them themselves with 16-byte cp.async (a tile = 2 warp instructions per warp; issuing one cp.async.bulk per
+//     row from the producer costs ~130 cycles each) through the ring of kPolStages stages, one named barrier per tile; when done,
+//     thread 0 arrives on `l0done` so the producer warp may start filling the stages.
+//   otherwise: tiles arrive from the producer warp (full / empty mbarriers).
+// (A mapping with 4 consecutive features per thread — one LDS.128 for the weights, 3 loads per 32 FMAs — was measured 40 % slower:
+// its per-tile bookkeeping outweighs the saved shared-memory traffic at 2 inputs per group and tile.)
+template <int NI, bool GATHER>
+__device__ __forceinline__ void consume_layer(const PolicyDev& p, int l, int K, const float* __restrict__ src, float* __restrict__ dst, float* tiles,
+                                              uint64_t* full, uint64_t* empty, uint64_t* l0done, const uint16_t* uidx, float* part, int& G, int tid, int lane) {
+    const int out = p.width[l], ostr = p.stride[l], kt = tile_rows(p, l), nt = (K + kt - 1) / kt;
+    const int half = tid / kPolHalf, ht = tid - half * kPolHalf;
+    float acc[NI][kPolRows];
+    int jc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int j = ht + i * kPolHalf;
+        jc[i] = min(j, ostr - 1);                          // out-of-range features read a valid word and are never written
+        const float b = (half == 0 && j < out) ? __ldg(p.bias[l] + j) : 0.0f;
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) acc[i][r] = b;
+    }
+    const bool active = NI > 1 || (ht & ~31) < out;        // warp-uniform: this warp owns at least one real feature
+    if constexpr (GATHER) {
+        const int cpr = ostr >> 2;                         // 16-byte chunks per weight row
+        const float* __restrict__ wt = p.wt[l];
+        auto issue = [&](int t) {
+            if (t < nt) {
+                float* tile = tiles + (size_t)(t % kPolStages) * kPolTileFloats;
+                const int k0 = t * kt, total = min(kt, K - k0) * cpr;
+                for (int ch = tid; ch < total; ch += kPolConsumers) {
+                    const int u = ch / cpr, cc = ch - u * cpr;
+                    cp_async_16(tile + (size_t)u * ostr + cc * 4, wt + (size_t)uidx[k0 + u] * ostr + cc * 4);
+                }
+            }
+            cp_async_commit();
+        };
+        for (int t = 0; t < kPolStages - 1; ++t) issue(t);
+        for (int t = 0; t < nt; ++t) {
+            cp_async_wait<kPolStages - 2>();               // this thread's part of tile t has landed
+            consumers_sync();                              // everybody's part has, and everybody is done with tile t-1
+            issue(t + kPolStages - 1);                     // into the stage tile t-1 used
+            if (active) {
+                const int k0 = t * kt;
+                fma_tile<NI>(acc, tiles + (size_t)(t % kPolStages) * kPolTileFloats, reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows), min(kt, K - k0), ostr, jc,
+                             half, kPolHalves);
+            }
+        }
+        cp_async_wait<0>();
+        consumers_sync();                                  // the stages are free: hand them to the producer warp
+        if (tid == 0) mbar_arrive(l0done);
+    } else {
+        for (int t = 0; t < nt; ++t, ++G) {
+            const int stage = G % kPolStages;
+            mbar_wait(full + stage, (uint32_t)((G / kPolStages) & 1));
+            if (active) {
+                const int k0 = t * kt;
+                fma_tile<NI>(acc, tiles + (size_t)stage * kPolTileFloats, reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows), min(kt, K - k0), ostr, jc, half,
+                             kPolHalves);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);     // this warp is done with the stage
+        }
+    }
+    // combine the halves' partial sums (half 1 -> shared memory -> half 0), activation, store
+    if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int j = ht + i * kPolHalf;
+            if (j < out) store_features(part, j, acc[i], false);
+        }
+    }
+    consumers_sync();
+    if (half == 0) {
+        const bool last = l == p.num_layers - 1;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int j = ht + i * kPolHalf;
+            if (j < out) {
+                const float4 lo = reinterpret_cast<const float4*>(part + (size_t)j * kPolRows)[0], hi = reinterpret_cast<const float4*>(part + (size_t)j * kPolRows)[1];
+                acc[i][0] += lo.x; acc[i][1] += lo.y; acc[i][2] += lo.z; acc[i][3] += lo.w;
+                acc[i][4] += hi.x; acc[i][5] += hi.y; acc[i][6] += hi.z; acc[i][7] += hi.w;
+                store_features(dst, j, acc[i], !last);
+            }
+        }
+    }
+}
+
+// A narrow layer (at most 64 output features, e.g. the action head): with one feature per thread only two warps would work and the
+// layer would be a latency-bound chain over its K inputs, so the inputs are split over the 16 warps instead (warp w takes the rows
+// u = w, w+16, .. of every tile; lane j owns features j and j+32), the partial sums are combined through shared memory in warp
+// order and the bias is added last.
+__device__ __forceinline__ void consume_layer_narrow(const PolicyDev& p, int l, int K, const float* __restrict__ src, float* __restrict__ dst, const float* tiles,
+                                                     uint64_t* full, uint64_t* empty, float* part, int& G, int tid, int lane) {
+    const int out = p.width[l], ostr = p.stride[l], kt = tile_rows(p, l), nt = (K + kt - 1) / kt, warp = tid >> 5;
+    float acc[2][kPolRows];
+    const int jc[2] = {min(lane, ostr - 1), min(lane + 32, ostr - 1)};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) acc[i][r] = 0.0f;
+    for (int t = 0; t < nt; ++t, ++G) {
+        const int stage = G % kPolStages;
+        mbar_wait(full + stage, (uint32_t)((G / kPolStages) & 1));
+        const int k0 = t * kt;
+        fma_tile<2>(acc, tiles + (size_t)stage * kPolTileFloats, reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows), min(kt, K - k0), ostr, jc, warp, kPolConsumers / 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+    }
+    // part: [warp][64 features][8 rows]
+#pragma unroll
+    for (int i = 0; i < 2; ++i) store_features(part + (size_t)warp * 64 * kPolRows, lane + 32 * i, acc[i], false);
+    consumers_sync();
+    if (tid < out) {
+        float v[kPolRows];
+        const float b = __ldg(p.bias[l] + tid);
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) v[r] = 0.0f;
+        for (int w = 0; w < kPolConsumers / 32; ++w) {
+            const float4 lo = reinterpret_cast<const float4*>(part + ((size_t)w * 64 + tid) * kPolRows)[0];
+            const float4 hi = reinterpret_cast<const float4*>(part + ((size_t)w * 64 + tid) * kPolRows)[1];
+            v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w; v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+        }
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) v[r] += b;
+        store_features(dst, tid, v, l != p.num_layers - 1);
+    }
+}
+
+// ---- shared-memory plan of one policy CTA ---------------------------------------------------------------------------------------
+struct PolicySmem {
+    float* tiles;        // [kPolStages][kPolTileFloats] weight tiles
+    float* act0;         // [act0_floats]
+    float* act1;         // [act1_floats]  (also the first layer's 0/1 inputs)
+    uint64_t* full;      // [kPolStages]
+    uint64_t* empty;     // [kPolStages]
+    uint64_t* l0done;    // [1] the consumers are done with the first layer's own use of the stages
+    float* part;         // [kPolPartFloats] partial sums [group][feature][row] of the current layer
+    uint32_t* rowbits;   // [kPolRows][obs_words]
+    int* wcnt;           // [16] per-warp counts, [31] = U
+    uint16_t* uidx;      // [obs_size] observation entries set in any of the CTA's rows
+};
+__host__ __device__ inline size_t policy_smem_bytes(const PolicyDev& p) {
+    size_t b = ((size_t)kPolStages * kPolTileFloats + p.act0_floats + p.act1_floats + kPolPartFloats) * 4 + (2 * kPolStages + 2) * 8 +
+               (size_t)kPolRows * p.obs_words * 4 + 32 * 4 + (size_t)p.obs_size * 2;
+    return (b + 127) / 128 * 128;
+}
+__device__ __forceinline__ PolicySmem policy_smem_carve(const PolicyDev& p, float* sm) {
+    PolicySmem s;
+    s.tiles = sm;
+    s.act0 = s.tiles + kPolStages * kPolTileFloats;
+    s.act1 = s.act0 + p.act0_floats;
+    s.part = s.act1 + p.act1_floats;
+    s.full = reinterpret_cast<uint64_t*>(s.part + kPolPartFloats);
+    s.empty = s.full + kPolStages;
+    s.l0done = s.empty + kPolStages;
+    s.rowbits = reinterpret_cast<uint32_t*>(s.l0done + 2);
+    s.wcnt = reinterpret_cast<int*>(s.rowbits + kPolRows * p.obs_words);
+    s.uidx = reinterpret_cast<uint16_t*>(s.wcnt + 32);
+    return s;
+}
+__device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int tid) {
+    if (tid == 0) {
+        for (int s = 0; s < kPolStages; ++s) { mbar_init(ps.full + s, 1); mbar_init(ps.empty + s, kPolConsumers / 32); }
+        mbar_init(ps.l0done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+}
+
+// One forward pass for the CTA's kPolRows batch rows starting at row0; every one of the kPolThreads threads calls it (it contains
+// __syncthreads).  Warps 0..7 compute (consumers); warp 8 is the producer: one lane streams the weight tiles of all layers, in
+// order, through a ring of kPolStages shared-memory stages (full / empty mbarriers), so no consumer ever waits for copy issue.
+// G is the running tile counter of the ring (same value in every thread; it carries over when the function is called again) and
+// `pass` counts the calls (0, 1, 2, ..).
+// `bits` may have been written earlier by this CTA in the same kernel: it is read with ld.global.cg, never through the
+// non-coherent path.
+// bits == nullptr: ps.rowbits already holds the rows' packed observations (the fused search kernel's step wrote them there).
+// probs_rows: row stride of `probs` is the action count and row r of the CTA goes to probs + (row_base + r) * A, with
+// row_base = row0 for the global [B][A] tensor or 0 for a CTA-private (shared-memory) buffer.
+__device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const PolicySmem& ps, const uint32_t* bits, int64_t row0, int64_t B,
+                                                    float* probs, float* logits_out, int& G, int pass = 0, int64_t probs_row_base = -1) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = tid >= kPolConsumers;
+    float* const tiles = ps.tiles; float* const act0 = ps.act0; float* const act1 = ps.act1;
+    uint64_t* const full = ps.full; uint64_t* const empty = ps.empty;
+    uint32_t* const rowbits = ps.rowbits; int* const wcnt = ps.wcnt; uint16_t* const uidx = ps.uidx;
+    // ---- 1. the entries set in any of the CTA's rows, ascending, with the rows' 0/1 values as the first layer's input ----
+    if (!producer) {
+        if (bits) {
+            for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) {
+                const int r = i / p.obs_words, w = i - r * p.obs_words;
+                uint32_t word = (row0 + r < B) ? __ldcg(bits + (size_t)(row0 + r) * p.obs_words + w) : 0u;
+                if (w == p.obs_words - 1 && (p.obs_size & 31)) word &= (1u << (p.obs_size & 31)) - 1u;
+                rowbits[i] = word;
+            }
+            consumers_sync();
+        }
+        int U = 0;
+        for (int base = 0; base < p.obs_size; base += kPolConsumers) {
+            const int k = base + tid;
+            uint32_t m = 0;
+            if (k < p.obs_size) {
+#pragma unroll
+                for (int r = 0; r < kPolRows; ++r) m |= ((rowbits[r * p.obs_words + (k >> 5)] >> (k & 31)) & 1u) << r;
+            }
+            const uint32_t vote = __ballot_sync(0xFFFFFFFFu, m != 0);
+            if (lane == 0) wcnt[warp] = __popc(vote);
+            consumers_sync();
+            int before = U, total = U;
+#pragma unroll
+            for (int w2 = 0; w2 < kPolConsumers / 32; ++w2) { const int c = wcnt[w2]; if (w2 < warp) before += c; total += c; }
+            if (m) {
+                const int at = before + __popc(vote & ((1u << lane) - 1u));
+                uidx[at] = (uint16_t)k;
+                float4 lo, hi;
+                lo.x = (m & 1u) ? 1.f : 0.f; lo.y = (m & 2u) ? 1.f : 0.f; lo.z = (m & 4u) ? 1.f : 0.f; lo.w = (m & 8u) ? 1.f : 0.f;
+                hi.x = (m & 16u) ? 1.f : 0.f; hi.y = (m & 32u) ? 1.f : 0.f; hi.z = (m & 64u) ? 1.f : 0.f; hi.w = (m & 128u) ? 1.f : 0.f;
+                reinterpret_cast<float4*>(act1 + (size_t)at * kPolRows)[0] = lo;
+                reinterpret_cast<float4*>(act1 + (size_t)at * kPolRows)[1] = hi;
+            }
+            U = total;
+            consumers_sync();
+        }
+        if (tid == 0) wcnt[31] = U;
+    }
+    __syncthreads();                               // U and uidx visible to the producer
+    const int U = wcnt[31];
+
+    // ---- 2. producer: streams the contiguous weight rows of the layers after the first, tile after tile (the first layer's rows
+    // are gathered by the consumers themselves, through the same stages: wait until they hand them over)
+    if (producer) {
+        int total = 0;
+        for (int l = 1; l < p.num_layers; ++l) total += layer_tiles(p, l, U);
+        if (lane == 0 && total > 0) {
+            mbar_wait(ps.l0done, (uint32_t)(pass & 1));
+            int g = G;
+            for (int l = 1; l < p.num_layers; ++l) {
+                const int K = p.width[l - 1], kt = tile_rows(p, l), nt = (K + kt - 1) / kt;
+                const uint32_t row_bytes = (uint32_t)p.stride[l] * 4u;
+                for (int t = 0; t < nt; ++t, ++g) {
+                    const int stage = g % kPolStages, k0 = t * kt, rows = min(kt, K - k0);
+                    if (g >= kPolStages) mbar_wait(empty + stage, (uint32_t)(((g / kPolStages) - 1) & 1));
+                    mbar_expect_tx(full + stage, row_bytes * (uint32_t)rows);
+                    bulk_g2s(tiles + (size_t)stage * kPolTileFloats, p.wt[l] + (size_t)k0 * p.stride[l], row_bytes * (uint32_t)rows, full + stage);
+                }
+            }
+        }
+        G += total;
+        return;
+    }
+
+    // ---- 3. consumers ------------------------------------------------------------------------------------------------------
+    float* src = act1;                             // layer 0 reads the 0/1 inputs
+    float* dst = act0;
+    for (int l = 0; l < p.num_layers; ++l) {
+        const int ni = (p.width[l] + kPolHalf - 1) / kPolHalf;
+        if (l == 0) {
+            switch (ni) {
+                case 1: consume_layer<1, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                case 2: consume_layer<2, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                case 3: consume_layer<3, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                default: consume_layer<4, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+            }
+        } else if (p.width[l] <= 64) {
+            consume_layer_narrow(p, l, p.width[l - 1], src, dst, tiles, full, empty, ps.part, G, tid, lane);
+        } else {
+            const int K = p.width[l - 1];
+            switch (ni) {
+                case 1: consume_layer<1, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                case 2: consume_layer<2, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                case 3: consume_layer<3, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                default: consume_layer<4, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+            }
+        }
+        consumers_sync();
+        src = dst;
+        dst = (dst == act0) ? act1 : act0;
+    }
+
+    // ---- 4. softmax over the action logits, warp r <-> row r -------------------------------------------------------------
+    if (warp < kPolRows) {
+        const int64_t row = row0 + warp;
+        if (row < B) {
+            const int A = p.width[p.num_layers - 1];
+            float mx = -INFINITY;
+            for (int a = lane; a < A; a += 32) mx = fmaxf(mx, src[(size_t)a * kPolRows + warp]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            float sum = 0.0f;
+            for (int a = lane; a < A; a += 32) sum += expf(src[(size_t)a * kPolRows + warp] - mx);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            const float inv = 1.0f / sum;
+            for (int a = lane; a < A; a += 32) {
+                const float lg = src[(size_t)a * kPolRows + warp];
+                if (probs) probs[(size_t)((probs_row_base < 0 ? row0 : probs_row_base) + warp) * A + a] = expf(lg - mx) * inv;
+                if (logits_out) logits_out[(size_t)row * A + a] = lg;
+            }
+        }
+    }
+}
+
+}  // namespace qg

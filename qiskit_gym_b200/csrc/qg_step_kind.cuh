@@ -1,6 +1,7 @@
 // qg_step_kind.cuh — definitions behind qg_launch.hpp; included by the per-kind translation units only.
 #pragma once
 #include "qg_launch.hpp"
+#include "qg_search_fused.cuh"
 
 namespace qg {
 
@@ -67,6 +68,7 @@ cudaError_t prepare_step_kind(size_t smem_bytes) {
 
 #define QG_INSTANTIATE_KIND(KIND)                                                                                              \
     template cudaError_t launch_step_kind<KIND>(int, int, const DevCfg&, const StepArgs&, const LaunchGeom&, cudaStream_t);    \
-    template cudaError_t prepare_step_kind<KIND>(size_t);
+    template cudaError_t prepare_step_kind<KIND>(size_t);                                                                      \
+    template cudaError_t launch_search_fused<KIND>(const DevCfg&, const StepArgs&, const PolicyDev&, int, int32_t*, size_t, cudaStream_t);
 
 }  // namespace qg

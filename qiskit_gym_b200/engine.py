@@ -326,6 +326,16 @@ class BatchedEnv:
         assert dst_slot is None or (dst_slot.dtype == torch.int32 and dst_slot.is_cuda and dst_slot.numel() >= count)
         check(lib().qg_copy_records(self._h, _dptr(dst_slot), src._h, count, self._stream()))
 
+    def search_run(self, policy, obs_bits: torch.Tensor, weights: torch.Tensor, max_decisions: int, deterministic: bool = False,
+                   decisions: torch.Tensor | None = None):
+        """The whole rollout search in one launch (qg_search_run); `policy` is a policy.FusedPolicy.  Call set_state,
+        search_begin and observe_bits(obs_bits) first."""
+        assert weights.dtype == torch.float32 and weights.is_cuda and weights.is_contiguous() and weights.numel() == self.batch * self._A
+        assert obs_bits.is_cuda and obs_bits.element_size() == 4 and obs_bits.is_contiguous() and obs_bits.numel() == self.batch * self.obs_words()
+        assert decisions is None or (decisions.dtype == torch.int32 and decisions.numel() >= (self.batch + 7) // 8)
+        check(lib().qg_search_run(self._h, policy._h, 1 if deterministic else 0, int(max_decisions), _dptr(obs_bits), _dptr(weights),
+                                  _dptr(decisions), self._stream()))
+
     def search_best(self):
         key, env = C.c_int64(), C.c_int64()
         check(lib().qg_search_best(self._h, C.byref(key), C.byref(env), self._stream()))

@@ -105,15 +105,17 @@ class RolloutSearch:
     """Device-resident `solve`: owns a BatchedEnv of `num_rollouts` rollouts on one GPU."""
 
     def __init__(self, env_kind, num_qubits, gateset, policy: torch.nn.Module, num_rollouts: int, device=None,
-                 max_depth: int = 128, use_cuda_graph: bool = True, policy_backend: str = "fused", **env_kwargs):
-        """policy_backend: "fused" = packed-bit observations + the one-kernel action network (policy.FusedPolicy);
-        "torch" = dense f32 observations + the PyTorch module (cuBLAS GEMMs, softmax)."""
+                 max_depth: int = 128, use_cuda_graph: bool = True, policy_backend: str = "persistent", **env_kwargs):
+        """policy_backend: "persistent" = the whole search in ONE kernel launch (qg_search_run: every CTA loops policy -> sample ->
+        step for its 8 rollouts); "fused" = two launches per decision (policy.FusedPolicy + qg_search_step_bits) in a CUDA graph;
+        "torch" = dense f32 observations + the PyTorch module (cuBLAS GEMMs, softmax).  "persistent" and "fused" take identical
+        decisions (same kernels' device code, same bits)."""
         env_kwargs.setdefault("add_perms", False)
         self.env = BatchedEnv(env_kind, num_qubits, gateset, num_rollouts, device=device, max_depth=max_depth, **env_kwargs)
         self.policy = policy.to(self.env.device).eval()
-        assert policy_backend in ("fused", "torch")
+        assert policy_backend in ("persistent", "fused", "torch")
         self.backend = policy_backend
-        if policy_backend == "fused":
+        if policy_backend in ("fused", "persistent"):
             from .policy import FusedPolicy
             self.fused = FusedPolicy(self.policy, device=self.env.device)
             self.obs_bits = self.env.new_obs_bits()
@@ -125,6 +127,7 @@ class RolloutSearch:
         self.use_graph = use_cuda_graph
         self._graphs = {}
         self._stream = torch.cuda.Stream(device=dev)
+        self._decisions = torch.zeros((self.B + 7) // 8, dtype=torch.int32, device=dev)
 
     def _iteration(self, deterministic):
         if self.backend == "fused":
@@ -137,7 +140,7 @@ class RolloutSearch:
         self.env.search_step(self.probs, deterministic=deterministic, obs=True, num_active=self.num_active)
 
     def _observe(self):
-        if self.backend == "fused":
+        if self.backend in ("fused", "persistent"):
             self.env.observe_bits(self.obs_bits)
         else:
             self.env.observe()
@@ -162,6 +165,17 @@ class RolloutSearch:
               group=None) -> SearchResult:
         env = self.env
         t0 = time.perf_counter()
+        if self.backend == "persistent":
+            with torch.cuda.stream(self._stream):
+                env.set_state(state)
+                env.search_begin(seed, first_rollout_id)
+                self._observe()
+                env.search_run(self.fused, self.obs_bits, self.probs, self.max_depth, deterministic=deterministic, decisions=self._decisions)
+                key, idx = env.search_best()
+                ok, rid = decode_key(key)
+                sol = env.solution(idx) if (ok and idx >= 0) else None
+                its = int(self._decisions.max().item())
+            return self._finish(key, sol, its, t0, group)
         with torch.cuda.stream(self._stream):
             env.set_state(state)                         # broadcast: every rollout starts from the target
             if self.use_graph:
@@ -181,6 +195,11 @@ class RolloutSearch:
             key, idx = env.search_best()
             ok, rid = decode_key(key)
             sol = env.solution(idx) if (ok and idx >= 0) else None
+        return self._finish(key, sol, its, t0, group)
+
+    def _finish(self, key, sol, its, t0, group):
+        env = self.env
+        ok, rid = decode_key(key)
         world = 1
         try:
             import torch.distributed as dist

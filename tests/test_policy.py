@@ -125,3 +125,38 @@ def test_rollout_search_fused_backend_solves_shallow_targets():
                 assert chk.success()
         results[backend] = solved
         assert solved >= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,deterministic,inverts", [("C1_perm_grid3", False, False), ("clifford3_allgates", False, False), ("lf5_line_swap", False, True),
+                                                        ("pauli3_line", False, False), ("C5_perm27_heavyhex", True, False), ("C1_perm_grid3", False, True)])
+def test_persistent_search_equals_two_kernel_search(name, deterministic, inverts):
+    """qg_search_run (the whole search in one launch) takes exactly the decisions of the per-decision launches of
+    qg_policy_forward_bits + qg_search_step_bits: same returns (f32 bits), same final states, same best rollout, same solution."""
+    from qiskit_gym_b200.search import BasicPolicy, RolloutSearch
+    kind, n, gs, kw = H.config_table()[name]
+    kw = dict(kw)
+    if kind != H.PAULI:
+        kw["add_inverts"] = inverts
+    R = 203
+    torch.manual_seed(2)
+    probe = orc.OracleEnv(kind, n, gs, add_perms=False, **kw)
+    pol = BasicPolicy(probe.obs_shape(), len(gs), embedding_size=64, common_layers=(32,))
+    tgt = orc.OracleEnv(kind, n, gs, difficulty=4, add_perms=False, **kw)
+    tgt.reset(seed=9, env_id=0)
+    if kind == H.PAULI:
+        t = H.random_targets(kind, n, gs, 1, 3, scramble=3, num_rotations=2)
+        state = t[0, : H.payload_lengths(kind, n, t)[0]].tolist()
+    else:
+        state = tgt.raw_state().astype(np.int64).tolist()
+    out = {}
+    for backend in ("fused", "persistent"):
+        rs = RolloutSearch(kind, n, gs, pol, R, max_depth=10, policy_backend=backend, use_cuda_graph=False, **kw)
+        res = rs.solve(state, deterministic=deterministic, seed=5, first_rollout_id=1000)
+        out[backend] = (res.key, res.actions, rs.env.returns().cpu().numpy().view(np.uint32).copy(), [rs.env.get_state(b) for b in (0, 7, 8, 100, R - 1)],
+                        rs.env.status()[3].cpu().numpy().copy())
+    a, b = out["fused"], out["persistent"]
+    assert a[0] == b[0] and a[1] == b[1]
+    assert np.array_equal(a[2], b[2])
+    assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
+    assert np.array_equal(a[4], b[4])
