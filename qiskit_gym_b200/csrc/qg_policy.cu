@@ -97,7 +97,7 @@ int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const
         d.wt[l] = w; d.bias[l] = b;
     }
     p->smem = policy_smem_bytes(d);
-    if (p->smem > 200 * 1024) { set_error("qg_policy_create: the network needs more shared memory than one SM has"); qg_policy_destroy(p); return QG_ERR_UNSUPPORTED; }
+    if (p->smem > 210 * 1024) { set_error("qg_policy_create: the network needs more shared memory than one SM has"); qg_policy_destroy(p); return QG_ERR_UNSUPPORTED; }
     {
         cudaError_t ce = cudaFuncSetAttribute(k_policy_mlp, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         if (ce == cudaSuccess && p->smem > 48 * 1024) ce = cudaFuncSetAttribute(k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
