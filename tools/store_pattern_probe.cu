@@ -45,6 +45,23 @@ __global__ void k_stg(float* ring, int R, long B, int obs, int steps, int delay_
     }
 }
 
+// K warps share one 32-env tile: warp w stores the 512-byte rows w, w+K, ... of the tile's slab (CTA = one tile).  With
+// delay_ns > 0 every warp idles before each slab (a CTA that alternates between phase 1 and the expansion in lock-step); with 0
+// the warps store back to back (a producer warp runs phase 1 ahead of the storing warps).
+__global__ void k_stgk(float* ring, int R, long B, int obs, int steps, int delay_ns) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, K = blockDim.x >> 5;
+    const long tile = blockIdx.x;
+    if (tile * 32 >= B) return;
+    const int n4 = obs * 8;   // float4 per tile
+    for (int t = 0; t < steps; ++t) {
+        busy_ns(delay_ns);
+        float4* out = reinterpret_cast<float4*>(ring + ((size_t)(t % R) * B + tile * 32) * obs);
+        const float4 v = make_float4((float)(t & 1), 0.f, 1.f, (float)(lane & 1));
+#pragma unroll 4
+        for (int j = warp * 32 + lane; j < n4; j += 32 * K) __stcs(out + j, v);
+    }
+}
+
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
@@ -116,6 +133,10 @@ int main(int argc, char** argv) {
     const double bytes = (double)slot * steps;
     timeit("fill", [&] { for (int t = 0; t < steps; ++t) k_fill<<<148 * 8, 256>>>(reinterpret_cast<float4*>(ring + (size_t)(t % R) * B * obs), slot / 16); }, bytes);
     timeit("stg", [&] { k_stg<<<grid, wpc * 32>>>(ring, R, B, obs, steps, delay); }, bytes);
+    for (int K = 2; K <= 8; K *= 2) {
+        char nm[16]; snprintf(nm, sizeof nm, "stgk%d", K);
+        timeit(nm, [&] { k_stgk<<<(unsigned)tiles, K * 32>>>(ring, R, B, obs, steps, delay); }, bytes);
+    }
     timeit("tma", [&] { k_tma<<<grid, wpc * 32, sm>>>(ring, R, B, obs, steps, delay, chunk); }, bytes);
     CK(cudaFree(ring));
     return 0;
