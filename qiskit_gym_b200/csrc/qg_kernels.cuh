@@ -388,6 +388,17 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         const uint32_t* src = bits + ((uint32_t)lane >> 3) * kStride;
         float4* o = out4 + lane;
         if (K == 2) {
+#ifdef QG_EXPAND_ALU
+            const uint32_t m0 = 1u << sh, m1 = 2u << sh, m2 = 4u << sh, m3 = 8u << sh;
+            auto mk = [&](uint32_t w) { return make_float4((w & m0) ? 1.0f : 0.0f, (w & m1) ? 1.0f : 0.0f, (w & m2) ? 1.0f : 0.0f, (w & m3) ? 1.0f : 0.0f); };
+#pragma unroll 4
+            for (uint32_t e = 0; e < cnt; ++e, o += 64) {
+                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+                const uint32_t w0 = src[e], w1 = src[4 * kStride + e];
+                st_slab(o, mk(w0));
+                st_slab(o + 32, mk(w1));
+            }
+#else
 #pragma unroll 4
             for (uint32_t e = 0; e < cnt; ++e, o += 64) {
                 if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
@@ -395,6 +406,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
                 st_slab(o, lut_get(lut_lane, (w0 >> sh) & 15u));
                 st_slab(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u));
             }
+#endif
         } else {
             for (uint32_t e = 0; e < cnt; ++e, o += VPE) {
                 if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;

@@ -1,5 +1,7 @@
 // qg_step_kind.cuh — definitions behind qg_launch.hpp; included by the per-kind translation units only.
 #pragma once
+#include <cstdlib>
+
 #include "qg_launch.hpp"
 #include "qg_search_fused.cuh"
 
@@ -45,7 +47,9 @@ template <int KIND, int MODE, int INV>
 cudaError_t prepare_one(size_t smem_bytes) {
     // same shared-memory carve-out as the policy kernel (qg_policy.cu): alternating launches of the two in a search do not make
     // the SMs reconfigure their L1 / shared-memory split in between
-    cudaError_t e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    int carve = (int)cudaSharedmemCarveoutMaxShared;
+    if (const char* v = std::getenv("QG_CARVEOUT")) carve = std::atoi(v);      // A/B runs: -1 = driver default, 0..100 = percent shared
+    cudaError_t e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     return e;
 }

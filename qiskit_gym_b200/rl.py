@@ -7,8 +7,8 @@ the device (and across ranks).  Config files and checkpoints are the reference's
 `RLSynthesis.save` (79-93) and the policy `state_dict` `.pt` (examples/models/*), so models trained with the
 reference load unchanged.
 
-`num_mcts_searches > 0` runs the device tree search of mcts.py.  Out of scope here: `learn()` (the PPO / AlphaZero optimisation loop
-lives in twisterl; collector.RolloutCollector is the data-collection half).
+`num_mcts_searches > 0` runs the device tree search of mcts.py.  `learn()` runs PPO (ppo.py) over collector.RolloutCollector;
+AlphaZero training (rl/configs.py AlphaZeroConfig) is not built.
 """
 from __future__ import annotations
 
@@ -119,5 +119,18 @@ class RLSynthesis:
         if actions is not None:
             return self.env.build_circuit_from_solution(actions, input)
 
-    def learn(self, initial_difficulty=1, num_iterations=int(1e10), tb_path=None):
-        raise NotImplementedError("training runs in twisterl (out of scope, DESIGN.md §7); use collector.RolloutCollector for on-device data collection")
+    def learn(self, initial_difficulty=1, num_iterations=int(1e10), tb_path=None, log=None, seed: int = 0):
+        """rl/synthesis.py:128-139: PPO on the device-resident collector (ppo.py).  The trained policy is `self.policy`
+        (searches built before the call are dropped so that `synth` uses the new weights)."""
+        if self.algorithm_cls.split(".")[-1] != "PPO":
+            raise NotImplementedError(f"algorithm class {self.algorithm_cls} is not supported (PPO only; AlphaZero training lives in twisterl)")
+        from .ppo import PPO
+        cfg = dict(self.env_config)
+        kind = _ENV_KINDS[self.env.cls_name]
+        kw = {k: v for k, v in cfg.items() if k not in ("num_qubits", "gateset")}
+        trainer = PPO(kind, cfg["num_qubits"], cfg["gateset"], self.policy, self.rl_config, device=self.device, seed=seed, **kw)
+        try:
+            return trainer.learn(initial_difficulty=initial_difficulty, num_iterations=num_iterations, tb_path=tb_path, log=log)
+        finally:
+            self.policy = trainer.policy.eval()
+            self._searches = {}
