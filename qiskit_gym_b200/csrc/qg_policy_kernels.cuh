@@ -64,6 +64,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// d0 += w * h0, d1 += w * h1 as ONE instruction (fma.rn.f32x2 -> FFMA2 with the weight as a broadcast scalar operand): the same two
+// IEEE fused multiply-adds as two fmaf, half the issue slots.  The mov.b64 packs / unpacks are register-pair naming only (ptxas
+// emits no instruction for them when the accumulators stay in aligned pairs).
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float w, float h0, float h1) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(h0), "f"(h1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
+
 // acc[i][r] += tile[u][j_i] * h[u][r] over the weight rows u = u0, u0 + ustep, .. of one tile (h: [u][8] activations, one 32-byte
 // broadcast per u)
 template <int NI>
@@ -75,10 +87,15 @@ __device__ __forceinline__ void fma_tile(float (&acc)[NI][kPolRows], const float
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const float w = tile[u * ostr + jc[i]];
+#ifdef QG_POLICY_FFMA1
             acc[i][0] = fmaf(w, h0.x, acc[i][0]); acc[i][1] = fmaf(w, h0.y, acc[i][1]);
             acc[i][2] = fmaf(w, h0.z, acc[i][2]); acc[i][3] = fmaf(w, h0.w, acc[i][3]);
             acc[i][4] = fmaf(w, h1.x, acc[i][4]); acc[i][5] = fmaf(w, h1.y, acc[i][5]);
             acc[i][6] = fmaf(w, h1.z, acc[i][6]); acc[i][7] = fmaf(w, h1.w, acc[i][7]);
+#else
+            ffma2_bcast(acc[i][0], acc[i][1], w, h0.x, h0.y); ffma2_bcast(acc[i][2], acc[i][3], w, h0.z, h0.w);
+            ffma2_bcast(acc[i][4], acc[i][5], w, h1.x, h1.y); ffma2_bcast(acc[i][6], acc[i][7], w, h1.z, h1.w);
+#endif
         }
     }
 }
