@@ -423,9 +423,12 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         envs = args.cpu_sample_envs or calibrate_cpu_envs(args, 12.0, threads)
         r = cpu_run(args, envs, threads=threads)
+        envs1 = max(256, envs // (4 * threads) // 64 * 64)          # ~3 s on one thread (one thread and all threads)
+        r1 = cpu_run(args, envs1, threads=1)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"{envs} envs x {T} env-steps (same config, targets and action distribution), oracle C++ port of the Rust core, "
-                                  f"per env-step step+observe+masks+reward+is_final, {threads} host threads, {r['seconds']:.1f} s"}
+                                  f"per env-step step+observe+masks+reward+is_final, {threads} host threads, {r['seconds']:.1f} s",
+                        "single_thread": {"value": r1["value"], "unit": UNIT, "cores": 1, "sample": f"{envs1} envs x {T} env-steps, {r1['seconds']:.1f} s"}}
     line = {
         "metric": METRIC if args.config == "C3_clifford8_full" else f"batched env-steps/sec ({args.config})",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
@@ -458,26 +461,31 @@ def run_collector(args, dev, local, rank, world):
     env = BatchedEnv(kind, n, gateset, B, device=local, difficulty=64, depth_slope=2, max_depth=128, add_perms=False, **pk)
     torch.manual_seed(0)
     pol = BasicPolicy(env.obs_shape(), len(gateset), embedding_size=512, common_layers=(256,))
-    col = RolloutCollector(env, pol, use_twists=False, seed=rank)
-    col.collect(4)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    ro = col.collect(T)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    episodes, success = ro.episode_stats()
-    return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "envs_per_gpu": B, "decisions": T, "ms_per_decision": ms / T,
-            "episodes_finished": episodes,
-            "note": "RolloutCollector.collect: reset_select + observe (dense f32) + PyTorch BasicPolicy 512/256 forward (f32 cuBLAS) + softmax + "
-                    "qg_collect_step + log-prob gather per decision, qg_gae at the end; difficulty 64, random-init policy"}
+    def leg(precision):
+        col = RolloutCollector(env, pol, use_twists=False, seed=rank, matmul_precision=precision)
+        col.collect(4)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ro = col.collect(T)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        episodes, _ = ro.episode_stats()
+        return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "ms_per_decision": ms / T, "episodes_finished": episodes}
+
+    out = leg("f32")
+    out.update({"envs_per_gpu": B, "decisions": T,
+                "note": "RolloutCollector.collect: reset_select + observe (dense f32) + PyTorch BasicPolicy 512/256 forward (f32 cuBLAS) + softmax + "
+                        "qg_collect_step + log-prob gather per decision, qg_gae at the end; difficulty 64, random-init policy",
+                "tf32_policy": dict(leg("tf32"), note="same collector with matmul_precision='tf32' (the policy's GEMMs on tensor cores, f32 accumulate)")})
+    return out
 
 
 def run_synth(args, dev, local, rank, world):

@@ -88,7 +88,12 @@ def twist_gather(src: torch.Tensor, table: torch.Tensor, index: torch.Tensor | N
 
 class RolloutCollector:
     def __init__(self, env: BatchedEnv, policy: torch.nn.Module, gamma: float = 0.995, lam: float = 0.995, use_twists: bool = True,
-                 seed: int = 0, first_env_id: int = 0):
+                 seed: int = 0, first_env_id: int = 0, matmul_precision: str = "f32"):
+        """matmul_precision: how PyTorch runs the policy's GEMMs while collecting — "f32" (the reference's arithmetic), "tf32" (tensor
+        cores, f32 accumulate; the observations are 0/1 and exact, only the weights are rounded to 10 mantissa bits) or "bf16"
+        (autocast).  The env side is unaffected; only the action probabilities the samples are drawn from change in their last bits."""
+        assert matmul_precision in ("f32", "tf32", "bf16")
+        self.matmul_precision = matmul_precision
         self.env, self.policy = env, policy.to(env.device).eval()
         self.gamma, self.lam = float(gamma), float(lam)
         self.seed, self.first_env_id = int(seed), int(first_env_id)
@@ -110,7 +115,18 @@ class RolloutCollector:
 
     def _policy(self, obs):
         with torch.no_grad():
-            logits, value = self.policy(obs)
+            if self.matmul_precision == "bf16":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    logits, value = self.policy(obs)
+            elif self.matmul_precision == "tf32":
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = True
+                try:
+                    logits, value = self.policy(obs)
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+            else:
+                logits, value = self.policy(obs)
             return torch.softmax(logits.float(), dim=-1), value.float().reshape(-1)
 
     def collect(self, num_steps: int, deterministic: bool = False) -> Rollout:

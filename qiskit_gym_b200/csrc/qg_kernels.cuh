@@ -388,17 +388,9 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         const uint32_t* src = bits + ((uint32_t)lane >> 3) * kStride;
         float4* o = out4 + lane;
         if (K == 2) {
-#ifdef QG_EXPAND_ALU
-            const uint32_t m0 = 1u << sh, m1 = 2u << sh, m2 = 4u << sh, m3 = 8u << sh;
-            auto mk = [&](uint32_t w) { return make_float4((w & m0) ? 1.0f : 0.0f, (w & m1) ? 1.0f : 0.0f, (w & m2) ? 1.0f : 0.0f, (w & m3) ? 1.0f : 0.0f); };
-#pragma unroll 4
-            for (uint32_t e = 0; e < cnt; ++e, o += 64) {
-                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
-                const uint32_t w0 = src[e], w1 = src[4 * kStride + e];
-                st_slab(o, mk(w0));
-                st_slab(o + 32, mk(w1));
-            }
-#else
+            // measured dead ends at 65 536 envs (profiles/r1_v15_ablation*.jsonl, r1_v16_ablation_pipe.jsonl): floats from selects
+            // instead of the table (no change), the words of 8 environments read ahead of 16 back-to-back stores (1.7 % slower),
+            // the L1 / shared-memory carve-out (no change), more storing warps per tile (tools/store_pattern_probe.cu: no change)
 #pragma unroll 4
             for (uint32_t e = 0; e < cnt; ++e, o += 64) {
                 if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
@@ -406,7 +398,6 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
                 st_slab(o, lut_get(lut_lane, (w0 >> sh) & 15u));
                 st_slab(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u));
             }
-#endif
         } else {
             for (uint32_t e = 0; e < cnt; ++e, o += VPE) {
                 if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;

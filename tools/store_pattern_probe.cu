@@ -31,11 +31,14 @@ __global__ void k_fill(float4* out, size_t n4) {
 }
 
 // ring: [R][B][obs] floats
-__global__ void k_stg(float* ring, int R, long B, int obs, int steps, int delay_ns) {
+// skew_ns > 0: warp w starts hash(w) % skew_ns late, so the warps are spread over the step period (and over the ring slots) like
+// the drifting warps of the real kernel instead of walking the ring in lock-step
+__global__ void k_stg(float* ring, int R, long B, int obs, int steps, int delay_ns, int skew_ns = 0) {
     const int lane = threadIdx.x & 31;
     const long tile = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile * 32 >= B) return;
     const int n4 = obs * 8;   // float4 per tile
+    if (skew_ns > 0) busy_ns((int)(((unsigned)tile * 2654435761u >> 8) % (unsigned)skew_ns));
     for (int t = 0; t < steps; ++t) {
         busy_ns(delay_ns);
         float4* out = reinterpret_cast<float4*>(ring + ((size_t)(t % R) * B + tile * 32) * obs);
@@ -133,7 +136,11 @@ int main(int argc, char** argv) {
     const double bytes = (double)slot * steps;
     timeit("fill", [&] { for (int t = 0; t < steps; ++t) k_fill<<<148 * 8, 256>>>(reinterpret_cast<float4*>(ring + (size_t)(t % R) * B * obs), slot / 16); }, bytes);
     timeit("stg", [&] { k_stg<<<grid, wpc * 32>>>(ring, R, B, obs, steps, delay); }, bytes);
-    for (int K = 2; K <= 8; K *= 2) {
+    for (int skew = 5000; skew <= 80000; skew *= 4) {
+        char nm[24]; snprintf(nm, sizeof nm, "stg_skew%d", skew);
+        timeit(nm, [&] { k_stg<<<grid, wpc * 32>>>(ring, R, B, obs, steps, delay, skew); }, bytes);
+    }
+    for (int K = 2; K <= 4; K *= 2) {
         char nm[16]; snprintf(nm, sizeof nm, "stgk%d", K);
         timeit(nm, [&] { k_stgk<<<(unsigned)tiles, K * 32>>>(ring, R, B, obs, steps, delay); }, bytes);
     }
