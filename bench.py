@@ -419,7 +419,7 @@ def run_ours(args):
                     "roofline_achieved_gbs": ach1, "roofline_frac": ach1 / peak,
                     "note": "one fused launch per env-step (qg_step, policy-in-the-loop granularity), programmatic dependent launch, CUDA graph"}
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU figure is reported beside the 1-GPU run only
         threads = os.cpu_count() or 1
         envs = args.cpu_sample_envs or calibrate_cpu_envs(args, 12.0, threads)
         r = cpu_run(args, envs, threads=threads)

@@ -28,6 +28,17 @@ import torch
 from .collector import RolloutCollector, decision_seed
 from .engine import BatchedEnv
 
+_EVAL_DEFAULT = {"num_episodes": 100, "deterministic": True, "num_searches": 1, "num_mcts_searches": 0, "num_cores": 32, "C": 1.41}
+# AlphaZeroConfig (configs.py:325-360)
+_AZ_DEFAULTS = {
+    "collecting": {"num_cores": 32, "num_episodes": 128, "num_mcts_searches": 1000, "C": 1.41, "max_expand_depth": 1},
+    "training": {"num_epochs": 10},
+    "learning": {"diff_threshold": 0.85, "diff_max": 256, "diff_metric": "mcts_100"},
+    "optimizer": {"lr": 3e-4},
+    "evals": {"ppo_deterministic": dict(_EVAL_DEFAULT), "ppo_10": dict(_EVAL_DEFAULT, deterministic=False, num_searches=10),
+              "mcts_100": dict(_EVAL_DEFAULT, num_mcts_searches=100)},
+    "logging": {"log_freq": 1, "checkpoint_freq": 10},
+}
 _DEFAULTS = {
     "collecting": {"num_cores": 32, "num_episodes": 1024, "lambda": 0.995, "gamma": 0.995},
     "training": {"num_epochs": 10, "vf_coef": 0.8, "ent_coef": 0.01, "clip_ratio": 0.1, "normalize_advantage": False},
@@ -39,26 +50,36 @@ _DEFAULTS = {
 }
 
 
-def merged_config(cfg: dict | None) -> dict:
-    """The reference's defaults (configs.py:133-166) overlaid with `cfg`; validates like `PPOConfig.validate` (168-196)."""
-    out = {k: dict(v) for k, v in _DEFAULTS.items()}
-    out["evals"] = {k: dict(v) for k, v in _DEFAULTS["evals"].items()}
+def merged_config(cfg: dict | None, algorithm: str = "PPO") -> dict:
+    """The reference's defaults (PPOConfig configs.py:133-166, AlphaZeroConfig 325-360) overlaid with `cfg`; validates like
+    `PPOConfig.validate` / `AlphaZeroConfig.validate` (168-196, 364-391)."""
+    base = _AZ_DEFAULTS if algorithm == "AZ" else _DEFAULTS
+    out = {k: dict(v) for k, v in base.items()}
+    out["evals"] = {k: dict(v) for k, v in base["evals"].items()}
     for sec, val in (cfg or {}).items():
         if sec == "evals":
-            out["evals"] = {name: {**_DEFAULTS["evals"]["ppo_deterministic"], **dict(ev)} for name, ev in dict(val).items()}
+            out["evals"] = {name: {**_EVAL_DEFAULT, **dict(ev)} for name, ev in dict(val).items()}
         elif sec in out:
             out[sec].update(dict(val))
     c, t, l = out["collecting"], out["training"], out["learning"]
     if c["num_episodes"] <= 0:
         raise ValueError("num_episodes must be > 0")
-    if not 0.0 <= c["lambda"] <= 1.0:
-        raise ValueError("gae_lambda must be in [0, 1]")
-    if not 0.0 <= c["gamma"] <= 1.0:
-        raise ValueError("gamma must be in [0, 1]")
+    if algorithm == "AZ":
+        if c["num_mcts_searches"] <= 0:
+            raise ValueError("num_mcts_searches must be > 0")
+        if c["C"] <= 0:
+            raise ValueError("C must be > 0")
+        if c["max_expand_depth"] < 1:
+            raise ValueError("max_expand_depth must be >= 1")
+    else:
+        if not 0.0 <= c["lambda"] <= 1.0:
+            raise ValueError("gae_lambda must be in [0, 1]")
+        if not 0.0 <= c["gamma"] <= 1.0:
+            raise ValueError("gamma must be in [0, 1]")
+        if t["clip_ratio"] <= 0:
+            raise ValueError("clip_ratio must be > 0")
     if t["num_epochs"] <= 0:
         raise ValueError("num_epochs must be > 0")
-    if t["clip_ratio"] <= 0:
-        raise ValueError("clip_ratio must be > 0")
     if not 0.0 <= l["diff_threshold"] <= 1.0:
         raise ValueError("diff_threshold must be in [0, 1]")
     if l["diff_max"] < 1:
@@ -66,115 +87,103 @@ def merged_config(cfg: dict | None) -> dict:
     if l["diff_metric"] not in out["evals"]:
         raise ValueError(f"diff_metric '{l['diff_metric']}' not found in evals: {list(out['evals'])}")
     for name, ev in out["evals"].items():
-        if ev["num_episodes"] <= 0 or ev["num_searches"] <= 0 or ev["num_mcts_searches"] < 0:
+        if ev["num_episodes"] <= 0 or ev["num_searches"] <= 0 or ev["num_mcts_searches"] < 0 or ev["C"] <= 0:
             raise ValueError(f"Invalid eval '{name}'")
     return out
 
 
-class PPO:
-    """`PPO(env_spec, policy, config).learn(...)`; env_spec = (env kind, num_qubits, gateset, BatchedEnv keyword arguments)."""
+class Trainer:
+    """What PPO and AlphaZero share: the envs, the difficulty curriculum, the evals, logging and checkpoints.
+    Subclasses provide `iterate() -> dict` (collect + update, returns the iteration's scalars)."""
+
+    algorithm = "PPO"
 
     def __init__(self, env_kind: int, num_qubits: int, gateset, policy: torch.nn.Module, config: dict | None = None, device=None,
-                 seed: int = 0, use_twists: bool = True, minibatch_size: int | None = None, **env_kwargs):
-        self.cfg = merged_config(config)
+                 seed: int = 0, minibatch_size: int | None = None, **env_kwargs):
+        self.cfg = merged_config(config, self.algorithm)
         self.spec = (env_kind, num_qubits, list(gateset), dict(env_kwargs))
-        B = int(self.cfg["collecting"]["num_episodes"])
-        self.env = BatchedEnv(env_kind, num_qubits, gateset, B, device=device, **env_kwargs)
-        self.device = self.env.device
-        self.policy = policy.to(self.device)
-        self.collector = RolloutCollector(self.env, self.policy, gamma=self.cfg["collecting"]["gamma"], lam=self.cfg["collecting"]["lambda"],
-                                          use_twists=use_twists, seed=seed)
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=float(self.cfg["optimizer"]["lr"]))
         self.seed = int(seed)
         self.minibatch_size = minibatch_size
         self._eval_envs = {}
+        self._eval_mcts = {}
         self.iteration = 0
         self.history = []
+        self._difficulty = int(env_kwargs.get("difficulty", 1))
+        self.env = self._make_env(int(self.cfg["collecting"]["num_episodes"]), device)
+        self.device = self.env.device
+        self.policy = policy.to(self.device)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=float(self.cfg["optimizer"]["lr"]))
+
+    def _make_env(self, batch: int, device) -> BatchedEnv:
+        kind, n, gs, kw = self.spec
+        return BatchedEnv(kind, n, gs, batch, device=device, **kw)
 
     # ---- difficulty (Env::set_difficulty on every env the trainer owns) -------------------------------------------
     @property
     def difficulty(self) -> int:
-        return int(self.env.difficulty)
+        return self._difficulty
 
     @difficulty.setter
     def difficulty(self, d: int):
+        self._difficulty = int(d)
         self.env.difficulty = int(d)
-        for e in self._eval_envs.values():
-            e.difficulty = int(d)
 
     def _episode_steps(self) -> int:
         """An episode lasts at most depth = min(depth_slope * difficulty, max_depth) decisions (e.g. clifford.rs:306-319)."""
         c = self.env.cfg
         return int(max(1, min(int(c.depth_slope) * self.difficulty, int(c.max_depth))))
 
-    # ---- one PPO iteration ---------------------------------------------------------------------------------------------
-    def update(self, ro) -> dict:
-        """`num_epochs` passes of the clipped-surrogate update over the valid decisions of a Rollout."""
-        t = self.cfg["training"]
-        valid = ro.valid.reshape(-1)
-        idx = valid.nonzero(as_tuple=False).squeeze(1)
-        obs = ro.obs.reshape((-1,) + tuple(ro.obs.shape[2:]))[idx]
-        act = ro.policy_actions.reshape(-1)[idx]
-        logp_old = ro.logp.reshape(-1)[idx]
-        adv = ro.advantages.reshape(-1)[idx]
-        ret = ro.returns.reshape(-1)[idx]
-        if t["normalize_advantage"] and adv.numel() > 1:
-            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-        n = int(idx.numel())
+    def _minibatches(self, n: int):
         mb = n if not self.minibatch_size else min(int(self.minibatch_size), n)
-        clip = float(t["clip_ratio"])
-        self.policy.train()
-        stats = {}
-        for _ in range(int(t["num_epochs"])):
-            perm = torch.randperm(n, device=self.device) if mb < n else None
-            for s in range(0, n, mb):
-                sel = slice(s, s + mb) if perm is None else perm[s:s + mb]
-                logits, value = self.policy(obs[sel])
-                logp_all = torch.log_softmax(logits.float(), dim=-1)
-                logp = logp_all.gather(1, act[sel][:, None]).squeeze(1)
-                ratio = torch.exp(logp - logp_old[sel])
-                a = adv[sel]
-                pi_loss = -torch.min(ratio * a, torch.clamp(ratio, 1.0 - clip, 1.0 + clip) * a).mean()
-                v_loss = torch.nn.functional.mse_loss(value.float().reshape(-1), ret[sel])
-                entropy = -(logp_all.exp() * logp_all).sum(-1).mean()
-                loss = pi_loss + float(t["vf_coef"]) * v_loss - float(t["ent_coef"]) * entropy
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                self.opt.step()
-                stats = {"loss": loss.detach(), "pi_loss": pi_loss.detach(), "v_loss": v_loss.detach(), "entropy": entropy.detach(),
-                         "clip_frac": ((ratio - 1.0).abs() > clip).float().mean().detach()}
-        self.policy.eval()
-        return {k: float(v.item()) for k, v in stats.items()} | {"samples": n}
+        perm = torch.randperm(n, device=self.device) if mb < n else None
+        for s in range(0, n, mb):
+            yield slice(s, s + mb) if perm is None else perm[s:s + mb]
+
+    def _probs(self, obs):
+        with torch.no_grad():
+            logits, _ = self.policy(obs)
+            return torch.softmax(logits.float(), dim=-1).contiguous()
 
     # ---- evaluation ----------------------------------------------------------------------------------------------------
     def evaluate(self, name: str) -> float:
         """Success rate of `evals[name]`: num_episodes fresh targets at the current difficulty, each tried with `num_searches`
-        rollouts (greedy or sampled); an episode counts when any of its rollouts ends in success (configs.py:25-35)."""
+        rollouts (greedy or sampled; with a tree search of `num_mcts_searches` simulations per decision when that is > 0); an
+        episode counts when any of its rollouts ends in success (configs.py:25-35)."""
         ev = self.cfg["evals"][name]
-        if int(ev.get("num_mcts_searches", 0)):
-            raise NotImplementedError("evals with num_mcts_searches > 0: use RLSynthesis.solve(num_mcts_searches=...)")
-        E = int(ev["num_episodes"])
-        env = self._eval_envs.get(E)
-        if env is None:
-            kind, n, gs, kw = self.spec
-            env = BatchedEnv(kind, n, gs, E, device=self.device.index, **kw)
-            self._eval_envs[E] = env
-        env.difficulty = self.difficulty
+        E, sims = int(ev["num_episodes"]), int(ev.get("num_mcts_searches", 0))
         base = decision_seed(self.seed ^ 0x5EED5EED, 1_000_003 * (self.iteration + 1))
+        steps = self._episode_steps()
+        self.policy.eval()
+        if sims:
+            from .mcts import MCTSSearch
+            key = (E, sims, float(ev["C"]))
+            ms = self._eval_mcts.get(key)
+            if ms is None:
+                kind, n, gs, kw = self.spec
+                kw = {k: v for k, v in kw.items() if k != "max_depth"}
+                ms = MCTSSearch(kind, n, gs, self.policy, E, sims, C=float(ev["C"]), device=self.device.index, max_depth=int(self.env.cfg.max_depth), **kw)
+                self._eval_mcts[key] = ms
+            ms.policy = self.policy
+            env = ms.env
+        else:
+            env = self._eval_envs.get(E)
+            if env is None:
+                env = self._eval_envs[E] = self._make_env(E, self.device.index)
+        env.difficulty = self.difficulty
         env.reset(seed=base)
         env.snapshot()
         solved = torch.zeros(E, dtype=torch.bool, device=self.device)
-        steps = self._episode_steps()
         for s in range(int(ev["num_searches"])):
             if s:
                 env.restore()
             for k in range(steps):
-                with torch.no_grad():
-                    logits, _ = self.policy(env.observe())
-                    probs = torch.softmax(logits.float(), dim=-1).contiguous()
-                env.collect_step(probs, decision_seed(base, (s + 1) * 4099 + k), deterministic=bool(ev["deterministic"]), obs=False)
+                weights = ms.decide(k) if sims else self._probs(env.observe())
+                env.collect_step(weights, decision_seed(base, (s + 1) * 4099 + k), deterministic=bool(ev["deterministic"]), obs=False)
             solved |= env.status()[2]
         return float(solved.float().mean().item())
+
+    def iterate(self) -> dict:
+        raise NotImplementedError
 
     # ---- the loop ------------------------------------------------------------------------------------------------------
     def learn(self, initial_difficulty: int = 1, num_iterations: int = int(1e10), tb_path: str | None = None, log=None, stop_at_max: bool = False):
@@ -189,11 +198,8 @@ class PPO:
         try:
             for _ in range(int(num_iterations)):
                 t0 = time.time()
-                ro = self.collector.collect(self._episode_steps())
-                episodes, success = ro.episode_stats()
-                rec = {"iteration": self.iteration, "difficulty": self.difficulty, "episodes": episodes, "collect_success": success,
-                       "mean_reward": float(ro.rewards[ro.valid].mean().item()) if bool(ro.valid.any()) else 0.0}
-                rec.update(self.update(ro))
+                rec = {"iteration": self.iteration, "difficulty": self.difficulty}
+                rec.update(self.iterate())
                 if self.iteration % max(1, int(lg["log_freq"])) == 0:
                     for name in self.cfg["evals"]:
                         rec[f"eval/{name}"] = self.evaluate(name)
@@ -216,3 +222,138 @@ class PPO:
             if fh:
                 fh.close()
         return self.history
+
+
+class PPO(Trainer):
+    """`PPO(env kind, num_qubits, gateset, policy, config, **BatchedEnv keyword arguments).learn(...)`."""
+
+    algorithm = "PPO"
+
+    def __init__(self, env_kind: int, num_qubits: int, gateset, policy: torch.nn.Module, config: dict | None = None, device=None,
+                 seed: int = 0, use_twists: bool = True, minibatch_size: int | None = None, matmul_precision: str = "f32", **env_kwargs):
+        super().__init__(env_kind, num_qubits, gateset, policy, config, device=device, seed=seed, minibatch_size=minibatch_size, **env_kwargs)
+        self.collector = RolloutCollector(self.env, self.policy, gamma=self.cfg["collecting"]["gamma"], lam=self.cfg["collecting"]["lambda"],
+                                          use_twists=use_twists, seed=seed, matmul_precision=matmul_precision)
+
+    def iterate(self) -> dict:
+        ro = self.collector.collect(self._episode_steps())
+        episodes, success = ro.episode_stats()
+        rec = {"episodes": episodes, "collect_success": success,
+               "mean_reward": float(ro.rewards[ro.valid].mean().item()) if bool(ro.valid.any()) else 0.0}
+        rec.update(self.update(ro))
+        return rec
+
+    def update(self, ro) -> dict:
+        """`num_epochs` passes of the clipped-surrogate update over the valid decisions of a Rollout."""
+        t = self.cfg["training"]
+        idx = ro.valid.reshape(-1).nonzero(as_tuple=False).squeeze(1)
+        obs = ro.obs.reshape((-1,) + tuple(ro.obs.shape[2:]))[idx]
+        act = ro.policy_actions.reshape(-1)[idx]
+        logp_old = ro.logp.reshape(-1)[idx]
+        adv = ro.advantages.reshape(-1)[idx]
+        ret = ro.returns.reshape(-1)[idx]
+        if t["normalize_advantage"] and adv.numel() > 1:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        n = int(idx.numel())
+        clip = float(t["clip_ratio"])
+        self.policy.train()
+        stats = {}
+        for _ in range(int(t["num_epochs"])):
+            for sel in self._minibatches(n):
+                logits, value = self.policy(obs[sel])
+                logp_all = torch.log_softmax(logits.float(), dim=-1)
+                logp = logp_all.gather(1, act[sel][:, None]).squeeze(1)
+                ratio = torch.exp(logp - logp_old[sel])
+                a = adv[sel]
+                pi_loss = -torch.min(ratio * a, torch.clamp(ratio, 1.0 - clip, 1.0 + clip) * a).mean()
+                v_loss = torch.nn.functional.mse_loss(value.float().reshape(-1), ret[sel])
+                entropy = -(logp_all.exp() * logp_all).sum(-1).mean()
+                loss = pi_loss + float(t["vf_coef"]) * v_loss - float(t["ent_coef"]) * entropy
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self.opt.step()
+                stats = {"loss": loss.detach(), "pi_loss": pi_loss.detach(), "v_loss": v_loss.detach(), "entropy": entropy.detach(),
+                         "clip_frac": ((ratio - 1.0).abs() > clip).float().mean().detach()}
+        self.policy.eval()
+        return {k: float(v.item()) for k, v in stats.items()} | {"samples": n}
+
+
+class AlphaZero(Trainer):
+    """Self-play with the device tree search (mcts.py) and the AlphaZero update: every decision of every episode runs
+    `num_mcts_searches` PUCT simulations; the action is sampled from the root's visit counts; the policy is trained towards
+    the visit distribution (cross entropy) and the value head towards the episode's return-to-go (undiscounted, like the tree's
+    own back-up; episodes cut by the end of the collection bootstrap from the value head).  Config: AlphaZeroConfig.to_json()
+    (configs.py:404-429).  twisterl's AZ is not in the reference tree: this follows the config docstrings (295-323), not its code."""
+
+    algorithm = "AZ"
+
+    def __init__(self, env_kind: int, num_qubits: int, gateset, policy: torch.nn.Module, config: dict | None = None, device=None,
+                 seed: int = 0, minibatch_size: int | None = None, vf_coef: float = 1.0, **env_kwargs):
+        from .mcts import MCTSSearch
+        self._mcts_cls = MCTSSearch
+        self._policy_for_env = policy
+        self.vf_coef = float(vf_coef)
+        super().__init__(env_kind, num_qubits, gateset, policy, config, device=device, seed=seed, minibatch_size=minibatch_size, **env_kwargs)
+        self.counter = 0
+
+    def _make_env(self, batch: int, device) -> BatchedEnv:
+        if hasattr(self, "env"):                       # eval envs without a tree search
+            return super()._make_env(batch, device)
+        c = self.cfg["collecting"]
+        if int(c["max_expand_depth"]) != 1:
+            raise NotImplementedError("max_expand_depth != 1 is not supported by the device tree search (mcts.py)")
+        kind, n, gs, kw = self.spec
+        kw = {k: v for k, v in kw.items() if k != "max_depth"}
+        self.search = self._mcts_cls(kind, n, gs, self._policy_for_env, batch, int(c["num_mcts_searches"]), C=float(c["C"]), device=device,
+                                     max_depth=int(self.spec[3].get("max_depth", 128)), **kw)
+        return self.search.env
+
+    def iterate(self) -> dict:
+        from .collector import gae
+        env, ms, T, B = self.env, self.search, self._episode_steps(), self.env.batch
+        ms.policy = self.policy.eval()
+        dev, A = self.device, env.num_actions()
+        obs_buf = torch.empty((T, B) + tuple(env.obs_shape()), dtype=torch.float32, device=dev)
+        pi = torch.zeros((T, B, A), dtype=torch.float32, device=dev)
+        actions = torch.full((T, B), -1, dtype=torch.int32, device=dev)
+        rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
+        dones = torch.zeros((T, B), dtype=torch.bool, device=dev)
+        succ = torch.zeros((T, B), dtype=torch.bool, device=dev)
+        for t in range(T):
+            s = decision_seed(self.seed, self.counter)
+            env.reset_select(s, 0)
+            w = ms.decide(t)                         # observes into env.obs, grows the trees, leaves N(a) / sum N in ms.weights
+            obs_buf[t].copy_(env.obs)
+            pi[t].copy_(w)
+            env.collect_step(w, s, deterministic=False, obs=False, chosen=actions[t], reward=rewards[t], done=dones[t], success=succ[t])
+            self.counter += 1
+        valid = actions >= 0
+        values = torch.zeros((T + 1, B), dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            values[T] = self.policy(env.observe())[1].float().reshape(-1)
+        _, ret = gae(rewards, values, dones, 1.0, 1.0, valid)        # V = 0 inside, gamma = lambda = 1: the return-to-go (+ bootstrap)
+        fin = dones & valid
+        n_ep = int(fin.sum().item())
+        rec = {"episodes": n_ep, "collect_success": (float((succ & fin).sum().item()) / n_ep) if n_ep else 0.0,
+               "mean_reward": float(rewards[valid].mean().item()) if bool(valid.any()) else 0.0}
+        idx = valid.reshape(-1).nonzero(as_tuple=False).squeeze(1)
+        obs = obs_buf.reshape((-1,) + tuple(obs_buf.shape[2:]))[idx]
+        tgt_pi = pi.reshape(-1, A)[idx]
+        tgt_v = ret.reshape(-1)[idx]
+        n = int(idx.numel())
+        self.policy.train()
+        stats = {}
+        for _ in range(int(self.cfg["training"]["num_epochs"])):
+            for sel in self._minibatches(n):
+                logits, value = self.policy(obs[sel])
+                logp_all = torch.log_softmax(logits.float(), dim=-1)
+                pi_loss = -(tgt_pi[sel] * logp_all).sum(-1).mean()
+                v_loss = torch.nn.functional.mse_loss(value.float().reshape(-1), tgt_v[sel])
+                loss = pi_loss + self.vf_coef * v_loss
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self.opt.step()
+                stats = {"loss": loss.detach(), "pi_loss": pi_loss.detach(), "v_loss": v_loss.detach()}
+        self.policy.eval()
+        rec.update({k: float(v.item()) for k, v in stats.items()} | {"samples": n})
+        return rec

@@ -7,8 +7,8 @@ the device (and across ranks).  Config files and checkpoints are the reference's
 `RLSynthesis.save` (79-93) and the policy `state_dict` `.pt` (examples/models/*), so models trained with the
 reference load unchanged.
 
-`num_mcts_searches > 0` runs the device tree search of mcts.py.  `learn()` runs PPO (ppo.py) over collector.RolloutCollector;
-AlphaZero training (rl/configs.py AlphaZeroConfig) is not built.
+`num_mcts_searches > 0` runs the device tree search of mcts.py.  `learn()` runs PPO over collector.RolloutCollector or AlphaZero
+self-play over the device tree search (ppo.py), chosen by `algorithm_cls` like the reference does.
 """
 from __future__ import annotations
 
@@ -120,15 +120,16 @@ class RLSynthesis:
             return self.env.build_circuit_from_solution(actions, input)
 
     def learn(self, initial_difficulty=1, num_iterations=int(1e10), tb_path=None, log=None, seed: int = 0):
-        """rl/synthesis.py:128-139: PPO on the device-resident collector (ppo.py).  The trained policy is `self.policy`
-        (searches built before the call are dropped so that `synth` uses the new weights)."""
-        if self.algorithm_cls.split(".")[-1] != "PPO":
-            raise NotImplementedError(f"algorithm class {self.algorithm_cls} is not supported (PPO only; AlphaZero training lives in twisterl)")
-        from .ppo import PPO
+        """rl/synthesis.py:128-139: PPO (`twisterl.rl.PPO`) or AlphaZero (`twisterl.rl.AZ`) on the device (ppo.py).  The trained
+        policy is `self.policy` (searches built before the call are dropped so that `synth` uses the new weights)."""
+        from . import ppo
+        algo = self.algorithm_cls.split(".")[-1]
+        if algo not in ("PPO", "AZ"):
+            raise NotImplementedError(f"algorithm class {self.algorithm_cls} is not supported (twisterl.rl.PPO, twisterl.rl.AZ)")
         cfg = dict(self.env_config)
         kind = _ENV_KINDS[self.env.cls_name]
         kw = {k: v for k, v in cfg.items() if k not in ("num_qubits", "gateset")}
-        trainer = PPO(kind, cfg["num_qubits"], cfg["gateset"], self.policy, self.rl_config, device=self.device, seed=seed, **kw)
+        trainer = (ppo.PPO if algo == "PPO" else ppo.AlphaZero)(kind, cfg["num_qubits"], cfg["gateset"], self.policy, self.rl_config, device=self.device, seed=seed, **kw)
         try:
             return trainer.learn(initial_difficulty=initial_difficulty, num_iterations=num_iterations, tb_path=tb_path, log=log)
         finally:

@@ -32,6 +32,18 @@ def test_config_overlay_and_validation():
             ppo.merged_config(bad)
 
 
+def test_alphazero_config_defaults_and_validation():
+    c = ppo.merged_config(None, "AZ")
+    # rl/configs.py:325-360
+    assert c["collecting"] == {"num_cores": 32, "num_episodes": 128, "num_mcts_searches": 1000, "C": 1.41, "max_expand_depth": 1}
+    assert c["training"] == {"num_epochs": 10} and c["learning"]["diff_metric"] == "mcts_100"
+    assert c["evals"]["mcts_100"]["num_mcts_searches"] == 100 and c["evals"]["mcts_100"]["deterministic"] is True
+    for bad in ({"collecting": {"num_mcts_searches": 0}}, {"collecting": {"C": 0.0}}, {"collecting": {"max_expand_depth": 0}},
+                {"learning": {"diff_metric": "nope"}}):
+        with pytest.raises(ValueError):
+            ppo.merged_config(bad, "AZ")
+
+
 def test_reference_config_files_parse():
     """The `algorithm` section of the reference's own example configs (tests/golden/models/*.json) goes through unchanged."""
     import glob
@@ -66,7 +78,6 @@ def test_ppo_learns_permutation_line4(tmp_path):
         circ = rls.synth(t, deterministic=True, num_searches=1)
         if circ is not None:
             after += 1
-            perm = list(range(4))
             gates = circ if isinstance(circ, list) else [(i.operation.name.upper(), [circ.find_bit(q).index for q in i.qubits]) for i in circ.data]
             assert all(g[0] == "SWAP" for g in gates)
     assert after >= max(before + 5, int(0.8 * len(targets))), (before, after, len(targets))
@@ -74,3 +85,22 @@ def test_ppo_learns_permutation_line4(tmp_path):
     rls.save(str(tmp_path / "cfg.json"), str(tmp_path / "model.pt"))
     again = RLSynthesis.from_config_json(str(tmp_path / "cfg.json"), str(tmp_path / "model.pt"), device=0)
     assert (again.synth(targets[0], deterministic=True, num_searches=1) is None) == (rls.synth(targets[0], deterministic=True, num_searches=1) is None)
+
+
+@pytest.mark.gpu
+def test_alphazero_learns_permutation_line4():
+    """twisterl.rl.AZ: self-play with the device tree search; the curriculum must move and the tree-search eval must beat chance."""
+    from qiskit_gym_b200 import gyms
+    from qiskit_gym_b200.rl import RLSynthesis
+
+    torch.manual_seed(0)
+    env = gyms.PermutationGym.from_coupling_map([(0, 1), (1, 2), (2, 3)], difficulty=1, depth_slope=2, max_depth=32)
+    cfg = {"collecting": {"num_episodes": 256, "num_mcts_searches": 16, "C": 1.41}, "training": {"num_epochs": 4}, "optimizer": {"lr": 2e-3},
+           "learning": {"diff_threshold": 0.85, "diff_max": 6, "diff_metric": "mcts_16"},
+           "evals": {"ppo_deterministic": {"num_episodes": 64}, "mcts_16": {"num_episodes": 64, "num_mcts_searches": 16}}}
+    rls = RLSynthesis(env, cfg, {"embedding_size": 64, "common_layers": [64]}, device=0, algorithm_cls="twisterl.rl.AZ")
+    hist = rls.learn(initial_difficulty=1, num_iterations=25)
+    trace = [(h["difficulty"], round(h["eval/mcts_16"], 2), round(h["eval/ppo_deterministic"], 2)) for h in hist]
+    assert hist[-1]["difficulty"] >= 3, trace
+    assert max(h["eval/ppo_deterministic"] for h in hist[-5:]) >= 0.5, trace
+    assert all(np.isfinite(h["loss"]) for h in hist)

@@ -25,7 +25,12 @@ else:
 torch.manual_seed(0)
 cfg = {"collecting": {"num_episodes": int(os.environ.get("EPISODES", 512))}, "training": {"num_epochs": 4}, "optimizer": {"lr": float(os.environ.get("LR", 2e-3))},
        "learning": {"diff_max": 32}, "evals": {"ppo_deterministic": {"num_episodes": 128}, "ppo_10": {"num_episodes": 128, "deterministic": False, "num_searches": 10}}}
-rls = RLSynthesis(env, cfg, {"embedding_size": 64, "common_layers": [64]}, device=0)
+algo = os.environ.get("ALGO", "PPO")
+if algo == "AZ":
+    cfg["collecting"].update({"num_episodes": int(os.environ.get("EPISODES", 256)), "num_mcts_searches": int(os.environ.get("SIMS", 16)), "C": 1.41})
+    cfg["learning"]["diff_metric"] = "mcts"
+    cfg["evals"] = {"ppo_deterministic": {"num_episodes": 64}, "mcts": {"num_episodes": 64, "num_mcts_searches": int(os.environ.get("SIMS", 16))}}
+rls = RLSynthesis(env, cfg, {"embedding_size": 64, "common_layers": [64]}, device=0, algorithm_cls=f"twisterl.rl.{algo}")
 t0 = time.time()
 rls.learn(num_iterations=iters, log=lambda r: print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()}, flush=True))
 print("total s", round(time.time() - t0, 2))
