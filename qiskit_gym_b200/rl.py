@@ -35,6 +35,11 @@ class RLSynthesis:
                  policy_cls: str = "twisterl.nn.BasicPolicy", algorithm_cls: str = "twisterl.rl.PPO"):
         self.env = env
         self.env_config = env.to_json()
+        # config objects (configs.PPOConfig / AlphaZeroConfig / BasicPolicyConfig, as in the reference) or dicts in their JSON schema
+        if hasattr(rl_config, "to_json"):
+            algorithm_cls, rl_config = rl_config.algorithm_cls, rl_config.to_json()
+        if hasattr(model_config, "to_json"):
+            policy_cls, model_config = model_config.policy_cls, model_config.to_json()
         self.rl_config = dict(rl_config or {})
         self.model_config = dict(model_config or {})
         self.policy_cls = policy_cls

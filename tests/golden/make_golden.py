@@ -97,3 +97,27 @@ def copy_model_fixtures():
 
 if __name__ == "__main__" and os.path.isdir("/root/reference/examples/models"):
     copy_model_fixtures()
+
+
+def make_config_kats(out_path):
+    """config_kats.json: `to_json()` outputs of the reference's own config classes (src/qiskit_gym/rl/configs.py has no third-party
+    dependency, so it is imported as a plain module) for defaults, custom values and a partial `from_json`."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_configs", "/root/reference/src/qiskit_gym/rl/configs.py")
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["ref_configs"] = m
+    spec.loader.exec_module(m)
+    out = {
+        "ppo_default": m.PPOConfig().to_json(), "az_default": m.AlphaZeroConfig().to_json(),
+        "basic_default": m.BasicPolicyConfig().to_json(), "conv_default": m.Conv1dPolicyConfig().to_json(),
+        "ppo_custom": m.PPOConfig(num_episodes=64, gae_lambda=0.9, lr=1e-3, diff_max=12, evals={"quick": m.EvalConfig(num_episodes=8)}, diff_metric="quick").to_json(),
+        "az_custom": m.AlphaZeroConfig(num_mcts_searches=32, C=2.0, evals={"m": m.EvalConfig(num_mcts_searches=8)}, diff_metric="m").to_json(),
+        "ppo_from_partial": m.PPOConfig.from_json({"collecting": {"num_episodes": 7}, "evals": {"x": {"num_searches": 3}}}).to_json(),
+        "basic_custom": m.BasicPolicyConfig(embedding_size=64, common_layers=[32, 16], value_layers=[8]).to_json(),
+    }
+    json.dump(out, open(out_path, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and os.path.isfile("/root/reference/src/qiskit_gym/rl/configs.py"):
+    import sys
+    make_config_kats(os.path.join(os.path.dirname(os.path.abspath(__file__)), "config_kats.json"))
