@@ -4,7 +4,8 @@
 The reference hands the env to twisterl, whose Rust collectors step `num_episodes` cloned envs on a rayon pool and whose
 Python side runs the clipped-surrogate update.  Here the collection is `collector.RolloutCollector` (every env of one
 `BatchedEnv` plays episodes back to back on the GPU, GAE on the device) and the update is plain PyTorch on the tensors
-the collector left on the device; nothing crosses the PCIe bus during training except the logged scalars.
+the collector left on the device; nothing crosses the PCIe bus during training except the logged scalars.  Under `torch.distributed` (one process per GPU) every
+rank collects on its own environments and the gradients are averaged with one all-reduce per optimiser step (`sync_gradients`).
 
 Config: the nested dict `PPOConfig.to_json()` writes (configs.py:205-240) —
     collecting {num_cores (ignored: the batch is the parallelism), num_episodes, lambda, gamma}
@@ -92,6 +93,57 @@ def merged_config(cfg: dict | None, algorithm: str = "PPO") -> dict:
     return out
 
 
+# ---- data-parallel training: one process per GPU, every rank collects on its own shard of environments, gradients averaged ----
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+def sync_gradients(params, group=None) -> None:
+    """Average the gradients over the ranks with ONE all-reduce of the flattened gradient (NCCL on GPUs, gloo in the CPU tests)."""
+    dist = _dist()
+    if dist is None:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Every replica starts from rank `src`'s weights."""
+    dist = _dist()
+    if dist is None:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def agree_min(value: int, device=None, group=None) -> int:
+    """The smallest `value` over the ranks (how many optimiser steps an epoch makes: every rank must make the same number)."""
+    dist = _dist()
+    if dist is None:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return int(t.item())
+
+
+def mean_over_ranks(value: float, device=None, group=None) -> float:
+    dist = _dist()
+    if dist is None:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item()) / dist.get_world_size(group)
+
+
 class Trainer:
     """What PPO and AlphaZero share: the envs, the difficulty curriculum, the evals, logging and checkpoints.
     Subclasses provide `iterate() -> dict` (collect + update, returns the iteration's scalars)."""
@@ -112,6 +164,9 @@ class Trainer:
         self.env = self._make_env(int(self.cfg["collecting"]["num_episodes"]), device)
         self.device = self.env.device
         self.policy = policy.to(self.device)
+        d = _dist()
+        self.rank, self.world = (d.get_rank(), d.get_world_size()) if d else (0, 1)
+        broadcast_parameters(self.policy)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=float(self.cfg["optimizer"]["lr"]))
 
     def _make_env(self, batch: int, device) -> BatchedEnv:
@@ -134,10 +189,20 @@ class Trainer:
         return int(max(1, min(int(c.depth_slope) * self.difficulty, int(c.max_depth))))
 
     def _minibatches(self, n: int):
+        """Index sets of one epoch.  Under torch.distributed every rank makes the same number of optimiser steps (the smallest count
+        any rank would make), each over an equal share of its own samples."""
         mb = n if not self.minibatch_size else min(int(self.minibatch_size), n)
-        perm = torch.randperm(n, device=self.device) if mb < n else None
-        for s in range(0, n, mb):
-            yield slice(s, s + mb) if perm is None else perm[s:s + mb]
+        steps = agree_min(max(1, -(-n // max(mb, 1))), self.device)
+        mb = -(-n // steps)
+        perm = torch.randperm(n, device=self.device) if steps > 1 else None
+        for k in range(steps):
+            yield slice(k * mb, (k + 1) * mb) if perm is None else perm[k * mb:(k + 1) * mb]
+
+    def _step(self, loss):
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        sync_gradients(list(self.policy.parameters()))
+        self.opt.step()
 
     def _probs(self, obs):
         with torch.no_grad():
@@ -151,7 +216,7 @@ class Trainer:
         episode counts when any of its rollouts ends in success (configs.py:25-35)."""
         ev = self.cfg["evals"][name]
         E, sims = int(ev["num_episodes"]), int(ev.get("num_mcts_searches", 0))
-        base = decision_seed(self.seed ^ 0x5EED5EED, 1_000_003 * (self.iteration + 1))
+        base = decision_seed(self.seed ^ 0x5EED5EED, 1_000_003 * (self.iteration + 1) + 7919 * self.rank)
         steps = self._episode_steps()
         self.policy.eval()
         if sims:
@@ -180,7 +245,7 @@ class Trainer:
                 weights = ms.decide(k) if sims else self._probs(env.observe())
                 env.collect_step(weights, decision_seed(base, (s + 1) * 4099 + k), deterministic=bool(ev["deterministic"]), obs=False)
             solved |= env.status()[2]
-        return float(solved.float().mean().item())
+        return mean_over_ranks(float(solved.float().mean().item()), self.device)
 
     def iterate(self) -> dict:
         raise NotImplementedError
@@ -192,7 +257,7 @@ class Trainer:
         L, lg = self.cfg["learning"], self.cfg["logging"]
         self.difficulty = int(initial_difficulty)
         fh = None
-        if tb_path:
+        if tb_path and self.rank == 0:
             os.makedirs(tb_path, exist_ok=True)
             fh = open(os.path.join(tb_path, "metrics.jsonl"), "a")
         try:
@@ -233,7 +298,8 @@ class PPO(Trainer):
                  seed: int = 0, use_twists: bool = True, minibatch_size: int | None = None, matmul_precision: str = "f32", **env_kwargs):
         super().__init__(env_kind, num_qubits, gateset, policy, config, device=device, seed=seed, minibatch_size=minibatch_size, **env_kwargs)
         self.collector = RolloutCollector(self.env, self.policy, gamma=self.cfg["collecting"]["gamma"], lam=self.cfg["collecting"]["lambda"],
-                                          use_twists=use_twists, seed=seed, matmul_precision=matmul_precision)
+                                          use_twists=use_twists, seed=seed + 104729 * self.rank, first_env_id=self.rank * self.env.batch,
+                                          matmul_precision=matmul_precision)
 
     def iterate(self) -> dict:
         ro = self.collector.collect(self._episode_steps())
@@ -269,9 +335,7 @@ class PPO(Trainer):
                 v_loss = torch.nn.functional.mse_loss(value.float().reshape(-1), ret[sel])
                 entropy = -(logp_all.exp() * logp_all).sum(-1).mean()
                 loss = pi_loss + float(t["vf_coef"]) * v_loss - float(t["ent_coef"]) * entropy
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                self.opt.step()
+                self._step(loss)
                 stats = {"loss": loss.detach(), "pi_loss": pi_loss.detach(), "v_loss": v_loss.detach(), "entropy": entropy.detach(),
                          "clip_frac": ((ratio - 1.0).abs() > clip).float().mean().detach()}
         self.policy.eval()
@@ -320,8 +384,8 @@ class AlphaZero(Trainer):
         dones = torch.zeros((T, B), dtype=torch.bool, device=dev)
         succ = torch.zeros((T, B), dtype=torch.bool, device=dev)
         for t in range(T):
-            s = decision_seed(self.seed, self.counter)
-            env.reset_select(s, 0)
+            s = decision_seed(self.seed + 104729 * self.rank, self.counter)
+            env.reset_select(s, self.rank * B)
             w = ms.decide(t)                         # observes into env.obs, grows the trees, leaves N(a) / sum N in ms.weights
             obs_buf[t].copy_(env.obs)
             pi[t].copy_(w)
@@ -350,9 +414,7 @@ class AlphaZero(Trainer):
                 pi_loss = -(tgt_pi[sel] * logp_all).sum(-1).mean()
                 v_loss = torch.nn.functional.mse_loss(value.float().reshape(-1), tgt_v[sel])
                 loss = pi_loss + self.vf_coef * v_loss
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                self.opt.step()
+                self._step(loss)
                 stats = {"loss": loss.detach(), "pi_loss": pi_loss.detach(), "v_loss": v_loss.detach()}
         self.policy.eval()
         rec.update({k: float(v.item()) for k, v in stats.items()} | {"samples": n})

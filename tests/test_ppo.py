@@ -104,3 +104,57 @@ def test_alphazero_learns_permutation_line4():
     assert hist[-1]["difficulty"] >= 3, trace
     assert max(h["eval/ppo_deterministic"] for h in hist[-5:]) >= 0.5, trace
     assert all(np.isfinite(h["loss"]) for h in hist)
+
+
+def _dp_worker(rank, world, port, q):
+    """Two CPU replicas under gloo: equal start, different data, equal weights after synchronised steps."""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                          # replicas start different ...
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    ppo.broadcast_parameters(net)                          # ... and are made equal
+    start = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(7 + rank)            # every rank sees its own batch
+    x, y = torch.randn(8 + 4 * rank, 6, generator=g), torch.randn(8 + 4 * rank, 3, generator=g)
+    steps = ppo.agree_min(3 + rank)                        # rank 0 would make 3 steps, rank 1 four: both make 3
+    local_grads = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = ((net(x) - y) ** 2).mean()
+        loss.backward()
+        local_grads.append(torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone())
+        ppo.sync_gradients(list(net.parameters()))
+        opt.step()
+    end = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    synced = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    q.put((rank, start.tolist(), end.tolist(), steps, ppo.mean_over_ranks(float(rank + 1)), local_grads[-1].tolist(), synced.tolist()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_helpers_gloo():
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, s0, e0, k0, m0, lg0, sg0), (r1, s1, e1, k1, m1, lg1, sg1) = res
+    assert s0 == s1 and e0 == e1 and s0 != e0            # same start (broadcast), same end (averaged gradients), and they did move
+    assert k0 == k1 == 3 and m0 == m1 == 1.5
+    assert np.allclose(sg0, sg1) and np.allclose(sg0, (np.array(lg0) + np.array(lg1)) / 2, atol=1e-7)
+    # without a process group the helpers are no-ops
+    net = torch.nn.Linear(2, 2)
+    net(torch.ones(1, 2)).sum().backward()
+    g = net.weight.grad.clone()
+    ppo.sync_gradients(list(net.parameters()))
+    assert torch.equal(g, net.weight.grad) and ppo.agree_min(5) == 5 and ppo.mean_over_ranks(2.0) == 2.0
