@@ -188,7 +188,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -437,7 +437,7 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "per_step_launch": per_step, "cpu_baseline": cpu_baseline,
         "packed_obs": packed, "synth": synth, "collector": collector, "engine_error_flags": errs,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -545,8 +545,17 @@ def run_synth(args, dev, local, rank, world):
     return out
 
 
+JSON_OUT = sys.stdout
+
+
 def main():
+    global JSON_OUT
     args = parse_args()
+    # stdout carries exactly one JSON line: keep a private handle on the real stdout for it and point file descriptor 1 at stderr, so
+    # that nothing a library prints there (NCCL's version banner, a warning from a C extension) can land beside the line
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
