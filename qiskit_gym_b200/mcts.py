@@ -60,7 +60,9 @@ class MCTSSearch:
     R * (num_mcts_searches + 1) records for the tree nodes."""
 
     def __init__(self, env_kind, num_qubits, gateset, policy: torch.nn.Module, num_rollouts: int, num_mcts_searches: int, C: float = 2 ** 0.5,
-                 device=None, max_depth: int = 128, **env_kwargs):
+                 device=None, max_depth: int = 128, use_cuda_graph: bool = True, **env_kwargs):
+        """use_cuda_graph: a decision's launches (root evaluation, then per simulation PUCT descent -> clone + step -> policy -> back-up)
+        are captured once and replayed: the whole decision as one graph up to 128 simulations, one graph per simulation beyond."""
         assert num_mcts_searches >= 1
         env_kwargs.setdefault("add_perms", False)
         self.env = BatchedEnv(env_kind, num_qubits, gateset, num_rollouts, device=device, max_depth=max_depth, **env_kwargs)
@@ -81,14 +83,17 @@ class MCTSSearch:
         self.weights = torch.zeros((self.R, A), dtype=torch.float32, device=dev)
         self.num_active = torch.zeros(1, dtype=torch.int32, device=dev)
         self.hook = None            # tests: hook(kind, decision, simulation, tensors...) sees the policy outputs the trees consumed
+        self.use_graph = bool(use_cuda_graph)
+        self._graphs = None         # (root graph or None, simulation graph or None, whole-decision graph or None)
+        self._graph_policy = None
+        self._stream = torch.cuda.Stream(device=dev)
 
     def _policy(self, obs):
         with torch.no_grad():
             logits, value = self.policy(obs)
             return torch.softmax(logits.float(), dim=-1).contiguous(), value.float().reshape(-1).contiguous()
 
-    def decide(self, decision: int = 0):
-        """One decision's tree search for every rollout; leaves the root visit weights in self.weights."""
+    def _root(self, decision: int = 0):
         env, pool, tree = self.env, self.pool, self.tree
         env.observe()
         _, done, _, _ = env.status()
@@ -97,14 +102,59 @@ class MCTSSearch:
             self.hook("root", decision, -1, prior, None)
         pool.copy_records_from(env, self.root_slots)
         tree.begin(prior, done)
+
+    def _simulation(self, decision: int = 0, s: int = 0):
+        pool, tree = self.pool, self.tree
+        tree.select(self.c_puct, self.src, self.dst, self.act)
+        pool.step_slots(self.src, self.dst, self.act, obs=self.leaf_obs, reward=self.leaf_reward, done=self.leaf_done)
+        p, v = self._policy(self.leaf_obs)
+        if self.hook:
+            self.hook("leaf", decision, s, p, v)
+        tree.backup(p, v, self.leaf_reward, self.leaf_done)
+
+    def _decide_eager(self, decision: int = 0):
+        self._root(decision)
         for s in range(self.S):
-            tree.select(self.c_puct, self.src, self.dst, self.act)
-            pool.step_slots(self.src, self.dst, self.act, obs=self.leaf_obs, reward=self.leaf_reward, done=self.leaf_done)
-            p, v = self._policy(self.leaf_obs)
-            if self.hook:
-                self.hook("leaf", decision, s, p, v)
-            tree.backup(p, v, self.leaf_reward, self.leaf_done)
-        return tree.root_weights(self.weights)
+            self._simulation(decision, s)
+        return self.tree.root_weights(self.weights)
+
+    def _capture(self):
+        """Graphs of one decision.  The search reads the rollout engine and writes only the slot pool, the trees and self.weights, so
+        the warm-up runs (cuBLAS workspaces, lazy initialisation) leave the rollouts untouched."""
+        dev = self.env.device
+        for _ in range(2):
+            self._root()
+            self._simulation()
+        self.tree.root_weights(self.weights)
+        torch.cuda.current_stream(dev).synchronize()
+        if self.S <= 128:
+            whole = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(whole, stream=self._stream):
+                self._decide_eager()
+            self._graphs = (None, None, whole)
+        else:
+            root, sim = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(root, stream=self._stream):
+                self._root()
+            with torch.cuda.graph(sim, stream=self._stream):
+                self._simulation()
+            self._graphs = (root, sim, None)
+        self._graph_policy = self.policy
+
+    def decide(self, decision: int = 0):
+        """One decision's tree search for every rollout; leaves the root visit weights in self.weights."""
+        if not self.use_graph or self.hook is not None:
+            return self._decide_eager(decision)
+        if self._graphs is None or self._graph_policy is not self.policy:      # (a graph holds the policy's parameter tensors)
+            self._capture()
+        root, sim, whole = self._graphs
+        if whole is not None:
+            whole.replay()
+            return self.weights
+        root.replay()
+        for _ in range(self.S):
+            sim.replay()
+        return self.tree.root_weights(self.weights)
 
     def solve(self, state, deterministic: bool = False, seed: int = 0, first_rollout_id: int = 0, check_every: int = 4, group=None) -> SearchResult:
         env = self.env

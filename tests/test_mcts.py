@@ -157,3 +157,36 @@ def test_mcts_solve_finds_shallow_targets():
                 chk.step(a)
             assert chk.success()
     assert solved >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sims", [12, 130])
+def test_graph_replay_equals_eager_tree_search(sims):
+    """The captured decision (one graph up to 128 simulations, root + per-simulation graphs beyond) leaves the same visit weights, bit
+    for bit, as the launch-by-launch search; prints the time of both."""
+    import time
+    from qiskit_gym_b200.mcts import MCTSSearch
+    from qiskit_gym_b200.search import BasicPolicy
+    kind, n, gs, kw = H.config_table()["C2_lf8_line"]
+    torch.manual_seed(1)
+    pol = BasicPolicy([n, n], len(gs), embedding_size=64, common_layers=(32,))
+    R = 96
+    tarr = H.random_targets(kind, n, gs, R, 3, scramble=6)
+    out = {}
+    for graph in (False, True):
+        ms = MCTSSearch(kind, n, gs, pol, R, sims, max_depth=16, add_inverts=False, use_cuda_graph=graph)
+        ms.env.set_state(tarr)
+        ms.env.search_begin(5, 0)
+        w = []
+        for d in range(3):
+            w.append(ms.decide(d).clone())
+            ms.env.search_step(ms.weights, deterministic=True, obs=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for d in range(3):
+            ms.decide(d)
+        torch.cuda.synchronize()
+        out[graph] = (w, (time.perf_counter() - t0) / 3)
+    for a, b in zip(out[False][0], out[True][0]):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    print(f"tree search decision, {R} rollouts x {sims} simulations: eager {out[False][1] * 1e3:.2f} ms, graph {out[True][1] * 1e3:.2f} ms")

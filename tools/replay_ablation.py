@@ -17,7 +17,7 @@ def main():
     cfg = sys.argv[1] if len(sys.argv) > 1 else "C3_clifford8_full"
     sizes = [int(x) for x in sys.argv[2:]] or [65536]
     kind, n, gateset, kw = W.baseline_configs()[cfg]
-    T, RING = 128, 5
+    T, RING = 128, int(os.environ.get("RING", 5))
     for B in sizes:
         env = BatchedEnv(kind, n, gateset, B, device=0, add_inverts=False, add_perms=False, **kw)
         env.set_state(W.random_targets(kind, n, gateset, min(B, 65536), seed=1)[np.arange(B) % min(B, 65536)])
@@ -55,7 +55,7 @@ def main():
             ms = e0.elapsed_time(e1) / reps
             nbytes = T * B * ((4 * O if "obs" in kwv else 0) + (A if "mask" in kwv else 0) + (6 if "reward" in kwv else 0) + 4)
             print(json.dumps({"config": cfg, "envs": B, "variant": name, "ms": ms, "env_steps_per_s": T * B / ms * 1e3, "stream_gbs": nbytes / ms / 1e6,
-                              "stagger": os.environ.get("QG_STAGGER_NS", "default")}), flush=True)
+                              "stagger": os.environ.get("QG_STAGGER_NS", "default"), "ring": RING}), flush=True)
         del env, obs, mask
 
 
