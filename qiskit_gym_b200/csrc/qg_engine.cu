@@ -733,11 +733,19 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
     const size_t step_smem = (size_t)e->sm_warp_words * 4 + 16;
     if (policy_smem_bytes(pol->d) + step_smem > 220 * 1024) { set_error("qg_search_run: policy + env do not fit one SM's shared memory"); return QG_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
+    // the policy's first-layer accumulators, one set per CTA of 8 rollouts (grown on first use; a launch in flight on another stream
+    // with the same policy handle must not overlap a growing call: one host thread per handle, like the engine)
+    const size_t ctas = (size_t)((e->B + kPolRows - 1) / kPolRows);
+    if (ctas > pol->acc0_ctas) {
+        if (pol->acc0) { CUDA_OK(cudaDeviceSynchronize()); CUDA_OK(cudaFree(pol->acc0)); pol->acc0 = nullptr; pol->acc0_ctas = 0; }
+        CUDA_OK(cudaMalloc(&pol->acc0, ctas * kPolRows * (size_t)pol->d.width[0] * sizeof(long long)));
+        pol->acc0_ctas = ctas;
+    }
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: CUDA_OK(launch_search_fused<QG_ENV_PERMUTATION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
-        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_search_fused<QG_ENV_LINEAR_FUNCTION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
-        case QG_ENV_CLIFFORD: CUDA_OK(launch_search_fused<QG_ENV_CLIFFORD>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
-        default: CUDA_OK(launch_search_fused<QG_ENV_PAULI_NETWORK>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, st)); break;
+        case QG_ENV_PERMUTATION: CUDA_OK(launch_search_fused<QG_ENV_PERMUTATION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_search_fused<QG_ENV_LINEAR_FUNCTION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(launch_search_fused<QG_ENV_CLIFFORD>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
+        default: CUDA_OK(launch_search_fused<QG_ENV_PAULI_NETWORK>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
     }
     return QG_OK;
 }

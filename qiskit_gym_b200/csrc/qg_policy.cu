@@ -12,10 +12,11 @@
 // and keeps one f32 accumulator per (feature, row) in registers, so each weight feeds 8 FMAs.  Weights are kept
 // transposed ([in][out], rows padded to 16 bytes) and stream L2 -> shared memory in 16 KB tiles with cp.async.bulk
 // completing on mbarriers, three tiles in flight, one flat tile schedule across all layers so the pipeline never
-// drains at a layer boundary.  The first layer's tiles are the weight rows of the observation entries set in any of
-// the CTA's rows (its input is then the rows' 0/1 values, so it runs through the same FMA loop as the dense layers).
-// Sums run over the input features in ascending order, in f32.
+// drains at a layer boundary.  The first layer is an exact gather-sum in fixed point (layer0_fixed in qg_policy_kernels.cuh:
+// 64-bit integer accumulators, order independent), which the one-launch search updates incrementally from the observation
+// bits that changed; the dense layers sum over the input features in ascending order, in f32.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -57,6 +58,7 @@ extern "C" {
 void qg_policy_destroy(qg_policy* p) {
     if (!p) return;
     for (float* b : p->bufs) cudaFree(b);
+    if (p->acc0) cudaFree(p->acc0);
     delete p;
 }
 
@@ -82,19 +84,29 @@ int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const
     PolicyDev& d = p->d;
     d.num_layers = num_layers; d.obs_size = obs_size; d.obs_words = (obs_size + 31) / 32;
     d.act0_floats = maxw * kPolRows;
-    d.act1_floats = std::max(maxw, obs_size) * kPolRows;
+    d.act1_floats = maxw * kPolRows;
     for (int l = 0; l < num_layers; ++l) {
         const int in = l == 0 ? obs_size : out_features[l - 1], o = out_features[l], os = (o + 3) / 4 * 4;
         d.width[l] = o; d.stride[l] = os;
         std::vector<float> t((size_t)in * os, 0.0f);
         for (int j = 0; j < o; ++j) for (int k = 0; k < in; ++k) t[(size_t)k * os + j] = weights_host[l][(size_t)j * in + k];   // torch Linear.weight is [out][in]
+        if (l == 0) {
+            // fixed point for the exact (order-independent) first-layer sum: the largest |weight| lands just below 2^30
+            float mx = 0.0f;
+            for (float v : t) { if (!std::isfinite(v)) { set_error("qg_policy_create: non-finite weight"); qg_policy_destroy(p); return QG_ERR_INVALID; } mx = std::max(mx, std::fabs(v)); }
+            int shift = 30;
+            if (mx > 0.0f) { int e = 0; std::frexp(mx, &e); shift = std::min(30 - e, 120); }      // mx < 2^e  =>  mx * 2^(30-e) < 2^30
+            d.w0_scale = std::ldexp(1.0f, -shift);
+            for (float& v : t) { const int32_t q = (int32_t)std::llrint(std::ldexp((double)v, shift)); std::memcpy(&v, &q, 4); }
+        }
         float *w = nullptr, *b = nullptr;
         cudaError_t ce = cudaMalloc(&w, t.size() * 4);
         if (ce == cudaSuccess) { p->bufs.push_back(w); ce = cudaMalloc(&b, (size_t)o * 4); }
         if (ce == cudaSuccess) { p->bufs.push_back(b); ce = cudaMemcpy(w, t.data(), t.size() * 4, cudaMemcpyHostToDevice); }
         if (ce == cudaSuccess) ce = cudaMemcpy(b, biases_host[l], (size_t)o * 4, cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) { set_error(std::string("qg_policy_create: ") + cudaGetErrorString(ce)); qg_policy_destroy(p); return QG_ERR_CUDA; }
-        d.wt[l] = w; d.bias[l] = b;
+        d.wt[l] = l == 0 ? nullptr : w; d.bias[l] = b;
+        if (l == 0) d.w0q = reinterpret_cast<const int32_t*>(w);
     }
     p->smem = policy_smem_bytes(d);
     if (p->smem > 210 * 1024) { set_error("qg_policy_create: the network needs more shared memory than one SM has"); qg_policy_destroy(p); return QG_ERR_UNSUPPORTED; }

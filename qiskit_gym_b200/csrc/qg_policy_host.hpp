@@ -9,4 +9,6 @@ struct qg_policy {
     qg::PolicyDev d{};
     std::vector<float*> bufs;
     size_t smem = 0;
+    long long* acc0 = nullptr;       // first-layer accumulators of the one-launch search, [CTAs][8][width[0]] (allocated on first use)
+    size_t acc0_ctas = 0;
 };

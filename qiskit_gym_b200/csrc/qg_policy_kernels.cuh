@@ -22,9 +22,11 @@ struct PolicyDev {
     int32_t num_layers, obs_size, obs_words;
     int32_t width[kPolMaxLayers];        // output features of layer l (layer 0 consumes the observation)
     int32_t stride[kPolMaxLayers];       // width rounded up to a multiple of 4 floats: row stride of the transposed weights
-    const float* wt[kPolMaxLayers];      // transposed weights [in][stride]
+    const float* wt[kPolMaxLayers];      // transposed weights [in][stride] (layer 0: null, see w0q)
     const float* bias[kPolMaxLayers];
-    int32_t act0_floats, act1_floats;    // activation buffers ([feature][row]); act1 also holds the first layer's 0/1 inputs
+    const int32_t* w0q;                  // first layer's transposed weights in fixed point: w0q[k][j] = rint(W0[j][k] * 2^w0_shift), [obs_size][stride[0]]
+    float w0_scale;                      // 2^-w0_shift
+    int32_t act0_floats, act1_floats;    // activation buffers ([feature][row])
 };
 
 // ---- mbarrier / bulk-copy primitives (weights stream L2 -> shared memory with cp.async.bulk, no register staging) ------
@@ -111,19 +113,64 @@ __device__ __forceinline__ void store_features(float* __restrict__ dst, int j, c
     reinterpret_cast<float4*>(dst + (size_t)j * kPolRows)[1] = hi;
 }
 
-// One layer for the consumer warps: the 512 compute threads are two halves of 256; within a half, thread ht owns the output
+// The first layer: h[r][j] = act(bias[j] + sum over the set observation entries k of row r of W0[j][k]), as an EXACT sum.  The weights
+// are fixed-point integers (w0q, 31 significant bits below the largest |weight|: finer than the f32 weights' own 24 bits there) and the
+// accumulators 64-bit integers, so the sum does not depend on the order of its terms.  That is what lets the one-launch search update
+// it instead of recomputing it: between two decisions of a rollout only a few entries change (a SWAP moves two of a permutation's 27
+// one-hot positions), so the CTA adds the weight rows of the entries that appeared and subtracts those of the entries that vanished
+// (`acc0`: its accumulators [row][feature] in global memory, L2 resident) — the same integers a fresh sum over all set entries gives,
+// bit for bit (the stand-alone kernel and the first decision do exactly that: acc0 == nullptr / fresh).  ~30 weight rows per decision
+// instead of ~200, fetched with plain coalesced loads (4 in flight per thread), no shared-memory staging.
+// uent[0..U): entry index | rows that gained it << 16 | rows that lost it << 24.  Thread t owns features t, t + 512.
+__device__ __forceinline__ void layer0_fixed(const PolicyDev& p, int U, const uint32_t* __restrict__ uent, float* __restrict__ dst, long long* __restrict__ acc0,
+                                             bool fresh, bool relu, int tid) {
+    const int out = p.width[0], ostr = p.stride[0];
+    const int32_t* __restrict__ wq = p.w0q;
+    for (int j = tid; j < out; j += kPolConsumers) {
+        // acc[r] carries row r's sum scaled by 2^r: the row's bit of the mask is used as it stands (value 2^r) as the multiplier of one
+        // 32 x 32 + 64-bit multiply-add, instead of being turned into 0 / 1 first; the scale comes off with an exact shift at the end
+        long long acc[kPolRows];
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) acc[r] = (acc0 && !fresh) ? acc0[(size_t)r * out + j] * (1ll << r) : 0ll;
+        auto apply = [&](int w, uint32_t e) {          // e is the same in every thread of the CTA: the test of its `lost` byte is a uniform branch
+            const uint32_t gained = (e >> 16) & 0xFFu, lost = e >> 24;
+#pragma unroll
+            for (int r = 0; r < kPolRows; ++r) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[r]) : "r"(w), "r"((int)(gained & (1u << r))));
+            if (lost) {
+                const int nw = -w;
+#pragma unroll
+                for (int r = 0; r < kPolRows; ++r) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[r]) : "r"(nw), "r"((int)(lost & (1u << r))));
+            }
+        };
+        int u = 0;
+        for (; u + 4 <= U; u += 4) {
+            uint32_t e[4]; int w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { e[i] = uent[u + i]; w[i] = __ldg(wq + (size_t)(e[i] & 0xFFFFu) * ostr + j); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) apply(w[i], e[i]);
+        }
+        for (; u < U; ++u) { const uint32_t e = uent[u]; apply(__ldg(wq + (size_t)(e & 0xFFFFu) * ostr + j), e); }
+        float v[kPolRows];
+        const float b = __ldg(p.bias[0] + j);
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) {
+            const long long a = acc[r] >> r;                               // exact: every term is a multiple of 2^r
+            if (acc0) acc0[(size_t)r * out + j] = a;
+            v[r] = __fadd_rn(b, __fmul_rn((float)a, p.w0_scale));           // (float)int64: one rounding; the scale is a power of two
+        }
+        store_features(dst, j, v, relu);
+    }
+}
+
+// One dense layer for the consumer warps: the 512 compute threads are two halves of 256; within a half, thread ht owns the output
 // features ht + i * 256 (NI of them) for all 8 rows, and half h takes the inputs u = h, h + 2, .. of every tile; half 1 hands its
-// partial sums to half 0 through shared memory.
-//   GATHER (the first layer): the layer's K inputs are the listed observation entries uidx[0..K) and its weight rows are scattered;
-//     the consumers fetch them themselves with 16-byte cp.async (a tile = 2 warp instructions per warp; issuing one cp.async.bulk per
-//     row from the producer costs ~130 cycles each) through the ring of kPolStages stages, one named barrier per tile; when done,
-//     thread 0 arrives on `l0done` so the producer warp may start filling the stages.
-//   otherwise: tiles arrive from the producer warp (full / empty mbarriers).
+// partial sums to half 0 through shared memory.  Tiles arrive from the producer warp (full / empty mbarriers).
 // (A mapping with 4 consecutive features per thread — one LDS.128 for the weights, 3 loads per 32 FMAs — was measured 40 % slower:
 // its per-tile bookkeeping outweighs the saved shared-memory traffic at 2 inputs per group and tile.)
-template <int NI, bool GATHER>
+template <int NI>
 __device__ __forceinline__ void consume_layer(const PolicyDev& p, int l, int K, const float* __restrict__ src, float* __restrict__ dst, float* tiles,
-                                              uint64_t* full, uint64_t* empty, uint64_t* l0done, const uint16_t* uidx, float* part, int& G, int tid, int lane) {
+                                              uint64_t* full, uint64_t* empty, float* part, int& G, int tid, int lane) {
     const int out = p.width[l], ostr = p.stride[l], kt = tile_rows(p, l), nt = (K + kt - 1) / kt;
     const int half = tid / kPolHalf, ht = tid - half * kPolHalf;
     float acc[NI][kPolRows];
@@ -137,46 +184,16 @@ __device__ __forceinline__ void consume_layer(const PolicyDev& p, int l, int K, 
         for (int r = 0; r < kPolRows; ++r) acc[i][r] = b;
     }
     const bool active = NI > 1 || (ht & ~31) < out;        // warp-uniform: this warp owns at least one real feature
-    if constexpr (GATHER) {
-        const int cpr = ostr >> 2;                         // 16-byte chunks per weight row
-        const float* __restrict__ wt = p.wt[l];
-        auto issue = [&](int t) {
-            if (t < nt) {
-                float* tile = tiles + (size_t)(t % kPolStages) * kPolTileFloats;
-                const int k0 = t * kt, total = min(kt, K - k0) * cpr;
-                for (int ch = tid; ch < total; ch += kPolConsumers) {
-                    const int u = ch / cpr, cc = ch - u * cpr;
-                    cp_async_16(tile + (size_t)u * ostr + cc * 4, wt + (size_t)uidx[k0 + u] * ostr + cc * 4);
-                }
-            }
-            cp_async_commit();
-        };
-        for (int t = 0; t < kPolStages - 1; ++t) issue(t);
-        for (int t = 0; t < nt; ++t) {
-            cp_async_wait<kPolStages - 2>();               // this thread's part of tile t has landed
-            consumers_sync();                              // everybody's part has, and everybody is done with tile t-1
-            issue(t + kPolStages - 1);                     // into the stage tile t-1 used
-            if (active) {
-                const int k0 = t * kt;
-                fma_tile<NI>(acc, tiles + (size_t)(t % kPolStages) * kPolTileFloats, reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows), min(kt, K - k0), ostr, jc,
-                             half, kPolHalves);
-            }
+    for (int t = 0; t < nt; ++t, ++G) {
+        const int stage = G % kPolStages;
+        mbar_wait(full + stage, (uint32_t)((G / kPolStages) & 1));
+        if (active) {
+            const int k0 = t * kt;
+            fma_tile<NI>(acc, tiles + (size_t)stage * kPolTileFloats, reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows), min(kt, K - k0), ostr, jc, half,
+                         kPolHalves);
         }
-        cp_async_wait<0>();
-        consumers_sync();                                  // the stages are free: hand them to the producer warp
-        if (tid == 0) mbar_arrive(l0done);
-    } else {
-        for (int t = 0; t < nt; ++t, ++G) {
-            const int stage = G % kPolStages;
-            mbar_wait(full + stage, (uint32_t)((G / kPolStages) & 1));
-            if (active) {
-                const int k0 = t * kt;
-                fma_tile<NI>(acc, tiles + (size_t)stage * kPolTileFloats, reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows), min(kt, K - k0), ostr, jc, half,
-                             kPolHalves);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);     // this warp is done with the stage
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);         // this warp is done with the stage
     }
     // combine the halves' partial sums (half 1 -> shared memory -> half 0), activation, store
     if (half == 1) {
@@ -247,18 +264,18 @@ __device__ __forceinline__ void consume_layer_narrow(const PolicyDev& p, int l, 
 struct PolicySmem {
     float* tiles;        // [kPolStages][kPolTileFloats] weight tiles
     float* act0;         // [act0_floats]
-    float* act1;         // [act1_floats]  (also the first layer's 0/1 inputs)
+    float* act1;         // [act1_floats]
     uint64_t* full;      // [kPolStages]
     uint64_t* empty;     // [kPolStages]
-    uint64_t* l0done;    // [1] the consumers are done with the first layer's own use of the stages
     float* part;         // [kPolPartFloats] partial sums [group][feature][row] of the current layer
-    uint32_t* rowbits;   // [kPolRows][obs_words]
+    uint32_t* rowbits;   // [kPolRows][obs_words] the rows' packed observations
+    uint32_t* oldbits;   // [kPolRows][obs_words] the observations the first layer's accumulators (acc0) currently stand for
     int* wcnt;           // [16] per-warp counts, [31] = U
-    uint16_t* uidx;      // [obs_size] observation entries set in any of the CTA's rows
+    uint32_t* uent;      // [obs_size] entries that changed in any of the CTA's rows: index | gained-by rows << 16 | lost-by rows << 24
 };
 __host__ __device__ inline size_t policy_smem_bytes(const PolicyDev& p) {
     size_t b = ((size_t)kPolStages * kPolTileFloats + p.act0_floats + p.act1_floats + kPolPartFloats) * 4 + (2 * kPolStages + 2) * 8 +
-               (size_t)kPolRows * p.obs_words * 4 + 32 * 4 + (size_t)p.obs_size * 2;
+               (size_t)2 * kPolRows * p.obs_words * 4 + 32 * 4 + (size_t)p.obs_size * 4;
     return (b + 127) / 128 * 128;
 }
 __device__ __forceinline__ PolicySmem policy_smem_carve(const PolicyDev& p, float* sm) {
@@ -269,86 +286,47 @@ __device__ __forceinline__ PolicySmem policy_smem_carve(const PolicyDev& p, floa
     s.part = s.act1 + p.act1_floats;
     s.full = reinterpret_cast<uint64_t*>(s.part + kPolPartFloats);
     s.empty = s.full + kPolStages;
-    s.l0done = s.empty + kPolStages;
-    s.rowbits = reinterpret_cast<uint32_t*>(s.l0done + 2);
-    s.wcnt = reinterpret_cast<int*>(s.rowbits + kPolRows * p.obs_words);
-    s.uidx = reinterpret_cast<uint16_t*>(s.wcnt + 32);
+    s.rowbits = reinterpret_cast<uint32_t*>(s.empty + kPolStages + 2);
+    s.oldbits = s.rowbits + kPolRows * p.obs_words;
+    s.wcnt = reinterpret_cast<int*>(s.oldbits + kPolRows * p.obs_words);
+    s.uent = reinterpret_cast<uint32_t*>(s.wcnt + 32);
     return s;
 }
 __device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int tid) {
     if (tid == 0) {
         for (int s = 0; s < kPolStages; ++s) { mbar_init(ps.full + s, 1); mbar_init(ps.empty + s, kPolConsumers / 32); }
-        mbar_init(ps.l0done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
 }
 
-// One forward pass for the CTA's kPolRows batch rows starting at row0; every one of the kPolThreads threads calls it (it contains
-// __syncthreads).  Warps 0..7 compute (consumers); warp 8 is the producer: one lane streams the weight tiles of all layers, in
-// order, through a ring of kPolStages shared-memory stages (full / empty mbarriers), so no consumer ever waits for copy issue.
+// One forward pass for the CTA's kPolRows batch rows starting at row0; every one of the kPolThreads threads calls it.  Warps 0..15
+// compute (consumers); warp 16 is the producer: one lane streams the weight tiles of the layers after the first, in order, through a
+// ring of kPolStages shared-memory stages (full / empty mbarriers) — it starts right away, so the second layer's first tiles land
+// while the consumers are still busy with the first layer (whose weights they read themselves, layer0_fixed).
 // G is the running tile counter of the ring (same value in every thread; it carries over when the function is called again) and
 // `pass` counts the calls (0, 1, 2, ..).
 // `bits` may have been written earlier by this CTA in the same kernel: it is read with ld.global.cg, never through the
 // non-coherent path.
 // bits == nullptr: ps.rowbits already holds the rows' packed observations (the fused search kernel's step wrote them there).
+// acc0: the CTA's first-layer accumulators [kPolRows][width[0]] (int64, global memory) when the caller evaluates the same rows again
+// and again (the one-launch search): pass 0 sums every set entry, later passes only apply what changed since the previous pass.
+// nullptr: a fresh sum, nothing kept.
 // probs_rows: row stride of `probs` is the action count and row r of the CTA goes to probs + (row_base + r) * A, with
 // row_base = row0 for the global [B][A] tensor or 0 for a CTA-private (shared-memory) buffer.
 __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const PolicySmem& ps, const uint32_t* bits, int64_t row0, int64_t B,
-                                                    float* probs, float* logits_out, int& G, int pass = 0, int64_t probs_row_base = -1) {
+                                                    float* probs, float* logits_out, int& G, int pass = 0, int64_t probs_row_base = -1,
+                                                    long long* acc0 = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = tid >= kPolConsumers;
     float* const tiles = ps.tiles; float* const act0 = ps.act0; float* const act1 = ps.act1;
     uint64_t* const full = ps.full; uint64_t* const empty = ps.empty;
-    uint32_t* const rowbits = ps.rowbits; int* const wcnt = ps.wcnt; uint16_t* const uidx = ps.uidx;
-    // ---- 1. the entries set in any of the CTA's rows, ascending, with the rows' 0/1 values as the first layer's input ----
-    if (!producer) {
-        if (bits) {
-            for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) {
-                const int r = i / p.obs_words, w = i - r * p.obs_words;
-                uint32_t word = (row0 + r < B) ? __ldcg(bits + (size_t)(row0 + r) * p.obs_words + w) : 0u;
-                if (w == p.obs_words - 1 && (p.obs_size & 31)) word &= (1u << (p.obs_size & 31)) - 1u;
-                rowbits[i] = word;
-            }
-            consumers_sync();
-        }
-        int U = 0;
-        for (int base = 0; base < p.obs_size; base += kPolConsumers) {
-            const int k = base + tid;
-            uint32_t m = 0;
-            if (k < p.obs_size) {
-#pragma unroll
-                for (int r = 0; r < kPolRows; ++r) m |= ((rowbits[r * p.obs_words + (k >> 5)] >> (k & 31)) & 1u) << r;
-            }
-            const uint32_t vote = __ballot_sync(0xFFFFFFFFu, m != 0);
-            if (lane == 0) wcnt[warp] = __popc(vote);
-            consumers_sync();
-            int before = U, total = U;
-#pragma unroll
-            for (int w2 = 0; w2 < kPolConsumers / 32; ++w2) { const int c = wcnt[w2]; if (w2 < warp) before += c; total += c; }
-            if (m) {
-                const int at = before + __popc(vote & ((1u << lane) - 1u));
-                uidx[at] = (uint16_t)k;
-                float4 lo, hi;
-                lo.x = (m & 1u) ? 1.f : 0.f; lo.y = (m & 2u) ? 1.f : 0.f; lo.z = (m & 4u) ? 1.f : 0.f; lo.w = (m & 8u) ? 1.f : 0.f;
-                hi.x = (m & 16u) ? 1.f : 0.f; hi.y = (m & 32u) ? 1.f : 0.f; hi.z = (m & 64u) ? 1.f : 0.f; hi.w = (m & 128u) ? 1.f : 0.f;
-                reinterpret_cast<float4*>(act1 + (size_t)at * kPolRows)[0] = lo;
-                reinterpret_cast<float4*>(act1 + (size_t)at * kPolRows)[1] = hi;
-            }
-            U = total;
-            consumers_sync();
-        }
-        if (tid == 0) wcnt[31] = U;
-    }
-    __syncthreads();                               // U and uidx visible to the producer
-    const int U = wcnt[31];
+    uint32_t* const rowbits = ps.rowbits; uint32_t* const oldbits = ps.oldbits; int* const wcnt = ps.wcnt; uint32_t* const uent = ps.uent;
 
-    // ---- 2. producer: streams the contiguous weight rows of the layers after the first, tile after tile (the first layer's rows
-    // are gathered by the consumers themselves, through the same stages: wait until they hand them over)
+    // ---- producer: the contiguous weight rows of the layers after the first, tile after tile
     if (producer) {
         int total = 0;
-        for (int l = 1; l < p.num_layers; ++l) total += layer_tiles(p, l, U);
+        for (int l = 1; l < p.num_layers; ++l) total += layer_tiles(p, l, 0);
         if (lane == 0 && total > 0) {
-            mbar_wait(ps.l0done, (uint32_t)(pass & 1));
             int g = G;
             for (int l = 1; l < p.num_layers; ++l) {
                 const int K = p.width[l - 1], kt = tile_rows(p, l), nt = (K + kt - 1) / kt;
@@ -365,27 +343,60 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
         return;
     }
 
-    // ---- 3. consumers ------------------------------------------------------------------------------------------------------
-    float* src = act1;                             // layer 0 reads the 0/1 inputs
+    // ---- 1. consumers: the observation entries that changed in any of the CTA's rows since the accumulators were last brought up to
+    // date (all set entries on a fresh pass), ascending, each with the rows that gained / lost it
+    const bool fresh = acc0 == nullptr || pass == 0;
+    if (bits) {
+        for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) {
+            const int r = i / p.obs_words, w = i - r * p.obs_words;
+            uint32_t word = (row0 + r < B) ? __ldcg(bits + (size_t)(row0 + r) * p.obs_words + w) : 0u;
+            if (w == p.obs_words - 1 && (p.obs_size & 31)) word &= (1u << (p.obs_size & 31)) - 1u;
+            rowbits[i] = word;
+        }
+        consumers_sync();
+    }
+    int U = 0;
+    for (int base = 0; base < p.obs_size; base += kPolConsumers) {
+        const int k = base + tid;
+        uint32_t now = 0, was = 0;
+        if (k < p.obs_size) {
+#pragma unroll
+            for (int r = 0; r < kPolRows; ++r) {
+                now |= ((rowbits[r * p.obs_words + (k >> 5)] >> (k & 31)) & 1u) << r;
+                if (!fresh) was |= ((oldbits[r * p.obs_words + (k >> 5)] >> (k & 31)) & 1u) << r;
+            }
+        }
+        const uint32_t gained = now & ~was, lost = was & ~now;
+        const uint32_t vote = __ballot_sync(0xFFFFFFFFu, (gained | lost) != 0);
+        if (lane == 0) wcnt[warp] = __popc(vote);
+        consumers_sync();
+        int before = U, total = U;
+#pragma unroll
+        for (int w2 = 0; w2 < kPolConsumers / 32; ++w2) { const int c = wcnt[w2]; if (w2 < warp) before += c; total += c; }
+        if (gained | lost) uent[before + __popc(vote & ((1u << lane) - 1u))] = (uint32_t)k | (gained << 16) | (lost << 24);
+        U = total;
+        consumers_sync();
+    }
+    if (acc0) {                                    // the accumulators will stand for these observations
+        for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) oldbits[i] = rowbits[i];
+    }
+
+    // ---- 2. layers
+    float* src = act1;
     float* dst = act0;
     for (int l = 0; l < p.num_layers; ++l) {
         const int ni = (p.width[l] + kPolHalf - 1) / kPolHalf;
         if (l == 0) {
-            switch (ni) {
-                case 1: consume_layer<1, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-                case 2: consume_layer<2, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-                case 3: consume_layer<3, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-                default: consume_layer<4, true>(p, 0, U, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-            }
+            layer0_fixed(p, U, uent, dst, acc0, fresh, p.num_layers > 1, tid);
         } else if (p.width[l] <= 64) {
             consume_layer_narrow(p, l, p.width[l - 1], src, dst, tiles, full, empty, ps.part, G, tid, lane);
         } else {
             const int K = p.width[l - 1];
             switch (ni) {
-                case 1: consume_layer<1, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-                case 2: consume_layer<2, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-                case 3: consume_layer<3, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
-                default: consume_layer<4, false>(p, l, K, src, dst, tiles, full, empty, ps.l0done, uidx, ps.part, G, tid, lane); break;
+                case 1: consume_layer<1>(p, l, K, src, dst, tiles, full, empty, ps.part, G, tid, lane); break;
+                case 2: consume_layer<2>(p, l, K, src, dst, tiles, full, empty, ps.part, G, tid, lane); break;
+                case 3: consume_layer<3>(p, l, K, src, dst, tiles, full, empty, ps.part, G, tid, lane); break;
+                default: consume_layer<4>(p, l, K, src, dst, tiles, full, empty, ps.part, G, tid, lane); break;
             }
         }
         consumers_sync();
@@ -393,7 +404,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
         dst = (dst == act0) ? act1 : act0;
     }
 
-    // ---- 4. softmax over the action logits, warp r <-> row r -------------------------------------------------------------
+    // ---- 3. softmax over the action logits, warp r <-> row r -------------------------------------------------------------
     if (warp < kPolRows) {
         const int64_t row = row0 + warp;
         if (row < B) {

@@ -4,8 +4,9 @@
 // its 8 packed observations (policy_forward_rows: 8 compute warps + the weight-streaming producer warp), then warp 0 plays the
 // sampled / arg-max actions on its 8 environments with the same step_tile<KIND, MODE_SEARCH> the two-kernel path launches,
 // which writes the next packed observations; it loops until its rollouts are all final or the decision budget is spent.  No
-// launch gaps, no host round trips: a search is one launch.  Observations and action weights go through global memory (L2) like
-// in the two-kernel path, so both paths produce identical bits.
+// launch gaps, no host round trips: a search is one launch.  The first layer's exact integer accumulators stay in global memory
+// (L2) between decisions and are only updated with the observation entries the step changed (layer0_fixed); since that sum is order
+// independent, the decisions are bit for bit those of the two-kernel path, which sums every set entry afresh.
 #pragma once
 #include "qg_kernels.cuh"
 #include "qg_policy_kernels.cuh"
@@ -14,7 +15,7 @@ namespace qg {
 
 template <int KIND>
 __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a, const __grid_constant__ PolicyDev p,
-                                                               int max_decisions, int32_t* __restrict__ decisions_out) {
+                                                               int max_decisions, int32_t* __restrict__ decisions_out, long long* __restrict__ acc0_all) {
     extern __shared__ __align__(128) float smf[];
     __shared__ uint32_t s_active;
     const PolicySmem ps = policy_smem_carve(p, smf);
@@ -25,13 +26,14 @@ __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_const
     float* const s_probs = reinterpret_cast<float*>(wbase + a.sm_warp_words);      // [kPolRows][A] action weights of the CTA's rollouts
     const bool obs_from_O = (KIND == QG_ENV_PAULI_NETWORK) || (KIND == QG_ENV_PERMUTATION && c.OW > 0);
     const uint32_t* const obs_stream = wbase + (obs_from_O ? a.sm_obs : c.off_state * kStride);   // the step's [word][env] observation bit stream
+    long long* const acc0 = acc0_all + (size_t)blockIdx.x * kPolRows * p.width[0];     // this CTA's first-layer accumulators
     policy_init_barriers(ps, tid);
     __syncthreads();
     int G = 0, it = 0;
     for (; it < max_decisions; ++it) {
         // decision `it`: the first one reads the packed observations qg_observe_bits left in global memory, the later ones find them
         // in ps.rowbits; the action weights stay in shared memory; the env records stay in the step's shared-memory region
-        policy_forward_rows(p, ps, it == 0 ? a.obs_bits : nullptr, row0, c.B, s_probs, nullptr, G, it, 0);
+        policy_forward_rows(p, ps, it == 0 ? a.obs_bits : nullptr, row0, c.B, s_probs, nullptr, G, it, 0, acc0);
         __syncthreads();
         if (warp == 0) {
             const uint32_t en = step_tile<KIND, MODE_SEARCH, 0>(c, a, wbase, nullptr, lane, row0, cnt, it > 0, s_probs);
@@ -51,12 +53,13 @@ __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_const
 }
 
 template <int KIND>
-cudaError_t launch_search_fused(const DevCfg& c, const StepArgs& a, const PolicyDev& p, int max_decisions, int32_t* decisions_out, size_t step_smem_bytes, cudaStream_t st) {
+cudaError_t launch_search_fused(const DevCfg& c, const StepArgs& a, const PolicyDev& p, int max_decisions, int32_t* decisions_out, size_t step_smem_bytes, long long* acc0,
+                                cudaStream_t st) {
     const size_t smem = policy_smem_bytes(p) + step_smem_bytes + (size_t)kPolRows * p.width[p.num_layers - 1] * 4;
     cudaError_t e = cudaFuncSetAttribute(k_search_fused<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((c.B + kPolRows - 1) / kPolRows);
-    k_search_fused<KIND><<<grid, kPolThreads, smem, st>>>(c, a, p, max_decisions, decisions_out);
+    k_search_fused<KIND><<<grid, kPolThreads, smem, st>>>(c, a, p, max_decisions, decisions_out, acc0);
     return cudaGetLastError();
 }
 
