@@ -113,6 +113,40 @@ __device__ __forceinline__ void store_features(float* __restrict__ dst, int j, c
     reinterpret_cast<float4*>(dst + (size_t)j * kPolRows)[1] = hi;
 }
 
+// ---- shared-memory plan of one policy CTA ---------------------------------------------------------------------------------------
+struct PolicySmem {
+    float* tiles;        // [kPolStages][kPolTileFloats] weight tiles
+    float* act0;         // [act0_floats]
+    float* act1;         // [act1_floats]
+    uint64_t* full;      // [kPolStages]
+    uint64_t* empty;     // [kPolStages]
+    float* part;         // [kPolPartFloats] partial sums [group][feature][row] of the current layer
+    uint32_t* rowbits;   // [kPolRows][obs_words] the rows' packed observations
+    uint32_t* oldbits;   // [kPolRows][obs_words] the observations the first layer's accumulators (acc0) currently stand for
+    int* wcnt;           // [16] per-warp counts, [31] = U
+    uint32_t* uent;      // [policy_ent_cap] per-row lists of the observation entries that changed: index | lost << 31
+};
+// entries the lists hold: every row's list fits on its own (<= obs_size entries), typical fresh sums of all 8 rows fit together
+__host__ __device__ inline int policy_ent_cap(const PolicyDev& p) { return p.obs_size > 2048 ? p.obs_size : (8 * p.obs_size < 2048 ? 8 * p.obs_size : 2048); }
+__host__ __device__ inline size_t policy_smem_bytes(const PolicyDev& p) {
+    size_t b = ((size_t)kPolStages * kPolTileFloats + p.act0_floats + p.act1_floats + kPolPartFloats) * 4 + (2 * kPolStages + 2) * 8 +
+               (size_t)2 * kPolRows * p.obs_words * 4 + 32 * 4 + (size_t)policy_ent_cap(p) * 4;
+    return (b + 127) / 128 * 128;
+}
+__device__ __forceinline__ PolicySmem policy_smem_carve(const PolicyDev& p, float* sm) {
+    PolicySmem s;
+    s.tiles = sm;
+    s.act0 = s.tiles + kPolStages * kPolTileFloats;
+    s.act1 = s.act0 + p.act0_floats;
+    s.part = s.act1 + p.act1_floats;
+    s.full = reinterpret_cast<uint64_t*>(s.part + kPolPartFloats);
+    s.empty = s.full + kPolStages;
+    s.rowbits = reinterpret_cast<uint32_t*>(s.empty + kPolStages + 2);
+    s.oldbits = s.rowbits + kPolRows * p.obs_words;
+    s.wcnt = reinterpret_cast<int*>(s.oldbits + kPolRows * p.obs_words);
+    s.uent = reinterpret_cast<uint32_t*>(s.wcnt + 32);
+    return s;
+}
 // The first layer: h[r][j] = act(bias[j] + sum over the set observation entries k of row r of W0[j][k]), as an EXACT sum.  The weights
 // are fixed-point integers (w0q, 31 significant bits below the largest |weight|: finer than the f32 weights' own 24 bits there) and the
 // accumulators 64-bit integers, so the sum does not depend on the order of its terms.  That is what lets the one-launch search update
@@ -120,46 +154,102 @@ __device__ __forceinline__ void store_features(float* __restrict__ dst, int j, c
 // one-hot positions), so the CTA adds the weight rows of the entries that appeared and subtracts those of the entries that vanished
 // (`acc0`: its accumulators [row][feature] in global memory, L2 resident) — the same integers a fresh sum over all set entries gives,
 // bit for bit (the stand-alone kernel and the first decision do exactly that: acc0 == nullptr / fresh).  ~30 weight rows per decision
-// instead of ~200, fetched with plain coalesced loads (4 in flight per thread), no shared-memory staging.
-// uent[0..U): entry index | rows that gained it << 16 | rows that lost it << 24.  Thread t owns features t, t + 512.
-__device__ __forceinline__ void layer0_fixed(const PolicyDev& p, int U, const uint32_t* __restrict__ uent, float* __restrict__ dst, long long* __restrict__ acc0,
-                                             bool fresh, bool relu, int tid) {
-    const int out = p.width[0], ostr = p.stride[0];
+// instead of ~200, fetched with plain coalesced loads, no shared-memory staging.
+// The changed entries are found word by word (new ^ old of the packed observations, one (row, word) pair per thread) and appended to
+// per-row lists with shared-memory atomics — any order will do, the sum is exact.  ent[]: entry index | lost << 31, row r's list at
+// ent[off[r] .. off[r] + cnt[r]).  Thread t owns features t, t + 512 and keeps row r's accumulator in a register of its own.  When the
+// lists of all 8 rows do not fit `cap` entries (dense observations summed afresh), rows are processed in groups.
+__device__ __forceinline__ void layer0_fixed(const PolicyDev& p, const PolicySmem& ps, float* __restrict__ dst, long long* __restrict__ acc0, bool fresh, bool relu,
+                                             int tid) {
+    const int out = p.width[0], ostr = p.stride[0], OW = p.obs_words, NW = kPolRows * OW, cap = policy_ent_cap(p);
     const int32_t* __restrict__ wq = p.w0q;
-    for (int j = tid; j < out; j += kPolConsumers) {
-        // acc[r] carries row r's sum scaled by 2^r: the row's bit of the mask is used as it stands (value 2^r) as the multiplier of one
-        // 32 x 32 + 64-bit multiply-add, instead of being turned into 0 / 1 first; the scale comes off with an exact shift at the end
+    const uint32_t* __restrict__ rowbits = ps.rowbits; uint32_t* __restrict__ oldbits = ps.oldbits; uint32_t* __restrict__ ent = ps.uent;
+    int* const cnt = ps.wcnt; int* const fill = ps.wcnt + kPolRows;        // per-row list lengths / append cursors
+    if (tid < 2 * kPolRows) cnt[tid] = 0;
+    consumers_sync();
+    for (int i = tid; i < NW; i += kPolConsumers) {
+        const uint32_t d = rowbits[i] ^ (fresh ? 0u : oldbits[i]);
+        if (d) atomicAdd(&cnt[i / OW], __popc(d));
+    }
+    consumers_sync();
+    for (int jb = 0; jb < out; jb += kPolConsumers) {
+        const int j = jb + tid;
+        const bool mine = j < out;
         long long acc[kPolRows];
 #pragma unroll
-        for (int r = 0; r < kPolRows; ++r) acc[r] = (acc0 && !fresh) ? acc0[(size_t)r * out + j] * (1ll << r) : 0ll;
-        auto apply = [&](int w, uint32_t e) {          // e is the same in every thread of the CTA: the test of its `lost` byte is a uniform branch
-            const uint32_t gained = (e >> 16) & 0xFFu, lost = e >> 24;
+        for (int r = 0; r < kPolRows; ++r) acc[r] = (mine && acc0 && !fresh) ? acc0[(size_t)r * out + j] : 0ll;
+        for (int r0 = 0; r0 < kPolRows;) {
+            // rows [r0, r1): as many whole rows as fit the list (one row always does: cap >= obs_size)
+            int r1 = r0, tot = 0, off[kPolRows + 1];
 #pragma unroll
-            for (int r = 0; r < kPolRows; ++r) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[r]) : "r"(w), "r"((int)(gained & (1u << r))));
-            if (lost) {
-                const int nw = -w;
-#pragma unroll
-                for (int r = 0; r < kPolRows; ++r) asm("mad.wide.s32 %0, %1, %2, %0;" : "+l"(acc[r]) : "r"(nw), "r"((int)(lost & (1u << r))));
+            for (int r = 0; r < kPolRows; ++r) {
+                off[r] = tot;
+                if (r >= r0 && r == r1 && (r == r0 || tot + cnt[r] <= cap)) { tot += cnt[r]; r1 = r + 1; }
             }
-        };
-        int u = 0;
-        for (; u + 4 <= U; u += 4) {
-            uint32_t e[4]; int w[4];
+            off[kPolRows] = tot;
+            if (tot > 0) {
+                for (int i = tid; i < NW; i += kPolConsumers) {
+                    const int r = i / OW, w = i - r * OW;
+                    if (r < r0 || r >= r1) continue;
+                    const uint32_t was = fresh ? 0u : oldbits[i];
+                    uint32_t d = rowbits[i] ^ was;
+                    if (d) {
+                        int at = off[r] + atomicAdd(&fill[r], __popc(d));
+                        while (d) {
+                            const int bit = __ffs(d) - 1;
+                            d &= d - 1;
+                            ent[at++] = (uint32_t)(w * 32 + bit) | (((was >> bit) & 1u) << 31);
+                        }
+                    }
+                }
+                consumers_sync();
+                if (mine) {
+                    // position t of every row's list in one batch: up to 16 independent loads in flight per thread, so the number of
+                    // L2 round trips is half the longest list, not the sum of the lists
+                    int c[kPolRows], tmax = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { e[i] = uent[u + i]; w[i] = __ldg(wq + (size_t)(e[i] & 0xFFFFu) * ostr + j); }
+                    for (int r = 0; r < kPolRows; ++r) { c[r] = (r >= r0 && r < r1) ? cnt[r] : 0; tmax = max(tmax, c[r]); }
+                    for (int t = 0; t < tmax; t += 2) {
+                        int w[2][kPolRows];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) apply(w[i], e[i]);
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int r = 0; r < kPolRows; ++r) {
+                                w[i][r] = 0;
+                                if (t + i < c[r]) {
+                                    const uint32_t e = ent[off[r] + t + i];
+                                    const int v = __ldg(wq + (size_t)(e & 0x7FFFFFFFu) * ostr + j);
+                                    w[i][r] = (e >> 31) ? -v : v;
+                                }
+                            }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int r = 0; r < kPolRows; ++r) acc[r] += (long long)w[i][r];
+                    }
+                }
+            }
+            r0 = r1;
+            if (r0 < kPolRows || jb + kPolConsumers < out) {          // the lists are rebuilt: everybody is done reading them, cursors back to zero
+                consumers_sync();
+                if (tid < kPolRows) fill[tid] = 0;
+                consumers_sync();
+            }
         }
-        for (; u < U; ++u) { const uint32_t e = uent[u]; apply(__ldg(wq + (size_t)(e & 0xFFFFu) * ostr + j), e); }
-        float v[kPolRows];
-        const float b = __ldg(p.bias[0] + j);
+        if (mine) {
+            float v[kPolRows];
+            const float b = __ldg(p.bias[0] + j);
 #pragma unroll
-        for (int r = 0; r < kPolRows; ++r) {
-            const long long a = acc[r] >> r;                               // exact: every term is a multiple of 2^r
-            if (acc0) acc0[(size_t)r * out + j] = a;
-            v[r] = __fadd_rn(b, __fmul_rn((float)a, p.w0_scale));           // (float)int64: one rounding; the scale is a power of two
+            for (int r = 0; r < kPolRows; ++r) {
+                if (acc0) acc0[(size_t)r * out + j] = acc[r];
+                v[r] = __fadd_rn(b, __fmul_rn((float)acc[r], p.w0_scale));       // (float)int64: one rounding; the scale is a power of two
+            }
+            store_features(dst, j, v, relu);
         }
-        store_features(dst, j, v, relu);
+    }
+    if (acc0) {                                    // the accumulators now stand for these observations
+        consumers_sync();
+        for (int i = tid; i < NW; i += kPolConsumers) oldbits[i] = rowbits[i];
     }
 }
 
@@ -260,38 +350,6 @@ __device__ __forceinline__ void consume_layer_narrow(const PolicyDev& p, int l, 
     }
 }
 
-// ---- shared-memory plan of one policy CTA ---------------------------------------------------------------------------------------
-struct PolicySmem {
-    float* tiles;        // [kPolStages][kPolTileFloats] weight tiles
-    float* act0;         // [act0_floats]
-    float* act1;         // [act1_floats]
-    uint64_t* full;      // [kPolStages]
-    uint64_t* empty;     // [kPolStages]
-    float* part;         // [kPolPartFloats] partial sums [group][feature][row] of the current layer
-    uint32_t* rowbits;   // [kPolRows][obs_words] the rows' packed observations
-    uint32_t* oldbits;   // [kPolRows][obs_words] the observations the first layer's accumulators (acc0) currently stand for
-    int* wcnt;           // [16] per-warp counts, [31] = U
-    uint32_t* uent;      // [obs_size] entries that changed in any of the CTA's rows: index | gained-by rows << 16 | lost-by rows << 24
-};
-__host__ __device__ inline size_t policy_smem_bytes(const PolicyDev& p) {
-    size_t b = ((size_t)kPolStages * kPolTileFloats + p.act0_floats + p.act1_floats + kPolPartFloats) * 4 + (2 * kPolStages + 2) * 8 +
-               (size_t)2 * kPolRows * p.obs_words * 4 + 32 * 4 + (size_t)p.obs_size * 4;
-    return (b + 127) / 128 * 128;
-}
-__device__ __forceinline__ PolicySmem policy_smem_carve(const PolicyDev& p, float* sm) {
-    PolicySmem s;
-    s.tiles = sm;
-    s.act0 = s.tiles + kPolStages * kPolTileFloats;
-    s.act1 = s.act0 + p.act0_floats;
-    s.part = s.act1 + p.act1_floats;
-    s.full = reinterpret_cast<uint64_t*>(s.part + kPolPartFloats);
-    s.empty = s.full + kPolStages;
-    s.rowbits = reinterpret_cast<uint32_t*>(s.empty + kPolStages + 2);
-    s.oldbits = s.rowbits + kPolRows * p.obs_words;
-    s.wcnt = reinterpret_cast<int*>(s.oldbits + kPolRows * p.obs_words);
-    s.uent = reinterpret_cast<uint32_t*>(s.wcnt + 32);
-    return s;
-}
 __device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int tid) {
     if (tid == 0) {
         for (int s = 0; s < kPolStages; ++s) { mbar_init(ps.full + s, 1); mbar_init(ps.empty + s, kPolConsumers / 32); }
@@ -320,7 +378,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
     const bool producer = tid >= kPolConsumers;
     float* const tiles = ps.tiles; float* const act0 = ps.act0; float* const act1 = ps.act1;
     uint64_t* const full = ps.full; uint64_t* const empty = ps.empty;
-    uint32_t* const rowbits = ps.rowbits; uint32_t* const oldbits = ps.oldbits; int* const wcnt = ps.wcnt; uint32_t* const uent = ps.uent;
+    uint32_t* const rowbits = ps.rowbits;
 
     // ---- producer: the contiguous weight rows of the layers after the first, tile after tile
     if (producer) {
@@ -343,8 +401,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
         return;
     }
 
-    // ---- 1. consumers: the observation entries that changed in any of the CTA's rows since the accumulators were last brought up to
-    // date (all set entries on a fresh pass), ascending, each with the rows that gained / lost it
+    // ---- 1. consumers: the rows' packed observations into shared memory
     const bool fresh = acc0 == nullptr || pass == 0;
     if (bits) {
         for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) {
@@ -353,32 +410,6 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
             if (w == p.obs_words - 1 && (p.obs_size & 31)) word &= (1u << (p.obs_size & 31)) - 1u;
             rowbits[i] = word;
         }
-        consumers_sync();
-    }
-    int U = 0;
-    for (int base = 0; base < p.obs_size; base += kPolConsumers) {
-        const int k = base + tid;
-        uint32_t now = 0, was = 0;
-        if (k < p.obs_size) {
-#pragma unroll
-            for (int r = 0; r < kPolRows; ++r) {
-                now |= ((rowbits[r * p.obs_words + (k >> 5)] >> (k & 31)) & 1u) << r;
-                if (!fresh) was |= ((oldbits[r * p.obs_words + (k >> 5)] >> (k & 31)) & 1u) << r;
-            }
-        }
-        const uint32_t gained = now & ~was, lost = was & ~now;
-        const uint32_t vote = __ballot_sync(0xFFFFFFFFu, (gained | lost) != 0);
-        if (lane == 0) wcnt[warp] = __popc(vote);
-        consumers_sync();
-        int before = U, total = U;
-#pragma unroll
-        for (int w2 = 0; w2 < kPolConsumers / 32; ++w2) { const int c = wcnt[w2]; if (w2 < warp) before += c; total += c; }
-        if (gained | lost) uent[before + __popc(vote & ((1u << lane) - 1u))] = (uint32_t)k | (gained << 16) | (lost << 24);
-        U = total;
-        consumers_sync();
-    }
-    if (acc0) {                                    // the accumulators will stand for these observations
-        for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) oldbits[i] = rowbits[i];
     }
 
     // ---- 2. layers
@@ -387,7 +418,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
     for (int l = 0; l < p.num_layers; ++l) {
         const int ni = (p.width[l] + kPolHalf - 1) / kPolHalf;
         if (l == 0) {
-            layer0_fixed(p, U, uent, dst, acc0, fresh, p.num_layers > 1, tid);
+            layer0_fixed(p, ps, dst, acc0, fresh, p.num_layers > 1, tid);
         } else if (p.width[l] <= 64) {
             consume_layer_narrow(p, l, p.width[l - 1], src, dst, tiles, full, empty, ps.part, G, tid, lane);
         } else {
