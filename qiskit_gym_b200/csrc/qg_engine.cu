@@ -725,7 +725,7 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
     if (max_decisions < 0) { set_error("qg_search_run: negative decision budget"); return QG_ERR_INVALID; }
     if (e->B == 0 || max_decisions == 0) return QG_OK;
     CUDA_OK(cudaSetDevice(e->device));
-    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs_bits = obs_bits_dev;
+    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic;      // (no packed-observation output: the kernel keeps the bit stream on chip)
     a.nsteps = 1; a.ring = 1; a.pdl_mode = 0; a.num_sms = e->num_sms;
     a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4; a.symplectic = e->all_symplectic ? 1 : 0;
@@ -742,10 +742,10 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
         pol->acc0_ctas = ctas;
     }
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: CUDA_OK(launch_search_fused<QG_ENV_PERMUTATION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
-        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_search_fused<QG_ENV_LINEAR_FUNCTION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
-        case QG_ENV_CLIFFORD: CUDA_OK(launch_search_fused<QG_ENV_CLIFFORD>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
-        default: CUDA_OK(launch_search_fused<QG_ENV_PAULI_NETWORK>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, st)); break;
+        case QG_ENV_PERMUTATION: CUDA_OK(launch_search_fused<QG_ENV_PERMUTATION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, obs_bits_dev, st)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(launch_search_fused<QG_ENV_LINEAR_FUNCTION>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, obs_bits_dev, st)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(launch_search_fused<QG_ENV_CLIFFORD>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, obs_bits_dev, st)); break;
+        default: CUDA_OK(launch_search_fused<QG_ENV_PAULI_NETWORK>(e->dc, a, pol->d, max_decisions, decisions_dev, step_smem, pol->acc0, obs_bits_dev, st)); break;
     }
     return QG_OK;
 }

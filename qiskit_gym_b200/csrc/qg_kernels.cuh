@@ -521,9 +521,14 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
 // resident: the warp's shared-memory region still holds the tile's records from its previous call (the fused search kernel calls
 // it once per decision for the same environments): skip the load.  weights_tile: MODE_SEARCH action weights of the tile's
 // environments, [cnt][A] starting at environment e0 (may point to shared memory), or null to read a.weights[env * A].
+// fused (the one-launch search, which keeps calling for the same tile): the observation bit stream is built in shared memory even though
+// no output tensor is given, the records are not written back to global memory (tile_writeback does that once, at the end), the running
+// return is kept in ret_local[lane] (shared memory) instead of c.ret, and a resident Permutation's one-hot stream is patched (4 bits per
+// SWAP) instead of rebuilt.
 template <int KIND, int MODE, int INV>
 __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a, uint32_t* const wbase, const uint32_t* const lut, const int lane,
-                                              const int64_t e0, const int cnt, const bool resident = false, const float* const weights_tile = nullptr) {
+                                              const int64_t e0, const int cnt, const bool resident = false, const float* const weights_tile = nullptr,
+                                              const bool fused = false, float* const ret_local = nullptr) {
     typedef SmWords<kStride> Wd;
     const int64_t env = e0 + lane;
     const bool live = lane < cnt;
@@ -577,12 +582,14 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                         for (int k = 1; k < c.A; ++k) { const float v = wt[k]; if (v > best) { best = v; action = k; } }
                     } else {
                         float total = 0.0f;
+#pragma unroll 4
                         for (int k = 0; k < c.A; ++k) total = __fadd_rn(total, wt[k]);
                         const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_SAMPLE);
                         if (!(total > 0.0f)) action = (int)__umulhi(raw, (uint32_t)c.A);
                         else {
                             const float target = __fmul_rn((float)(raw >> 8) * (1.0f / 16777216.0f), total);
                             float cum = 0.0f; action = c.A - 1;
+#pragma unroll 4
                             for (int k = 0; k < c.A; ++k) { cum = __fadd_rn(cum, wt[k]); if (cum > target) { action = k; break; } }
                         }
                     }
@@ -590,6 +597,8 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 if (a.chosen) a.chosen[env] = enabled ? action : -1;
             }
 
+            int oh_q0 = -1, oh_q1 = -1;                 // Permutation, fused + resident: the SWAP this step played (one-hot stream patch)
+            bool oh_full = !(fused && resident);
             if (MODE != MODE_OBSERVE && enabled) {
                 uint32_t err = 0;
                 float penalty = 0.0f;
@@ -614,6 +623,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                     R[HD_NCNOTS] = now.nc; R[HD_NGATES] = now.ng; R[HD_LAYERS] = (now.nl & 0xFFFFu) | (now.nlc << 16);
                     if (KIND == QG_ENV_PAULI_NETWORK) pn_act(c, S, X, pr, kind, q0, q1, SCR, nh, err);
                     else apply_gate_state<KIND>(c, S, kind, q0, q1);
+                    if (KIND == QG_ENV_PERMUTATION && kind == QG_SWAP) { oh_q0 = q0; oh_q1 = q1; }
                 }
                 // solution log: Permutation only for valid actions (permutation.rs:210-216), LF/Clifford always
                 // (linear_function.rs:315-321, clifford.rs:334-340), PauliNetwork gate + harvested rotations (pauli.rs:612-627)
@@ -643,7 +653,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                     if (a.coins) coin = (MODE == MODE_STEP) ? (coin_in != 0) : (a.coins[(size_t)t * a.in_stride + env] != 0);
                     else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
                     if (coin) {
-                        if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; }
+                        if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; oh_full = true; }
                         else {
                             bool inverted;
                             if constexpr (INV == 0) inverted = invert_matrix(c, S, SCR, SCR.at(c.SW));
@@ -660,7 +670,10 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 tick += 1;
                 R[HD_REWARD] = __float_as_uint(reward);
                 dirty = true;
-                if (MODE == MODE_SEARCH) c.ret[env] = __fadd_rn(c.ret[env], reward);
+                if (MODE == MODE_SEARCH) {
+                    if (ret_local) ret_local[lane] = __fadd_rn(ret_local[lane], reward);
+                    else c.ret[env] = __fadd_rn(c.ret[env], reward);
+                }
                 if (a.reward) a.reward[(size_t)t * a.out_stride + env] = reward;
             }
             if (MODE == MODE_OBSERVE && a.reward) a.reward[env] = __uint_as_float(R[HD_REWARD]);
@@ -670,21 +683,29 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
             }
 
             // observe(): build the observation bit stream where it is not the state itself
-            if (KIND == QG_ENV_PAULI_NETWORK && enabled) {
+            // (the first fused call builds the stream of every live env, final ones included: the policy reads all of the tile's rows)
+            if (KIND == QG_ENV_PAULI_NETWORK && (enabled || (fused && !resident))) {
                 // PauliNetwork picks its qubit permutation here (pauli.rs:653-665)
-                int perm_idx = 0;
-                if (c.nperms > 0 && (a.obs || a.obs_bits)) {
+                int perm_idx = c.nperms > 0 ? (int)(pr.misc & 0xFFFFu) : 0;
+                if (c.nperms > 0 && enabled && (a.obs || a.obs_bits || fused)) {
                     const uint32_t raw = a.perm_raw ? a.perm_raw[(size_t)t * a.in_stride + env] : philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_PERM);
                     perm_idx = (int)__umulhi(raw, (uint32_t)c.nperms);
                     pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
                     dirty = true;
                 }
-                if (a.obs || a.obs_bits) pn_build_obs(c, S, pr, O, perm_idx);
+                if (a.obs || a.obs_bits || fused) pn_build_obs(c, S, pr, O, perm_idx);
             }
-            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && enabled && (a.obs || a.obs_bits)) {
+            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && (enabled || (fused && !resident)) && (a.obs || a.obs_bits || fused)) {
                 // one-hot rows: bit i*n + state[i] (permutation.rs:241-243)
-                for (int w = 0; w < c.OW; ++w) O[w] = 0;
-                for (int i = 0, b = 0; i < c.n; ++i, b += c.n) { const int bit = b + (int)get8(S, i); O[bit >> 5] |= 1u << (bit & 31); }
+                if (oh_full) {
+                    for (int w = 0; w < c.OW; ++w) O[w] = 0;
+                    for (int i = 0, b = 0; i < c.n; ++i, b += c.n) { const int bit = b + (int)get8(S, i); O[bit >> 5] |= 1u << (bit & 31); }
+                } else if (oh_q0 >= 0 && oh_q0 != oh_q1) {
+                    // O still holds the stream of before the SWAP: rows q0 and q1 exchange their set columns
+                    const int va = (int)get8(S, oh_q1), vb = (int)get8(S, oh_q0);      // the old entries of q0 / q1
+                    auto toggle = [&](int bit) { O[bit >> 5] ^= 1u << (bit & 31); };
+                    toggle(oh_q0 * c.n + va); toggle(oh_q1 * c.n + vb); toggle(oh_q0 * c.n + vb); toggle(oh_q1 * c.n + va);
+                }
             }
         }
         __syncwarp();
@@ -731,14 +752,25 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         R[HD_DEPTH] = depth; R[HD_FLAGS] = flags; R[HD_TICK] = tick;
         if (KIND == QG_ENV_PAULI_NETWORK) { X[PX_PLO] = pr.plo; X[PX_PHI] = pr.phi; X[PX_ALIVE] = pr.alive; X[PX_ORD0] = pr.ord0; X[PX_ORD1] = pr.ord1; X[PX_MISC] = pr.misc; }
         if (MODE != MODE_OBSERVE) {
-            uint32_t* dst = c.rec + (a.dst_slot ? (int64_t)a.dst_slot[env] : env);
+            if (!fused) {
+                uint32_t* dst = c.rec + (a.dst_slot ? (int64_t)a.dst_slot[env] : env);
 #pragma unroll 4
-            for (int w = 0; w < c.W; ++w, dst += c.Bpad) *dst = R[w];
+                for (int w = 0; w < c.W; ++w, dst += c.Bpad) *dst = R[w];
+            }
         } else if (KIND == QG_ENV_PAULI_NETWORK) {
             c.rec[(size_t)(c.off_extra + PX_MISC) * c.Bpad + env] = pr.misc;
         }
     }
     return last_en_bits;
+}
+
+// The records of a tile that step_tile kept in shared memory (fused calls) go back to global memory.
+__device__ __forceinline__ void tile_writeback(const DevCfg& c, const uint32_t* const wbase, const int lane, const int64_t e0, const int cnt) {
+    if (lane >= cnt) return;
+    uint32_t* dst = c.rec + e0 + lane;
+    const uint32_t* src = wbase + lane;
+#pragma unroll 4
+    for (int w = 0; w < c.W; ++w, dst += c.Bpad, src += kStride) *dst = *src;
 }
 
 // INV: register bucket of the add_inverts inverse (qg_gf2.cuh): 0 = generic shared-memory Gauss-Jordan (or no inverts),

@@ -23,6 +23,6 @@ cudaError_t prepare_step_kind(size_t smem_bytes);
 // the whole rollout search in one launch (qg_search_fused.cuh); step_smem_bytes = one warp region of the step kernel
 struct PolicyDev;
 template <int KIND>
-cudaError_t launch_search_fused(const DevCfg& c, const StepArgs& a, const PolicyDev& p, int max_decisions, int32_t* decisions_out, size_t step_smem_bytes, long long* acc0, cudaStream_t st);
+cudaError_t launch_search_fused(const DevCfg& c, const StepArgs& a, const PolicyDev& p, int max_decisions, int32_t* decisions_out, size_t step_smem_bytes, long long* acc0, const uint32_t* first_bits, cudaStream_t st);
 
 }  // namespace qg

@@ -159,17 +159,26 @@ __device__ __forceinline__ PolicySmem policy_smem_carve(const PolicyDev& p, floa
 // per-row lists with shared-memory atomics — any order will do, the sum is exact.  ent[]: entry index | lost << 31, row r's list at
 // ent[off[r] .. off[r] + cnt[r]).  Thread t owns features t, t + 512 and keeps row r's accumulator in a register of its own.  When the
 // lists of all 8 rows do not fit `cap` entries (dense observations summed afresh), rows are processed in groups.
+// stream != nullptr: the rows' packed observations are read from the step kernel's own [word][33] shared-memory bit stream (row r of the
+// CTA = environment r of the tile, rows >= stream_rows are empty) instead of ps.rowbits.
 __device__ __forceinline__ void layer0_fixed(const PolicyDev& p, const PolicySmem& ps, float* __restrict__ dst, long long* __restrict__ acc0, bool fresh, bool relu,
-                                             int tid) {
+                                             int tid, const uint32_t* __restrict__ stream = nullptr, int stream_rows = 0) {
     const int out = p.width[0], ostr = p.stride[0], OW = p.obs_words, NW = kPolRows * OW, cap = policy_ent_cap(p);
     const int32_t* __restrict__ wq = p.w0q;
     const uint32_t* __restrict__ rowbits = ps.rowbits; uint32_t* __restrict__ oldbits = ps.oldbits; uint32_t* __restrict__ ent = ps.uent;
     int* const cnt = ps.wcnt; int* const fill = ps.wcnt + kPolRows;        // per-row list lengths / append cursors
+    const uint32_t last_mask = (p.obs_size & 31) ? ((1u << (p.obs_size & 31)) - 1u) : 0xFFFFFFFFu;
+    auto now_at = [&](int i, int r, int w) -> uint32_t {
+        if (!stream) return rowbits[i];
+        const uint32_t v = r < stream_rows ? stream[w * 33 + r] : 0u;
+        return w == OW - 1 ? (v & last_mask) : v;
+    };
     if (tid < 2 * kPolRows) cnt[tid] = 0;
     consumers_sync();
     for (int i = tid; i < NW; i += kPolConsumers) {
-        const uint32_t d = rowbits[i] ^ (fresh ? 0u : oldbits[i]);
-        if (d) atomicAdd(&cnt[i / OW], __popc(d));
+        const int r = i / OW;
+        const uint32_t d = now_at(i, r, i - r * OW) ^ (fresh ? 0u : oldbits[i]);
+        if (d) atomicAdd(&cnt[r], __popc(d));
     }
     consumers_sync();
     for (int jb = 0; jb < out; jb += kPolConsumers) {
@@ -192,7 +201,7 @@ __device__ __forceinline__ void layer0_fixed(const PolicyDev& p, const PolicySme
                     const int r = i / OW, w = i - r * OW;
                     if (r < r0 || r >= r1) continue;
                     const uint32_t was = fresh ? 0u : oldbits[i];
-                    uint32_t d = rowbits[i] ^ was;
+                    uint32_t d = now_at(i, r, w) ^ was;
                     if (d) {
                         int at = off[r] + atomicAdd(&fill[r], __popc(d));
                         while (d) {
@@ -249,7 +258,7 @@ __device__ __forceinline__ void layer0_fixed(const PolicyDev& p, const PolicySme
     }
     if (acc0) {                                    // the accumulators now stand for these observations
         consumers_sync();
-        for (int i = tid; i < NW; i += kPolConsumers) oldbits[i] = rowbits[i];
+        for (int i = tid; i < NW; i += kPolConsumers) { const int r = i / OW; oldbits[i] = now_at(i, r, i - r * OW); }
     }
 }
 
@@ -365,7 +374,8 @@ __device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int t
 // `pass` counts the calls (0, 1, 2, ..).
 // `bits` may have been written earlier by this CTA in the same kernel: it is read with ld.global.cg, never through the
 // non-coherent path.
-// bits == nullptr: ps.rowbits already holds the rows' packed observations (the fused search kernel's step wrote them there).
+// bits == nullptr: the rows' packed observations are in `stream` (the step's shared-memory bit stream of the fused search kernel), or,
+// without a stream, already in ps.rowbits.
 // acc0: the CTA's first-layer accumulators [kPolRows][width[0]] (int64, global memory) when the caller evaluates the same rows again
 // and again (the one-launch search): pass 0 sums every set entry, later passes only apply what changed since the previous pass.
 // nullptr: a fresh sum, nothing kept.
@@ -373,7 +383,7 @@ __device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int t
 // row_base = row0 for the global [B][A] tensor or 0 for a CTA-private (shared-memory) buffer.
 __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const PolicySmem& ps, const uint32_t* bits, int64_t row0, int64_t B,
                                                     float* probs, float* logits_out, int& G, int pass = 0, int64_t probs_row_base = -1,
-                                                    long long* acc0 = nullptr) {
+                                                    long long* acc0 = nullptr, const uint32_t* stream = nullptr, int stream_rows = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = tid >= kPolConsumers;
     float* const tiles = ps.tiles; float* const act0 = ps.act0; float* const act1 = ps.act1;
@@ -418,7 +428,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
     for (int l = 0; l < p.num_layers; ++l) {
         const int ni = (p.width[l] + kPolHalf - 1) / kPolHalf;
         if (l == 0) {
-            layer0_fixed(p, ps, dst, acc0, fresh, p.num_layers > 1, tid);
+            layer0_fixed(p, ps, dst, acc0, fresh, p.num_layers > 1, tid, bits ? nullptr : stream, stream_rows);
         } else if (p.width[l] <= 64) {
             consume_layer_narrow(p, l, p.width[l - 1], src, dst, tiles, full, empty, ps.part, G, tid, lane);
         } else {

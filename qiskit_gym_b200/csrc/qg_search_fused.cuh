@@ -13,11 +13,15 @@
 
 namespace qg {
 
+static_assert(kStride == 33, "layer0_fixed (qg_policy_kernels.cuh) reads the step's bit stream with a word stride of 33");
+
 template <int KIND>
 __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a, const __grid_constant__ PolicyDev p,
-                                                               int max_decisions, int32_t* __restrict__ decisions_out, long long* __restrict__ acc0_all) {
+                                                               int max_decisions, int32_t* __restrict__ decisions_out, long long* __restrict__ acc0_all,
+                                                               const uint32_t* __restrict__ first_bits) {
     extern __shared__ __align__(128) float smf[];
     __shared__ uint32_t s_active;
+    __shared__ float s_ret[kPolRows];              // running returns of the CTA's rollouts (Env::reward summed in step order)
     const PolicySmem ps = policy_smem_carve(p, smf);
     uint32_t* const wbase = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(smf) + policy_smem_bytes(p));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -28,38 +32,36 @@ __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_const
     const uint32_t* const obs_stream = wbase + (obs_from_O ? a.sm_obs : c.off_state * kStride);   // the step's [word][env] observation bit stream
     long long* const acc0 = acc0_all + (size_t)blockIdx.x * kPolRows * p.width[0];     // this CTA's first-layer accumulators
     policy_init_barriers(ps, tid);
+    if (tid < kPolRows) s_ret[tid] = tid < cnt ? c.ret[row0 + tid] : 0.0f;
     __syncthreads();
     int G = 0, it = 0;
     for (; it < max_decisions; ++it) {
-        // decision `it`: the first one reads the packed observations qg_observe_bits left in global memory, the later ones find them
-        // in ps.rowbits; the action weights stay in shared memory; the env records stay in the step's shared-memory region
-        policy_forward_rows(p, ps, it == 0 ? a.obs_bits : nullptr, row0, c.B, s_probs, nullptr, G, it, 0, acc0);
+        // decision `it`: the first one reads the packed observations qg_observe_bits left in global memory, the later ones read the
+        // step's own bit stream in shared memory; the action weights stay in shared memory; the env records stay in the step's region
+        policy_forward_rows(p, ps, it == 0 ? first_bits : nullptr, row0, c.B, s_probs, nullptr, G, it, 0, acc0, obs_stream, cnt);
         __syncthreads();
         if (warp == 0) {
-            const uint32_t en = step_tile<KIND, MODE_SEARCH, 0>(c, a, wbase, nullptr, lane, row0, cnt, it > 0, s_probs);
-            const int OWp = p.obs_words;
-            for (int i = lane; i < kPolRows * OWp; i += 32) {
-                const int r = i / OWp, w = i - r * OWp;
-                uint32_t word = r < cnt ? obs_stream[w * kStride + r] : 0u;
-                if (w == OWp - 1 && (p.obs_size & 31)) word &= (1u << (p.obs_size & 31)) - 1u;
-                ps.rowbits[i] = word;
-            }
+            const uint32_t en = step_tile<KIND, MODE_SEARCH, 0>(c, a, wbase, nullptr, lane, row0, cnt, it > 0, s_probs, true, s_ret);
             if (lane == 0) s_active = en;
         }
-        __syncthreads();                           // next packed observations in ps.rowbits, s_active set
+        __syncthreads();                           // next observations in the step's stream, s_active set
         if (s_active == 0) break;                  // every rollout of this CTA is final
+    }
+    if (warp == 0) {                               // what stayed in shared memory during the search goes back: records, returns
+        tile_writeback(c, wbase, lane, row0, cnt);
+        if (lane < cnt) c.ret[row0 + lane] = s_ret[lane];
     }
     if (tid == 0 && decisions_out) decisions_out[blockIdx.x] = min(it + 1, max_decisions);
 }
 
 template <int KIND>
 cudaError_t launch_search_fused(const DevCfg& c, const StepArgs& a, const PolicyDev& p, int max_decisions, int32_t* decisions_out, size_t step_smem_bytes, long long* acc0,
-                                cudaStream_t st) {
+                                const uint32_t* first_bits, cudaStream_t st) {
     const size_t smem = policy_smem_bytes(p) + step_smem_bytes + (size_t)kPolRows * p.width[p.num_layers - 1] * 4;
     cudaError_t e = cudaFuncSetAttribute(k_search_fused<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((c.B + kPolRows - 1) / kPolRows);
-    k_search_fused<KIND><<<grid, kPolThreads, smem, st>>>(c, a, p, max_decisions, decisions_out, acc0);
+    k_search_fused<KIND><<<grid, kPolThreads, smem, st>>>(c, a, p, max_decisions, decisions_out, acc0, first_bits);
     return cudaGetLastError();
 }
 
