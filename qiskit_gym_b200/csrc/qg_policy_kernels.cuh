@@ -318,6 +318,68 @@ __device__ __forceinline__ void consume_layer(const PolicyDev& p, int l, int K, 
     }
 }
 
+// A layer of 65..256 output features (the BasicPolicy's second layer): one feature per thread would leave the loop bound by its
+// shared-memory loads (two 16-byte activation broadcasts + one weight per 4 FFMA2), so a thread owns TWO adjacent features (one 8-byte
+// weight load, 3 loads per 8 FFMA2) and the inputs are split over four groups of 128 threads (group g takes u = g, g + 4, .. of every
+// tile); groups 1..3 hand their partial sums to group 0 through shared memory, which adds them in group order.
+__device__ __forceinline__ void consume_layer_pairs(const PolicyDev& p, int l, int K, const float* __restrict__ src, float* __restrict__ dst, const float* tiles,
+                                                    uint64_t* full, uint64_t* empty, float* part, int& G, int tid, int lane) {
+    constexpr int kGroups = 4, kGroupThreads = kPolConsumers / kGroups;       // 4 x 128
+    const int out = p.width[l], ostr = p.stride[l], kt = tile_rows(p, l), nt = (K + kt - 1) / kt;
+    const int grp = tid / kGroupThreads, gt = tid - grp * kGroupThreads;
+    const int j0 = 2 * gt, jc = min(j0, ostr - 2);                             // out-of-range pairs read valid words and are never written
+    float acc[2][kPolRows];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float b = (grp == 0 && j0 + i < out) ? __ldg(p.bias[l] + j0 + i) : 0.0f;
+#pragma unroll
+        for (int r = 0; r < kPolRows; ++r) acc[i][r] = b;
+    }
+    const bool active = (j0 & ~63) < out;                                      // warp-uniform: this warp owns at least one real feature
+    for (int t = 0; t < nt; ++t, ++G) {
+        const int stage = G % kPolStages;
+        mbar_wait(full + stage, (uint32_t)((G / kPolStages) & 1));
+        if (active) {
+            const int k0 = t * kt, rows = min(kt, K - k0);
+            const float* __restrict__ tile = tiles + (size_t)stage * kPolTileFloats;
+            const float4* __restrict__ h = reinterpret_cast<const float4*>(src + (size_t)k0 * kPolRows);
+#pragma unroll 4
+            for (int u = grp; u < rows; u += kGroups) {
+                const float4 h0 = h[2 * u], h1 = h[2 * u + 1];
+                const float2 w = *reinterpret_cast<const float2*>(tile + u * ostr + jc);
+                ffma2_bcast(acc[0][0], acc[0][1], w.x, h0.x, h0.y); ffma2_bcast(acc[0][2], acc[0][3], w.x, h0.z, h0.w);
+                ffma2_bcast(acc[0][4], acc[0][5], w.x, h1.x, h1.y); ffma2_bcast(acc[0][6], acc[0][7], w.x, h1.z, h1.w);
+                ffma2_bcast(acc[1][0], acc[1][1], w.y, h0.x, h0.y); ffma2_bcast(acc[1][2], acc[1][3], w.y, h0.z, h0.w);
+                ffma2_bcast(acc[1][4], acc[1][5], w.y, h1.x, h1.y); ffma2_bcast(acc[1][6], acc[1][7], w.y, h1.z, h1.w);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+    }
+    // part: [group - 1][256 features][8 rows]
+    if (grp > 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) if (j0 + i < out) store_features(part + (size_t)(grp - 1) * 256 * kPolRows, j0 + i, acc[i], false);
+    }
+    consumers_sync();
+    if (grp == 0) {
+        const bool last = l == p.num_layers - 1;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int j = j0 + i;
+            if (j < out) {
+#pragma unroll
+                for (int g = 0; g < kGroups - 1; ++g) {
+                    const float4 lo = reinterpret_cast<const float4*>(part + ((size_t)g * 256 + j) * kPolRows)[0], hi = reinterpret_cast<const float4*>(part + ((size_t)g * 256 + j) * kPolRows)[1];
+                    acc[i][0] += lo.x; acc[i][1] += lo.y; acc[i][2] += lo.z; acc[i][3] += lo.w;
+                    acc[i][4] += hi.x; acc[i][5] += hi.y; acc[i][6] += hi.z; acc[i][7] += hi.w;
+                }
+                store_features(dst, j, acc[i], !last);
+            }
+        }
+    }
+}
+
 // A narrow layer (at most 64 output features, e.g. the action head): with one feature per thread only two warps would work and the
 // layer would be a latency-bound chain over its K inputs, so the inputs are split over the 16 warps instead (warp w takes the rows
 // u = w, w+16, .. of every tile; lane j owns features j and j+32), the partial sums are combined through shared memory in warp
@@ -431,6 +493,8 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
             layer0_fixed(p, ps, dst, acc0, fresh, p.num_layers > 1, tid, bits ? nullptr : stream, stream_rows);
         } else if (p.width[l] <= 64) {
             consume_layer_narrow(p, l, p.width[l - 1], src, dst, tiles, full, empty, ps.part, G, tid, lane);
+        } else if (p.width[l] <= 256) {
+            consume_layer_pairs(p, l, p.width[l - 1], src, dst, tiles, full, empty, ps.part, G, tid, lane);
         } else {
             const int K = p.width[l - 1];
             switch (ni) {
