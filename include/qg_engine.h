@@ -254,7 +254,11 @@ QG_API int qg_search_step_bits(qg_engine* e, const float* weights_dev, int32_t d
  * action head) evaluated from packed observations in one kernel: first layer = bias + sum of the weight columns of the
  * set bits, then the Linear/ReLU chain and a softmax.  Layer l has out_features[l] outputs and consumes the
  * observation (l = 0) or layer l-1; weights_host[l] is torch's Linear.weight layout [out][in] row-major, f32; ReLU
- * follows every layer but the last.  Limits: 1..8 layers, widths <= 1024. */
+ * follows every layer but the last.  Limits: 1..8 layers, widths <= 1024.
+ * Arithmetic: the first layer's input is 0/1, so it is a sum of weight rows; it is computed EXACTLY: the weights are converted once to
+ * fixed point (int32, the largest |weight| just below 2^30) and summed in 64-bit integers, then scaled back and biased in f32.  The sum
+ * is therefore independent of the order of its terms, which lets qg_search_run update it from the observation entries that changed
+ * instead of recomputing it, with bit-identical results.  The other layers are f32 FMA chains over ascending input index. */
 QG_API int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features,
                             const float* const* weights_host, const float* const* biases_host, qg_policy** out);
 QG_API void qg_policy_destroy(qg_policy* p);
@@ -267,8 +271,10 @@ QG_API int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, in
  * sample / arg-max + fused step -> next packed observation  until its rollouts are final or max_decisions decisions were taken;
  * equivalent to max_decisions rounds of qg_policy_forward_bits + qg_search_step_bits (same bits), without launch gaps or host
  * round trips.  Call qg_set_state (broadcast), qg_search_begin and qg_observe_bits first; obs_bits_dev uint32[B][qg_obs_words]
- * and weights_dev float[B][num_actions] are the working buffers; decisions_dev int32[ceil(B/8)] (or NULL) receives the number of
- * decisions each CTA took.  Then qg_search_best / qg_solution_host as usual. */
+ * holds the initial packed observations (read only: during the search the records, the returns and the observation bits stay on chip
+ * and only the final records / returns are written back), weights_dev float[B][num_actions] is reserved; decisions_dev
+ * int32[ceil(B/8)] (or NULL) receives the number of decisions each CTA took.  Then qg_search_best / qg_solution_host as usual.
+ * Grows a per-policy scratch buffer (8 x width[0] int64 per CTA) on first use with a larger batch: one host thread per policy handle. */
 QG_API int qg_search_run(qg_engine* e, qg_policy* policy, int32_t deterministic, int32_t max_decisions, uint32_t* obs_bits_dev,
                          float* weights_dev, int32_t* decisions_dev, qg_stream stream);
 
