@@ -463,8 +463,10 @@ int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)e->B;
     if (!e->rp_in) {
-        // chunk: about 4 MB of actions per upload, at least 1 and at most 32 steps
-        e->rp_chunk = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(4 << 20) / std::max<int64_t>((int64_t)B * 4, 1)));
+        // chunk: about 1 MB of actions per upload, at least 1 and at most 32 steps (the first upload and the last download are not
+        // overlapped with compute; measured at 65 536 envs: chunks of 16 / 8 / 4 / 2 steps -> 4.35 / 4.45 / 4.51 / 3.67 x 10^9 env-steps/s)
+        e->rp_chunk = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(1 << 20) / std::max<int64_t>((int64_t)B * 4, 1)));
+        if (const char* v = std::getenv("QG_REPLAY_CHUNK")) e->rp_chunk = std::max(1, std::atoi(v));      // A/B runs
         CUDA_OK(cudaStreamCreateWithFlags(&e->rp_in, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&e->rp_out, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&e->rp_ev_start, cudaEventDisableTiming));
