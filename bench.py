@@ -382,7 +382,7 @@ def run_ours(args):
                        "f32 reward + u8 done + u8 success [T][B] D2H, copies pipelined with compute, call returns after the last byte arrived",
                "steps": Ke,
                "per_step_sync": {"value": world * B * T * Ks / (ems_ps * 1e-3), "unit": UNIT, "steps": Ks,
-                                 "note": "qg_step_host: one synchronous H2D + launch + D2H round trip per env-step (host-side collector)"}}
+                                 "note": "qg_step_host: one synchronous call per env-step with pinned host buffers (host-side collector): the kernel reads the actions and writes reward / done / success over PCIe itself (zero copy), one launch + one stream synchronisation per env-step"}}
 
     synth = None if args.no_synth else run_synth(args, dev, local, rank, world)
     collector = None if args.no_collector else run_collector(args, dev, local, rank, world)

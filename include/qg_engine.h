@@ -176,9 +176,11 @@ QG_API int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev
 QG_API int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host, const uint8_t* coins_host,
                           float* obs_dev, uint8_t* mask_dev, int32_t ring,
                           float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream);
-/* Same step with HOST buffers (pinned or pageable): copies actions (and coins) in, runs the step
- * writing obs/mask to the given DEVICE tensors (may be NULL), copies reward/done/success out and
- * synchronises.  This is the end-to-end call a host-side collector makes. */
+/* Same step with HOST buffers (pinned or pageable): actions (and coins) go in, the step runs
+ * writing obs/mask to the given DEVICE tensors (may be NULL), reward/done/success come out and the
+ * stream is synchronised.  This is the end-to-end call a host-side collector makes.  With pinned
+ * (page-locked) buffers the kernel accesses the host memory itself over PCIe (one launch, no
+ * staging copies); pageable buffers are staged through device buffers. */
 QG_API int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins_host,
                         float* obs_dev, uint8_t* mask_dev,
                         float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream);

@@ -514,6 +514,24 @@ int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins
     CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)e->B;
+    // Pinned host buffers are mapped into the device's address space (unified addressing): the kernel then reads the actions and writes
+    // reward / done / success over PCIe itself, and the call is one launch + one synchronisation instead of up to five copies around it.
+    auto mapped = [](const void* h) -> void* {
+        if (!h) return nullptr;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    };
+    void* const m_act = mapped(actions_host); void* const m_coin = mapped(coins_host);
+    void* const m_rew = mapped(reward_host); void* const m_done = mapped(done_host); void* const m_suc = mapped(success_host);
+    if (m_act && (!coins_host || m_coin) && (!reward_host || m_rew) && (!done_host || m_done) && (!success_host || m_suc)) {
+        StepArgs a{}; a.actions = (const int32_t*)m_act; a.coins = (const uint8_t*)m_coin; a.obs = obs_dev; a.mask = mask_dev;
+        a.reward = (float*)m_rew; a.done = (uint8_t*)m_done; a.success = (uint8_t*)m_suc;
+        const int rc = launch_step(e, MODE_STEP, a, st);
+        if (rc != QG_OK) return rc;
+        CUDA_OK(cudaStreamSynchronize(st));
+        return QG_OK;
+    }
     CUDA_OK(cudaMemcpyAsync(e->io_actions, actions_host, B * 4, cudaMemcpyHostToDevice, st));
     if (coins_host) CUDA_OK(cudaMemcpyAsync(e->io_coins, coins_host, B, cudaMemcpyHostToDevice, st));
     StepArgs a{}; a.actions = e->io_actions; a.coins = coins_host ? e->io_coins : nullptr; a.obs = obs_dev; a.mask = mask_dev;

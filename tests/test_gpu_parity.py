@@ -193,6 +193,36 @@ def test_replay_host_pipeline(name, B, T, inv):
     assert np.array_equal(r2.view(np.uint32), ref["reward"].view(np.uint32))
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_pinned_and_pageable(pinned):
+    """qg_step_host: with pinned buffers the kernel reads / writes host memory itself (zero copy), with pageable ones the call stages
+    copies; both must deliver what the oracle's steps do."""
+    from qiskit_gym_b200 import BatchedEnv
+
+    kind, n, gateset, kw = H.config_table()["C3_clifford8_full"]
+    B, T = 777, 12
+    rng = np.random.Generator(np.random.PCG64(31))
+    cfg = H.make_cfg(kind, n, gateset, add_inverts=True, add_perms=False)
+    tarr = H.random_targets(kind, n, gateset, B, 31, scramble=20)
+    actions = H.random_actions(rng, T, B, len(gateset), 0.02)
+    coins = rng.integers(0, 2, size=(T, B)).astype(np.uint8)
+    ref = orc.run_batch(cfg, tarr, H.payload_lengths(kind, n, tarr), actions, coins=coins)
+    env = BatchedEnv(kind, n, gateset, B, add_inverts=True, add_perms=False)
+    env.set_state(tarr)
+
+    def buf(shape, dt):
+        t = torch.zeros(shape, dtype=dt)
+        return (t.pin_memory() if pinned else t).numpy()
+    a_h, c_h = buf((T, B), torch.int32), buf((T, B), torch.uint8)
+    a_h[:] = actions; c_h[:] = coins
+    rew, don, suc = buf((B,), torch.float32), buf((B,), torch.uint8), buf((B,), torch.uint8)
+    for t in range(T):
+        env.step_host(a_h[t], rew, don, suc, coins=c_h[t], obs=env.obs)
+        assert np.array_equal(rew.view(np.uint32), ref["reward"][t].view(np.uint32)), f"reward bits differ at step {t}"
+        assert np.array_equal(don, ref["done"][t]) and np.array_equal(suc, ref["success"][t])
+        assert np.array_equal(env.obs.reshape(B, -1).cpu().numpy().astype(np.uint8), ref["obs"][t])
+
+
 @pytest.mark.parametrize("name", ["clifford20_line", "lf40_line"])
 def test_step_parity_wide_rows(name):
     run_parity(name, B=70, T=24, add_inverts=True, seed=5)
