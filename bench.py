@@ -378,8 +378,9 @@ def run_ours(args):
         ems_ps = host_timed(episode_host_per_step, Ks)
         e2e = {"value": world * B * T * Ke / (ems * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": T * B * (4 + (1 if c_np is not None else 0)), "d2h_bytes_per_step": T * B * 6,
-               "note": "qg_replay_host: int32 actions [T][B] pinned H2D, chunked fused launches (obs+mask stay on device for the policy), "
-                       "f32 reward + u8 done + u8 success [T][B] D2H, copies pipelined with compute, call returns after the last byte arrived",
+               "note": "qg_replay_host with pinned host buffers: int32 actions [T][B] are read by the kernel from host memory over PCIe (one step ahead), "
+                       "f32 reward + u8 done + u8 success [T][B] are written by the kernel to host memory, one launch per episode (obs+mask stay on "
+                       "the device for the policy); the call returns after the stream is synchronised, i.e. when every byte has arrived",
                "steps": Ke,
                "per_step_sync": {"value": world * B * T * Ks / (ems_ps * 1e-3), "unit": UNIT, "steps": Ks,
                                  "note": "qg_step_host: one synchronous call per env-step with pinned host buffers (host-side collector): the kernel reads the actions and writes reward / done / success over PCIe itself (zero copy), one launch + one stream synchronisation per env-step"}}

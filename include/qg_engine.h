@@ -170,9 +170,10 @@ QG_API int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev
                      float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
 /* qg_replay with HOST buffers (pinned recommended): actions_host int32[num_steps][B] (coins_host uint8[num_steps][B] or
  * NULL) go up, reward_host float[num_steps][B] / done_host / success_host uint8[num_steps][B] (each may be NULL) come back;
- * observations / masks stay in the device ring for the policy.  Chunks of steps are pipelined over a copy-in stream, the
- * caller's stream (one fused launch per chunk) and a copy-out stream; the call returns when everything has arrived.
- * Allocates its staging buffers on first use. */
+ * observations / masks stay in the device ring for the policy.  With pinned (page-locked) buffers the whole episode is ONE launch
+ * whose kernel reads / writes the host memory itself over PCIe; with pageable buffers chunks of steps are pipelined over a copy-in
+ * stream, the caller's stream (one fused launch per chunk) and a copy-out stream (staging buffers allocated on first use).  The call
+ * returns when everything has arrived. */
 QG_API int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host, const uint8_t* coins_host,
                           float* obs_dev, uint8_t* mask_dev, int32_t ring,
                           float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream);
