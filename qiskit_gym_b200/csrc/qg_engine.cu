@@ -454,6 +454,15 @@ int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const
 // Episode replay with HOST buffers, pipelined in chunks of steps over three streams: the copy-in stream uploads the
 // actions of chunk c+1 while the caller's stream replays chunk c (one fused launch per chunk) and the copy-out
 // stream downloads the rewards / flags of chunk c-1.
+// The device-side address of a pinned (page-locked) host buffer — under unified addressing such memory is mapped into the device's address
+// space, so a kernel can read / write it over PCIe — or nullptr for pageable memory.
+static void* mapped_host(const void* h) {
+    if (!h) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
                    int32_t ring, float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream) {
     if (!e || !actions_host) { set_error("null argument"); return QG_ERR_INVALID; }
@@ -468,14 +477,8 @@ int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host,
         // done / success over PCIe itself (see qg_step_host); no staging copies, no chunk boundaries.  Measured at 65 536 envs:
         // 5.20 x 10^9 env-steps/s against 4.49 x 10^9 for the chunked copy pipeline below (and 5.09 x 10^9 device resident: the three
         // small output streams leave over PCIe instead of taking HBM bandwidth)
-        auto mapped = [](const void* h) -> void* {
-            if (!h) return nullptr;
-            cudaPointerAttributes at{};
-            if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-            return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
-        };
-        void* const m_act = mapped(actions_host); void* const m_coin = mapped(coins_host);
-        void* const m_rew = mapped(reward_host); void* const m_done = mapped(done_host); void* const m_suc = mapped(success_host);
+        void* const m_act = mapped_host(actions_host); void* const m_coin = mapped_host(coins_host);
+        void* const m_rew = mapped_host(reward_host); void* const m_done = mapped_host(done_host); void* const m_suc = mapped_host(success_host);
         if (m_act && (!coins_host || m_coin) && (!reward_host || m_rew) && (!done_host || m_done) && (!success_host || m_suc)) {
             StepArgs a{}; a.actions = (const int32_t*)m_act; a.coins = (const uint8_t*)m_coin; a.obs = obs_dev; a.mask = mask_dev;
             a.reward = (float*)m_rew; a.done = (uint8_t*)m_done; a.success = (uint8_t*)m_suc;
@@ -540,14 +543,8 @@ int qg_step_host(qg_engine* e, const int32_t* actions_host, const uint8_t* coins
     const size_t B = (size_t)e->B;
     // Pinned host buffers are mapped into the device's address space (unified addressing): the kernel then reads the actions and writes
     // reward / done / success over PCIe itself, and the call is one launch + one synchronisation instead of up to five copies around it.
-    auto mapped = [](const void* h) -> void* {
-        if (!h) return nullptr;
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
-    };
-    void* const m_act = mapped(actions_host); void* const m_coin = mapped(coins_host);
-    void* const m_rew = mapped(reward_host); void* const m_done = mapped(done_host); void* const m_suc = mapped(success_host);
+    void* const m_act = mapped_host(actions_host); void* const m_coin = mapped_host(coins_host);
+    void* const m_rew = mapped_host(reward_host); void* const m_done = mapped_host(done_host); void* const m_suc = mapped_host(success_host);
     if (m_act && (!coins_host || m_coin) && (!reward_host || m_rew) && (!done_host || m_done) && (!success_host || m_suc)) {
         StepArgs a{}; a.actions = (const int32_t*)m_act; a.coins = (const uint8_t*)m_coin; a.obs = obs_dev; a.mask = mask_dev;
         a.reward = (float*)m_rew; a.done = (uint8_t*)m_done; a.success = (uint8_t*)m_suc;
