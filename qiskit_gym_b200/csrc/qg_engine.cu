@@ -39,6 +39,7 @@ struct qg_engine {
     int nperms = 0;
     int pdl_mode = 2;                // QG_PDL=0|1|2 in the environment: programmatic dependent launch variants (see StepArgs)
     int stagger_ns = 0, num_sms = 148;
+    size_t l2_persist_bytes = 0;
     bool all_symplectic = true;      // Clifford: every state loaded so far is symplectic (identity at construction, resets, checked set_state payloads)
     bool inv_bucket_enabled = true;  // QG_INV_REG=0 in the environment forces the generic shared-memory Gauss-Jordan (A/B runs)
     // qg_replay_host pipeline (allocated on first use): two chunk buffers, copy-in / copy-out streams
@@ -123,6 +124,10 @@ int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t log
     DevCfg dc = e->dc;
     dc.B = LB;
     LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), e->smem_bytes, a.pdl_mode ? 1 : 0};
+    if (e->l2_persist_bytes > 0 && mode == MODE_STEP && a.nsteps > 1 && a.actions) {
+        // replay: keep the resident action stream in L2 (persisting window) so that the launch's DRAM traffic is writes only
+        g.l2_base = a.actions; g.l2_bytes = std::min<size_t>((size_t)a.nsteps * (size_t)a.in_stride * 4, e->l2_persist_bytes);
+    }
     // register bucket of the add_inverts inverse (qg_gf2.cuh); 0 = generic shared-memory path (dimension > 32, or no inverts)
     int inv = 0;
     if (e->dc.add_inverts && e->inv_bucket_enabled && (e->L.kind == QG_ENV_LINEAR_FUNCTION || e->L.kind == QG_ENV_CLIFFORD))
@@ -250,6 +255,14 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     e->L = L; e->device = device; e->B = batch; e->Bpad = align_up(std::max<int64_t>(batch, 1), 32);
     e->nperms = (int)tw.act_perms.size();
     if (const char* v = std::getenv("QG_PDL")) e->pdl_mode = std::atoi(v);
+    if (const char* v = std::getenv("QG_L2_PERSIST_MB")) {                 // A/B runs: persisting-L2 window over the replay's action stream
+        int mx = 0, win = 0;
+        cudaDeviceGetAttribute(&mx, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t want = (size_t)std::atoi(v) << 20;
+        e->l2_persist_bytes = std::min({want, (size_t)mx, (size_t)win});
+        if (e->l2_persist_bytes > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, e->l2_persist_bytes);
+    }
     if (const char* v = std::getenv("QG_INV_REG")) e->inv_bucket_enabled = std::atoi(v) != 0;
     if (const char* v = std::getenv("QG_INV_SYMPLECTIC")) e->all_symplectic = std::atoi(v) != 0;   // 0: never use the transpose shortcut
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
@@ -451,9 +464,6 @@ int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const
     return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
 }
 
-// Episode replay with HOST buffers, pipelined in chunks of steps over three streams: the copy-in stream uploads the
-// actions of chunk c+1 while the caller's stream replays chunk c (one fused launch per chunk) and the copy-out
-// stream downloads the rewards / flags of chunk c-1.
 // The device-side address of a pinned (page-locked) host buffer — under unified addressing such memory is mapped into the device's address
 // space, so a kernel can read / write it over PCIe — or nullptr for pageable memory.
 static void* mapped_host(const void* h) {
@@ -463,6 +473,9 @@ static void* mapped_host(const void* h) {
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
+// Episode replay with HOST buffers.  Pinned buffers: one launch, the kernel accesses them itself.  Pageable buffers: pipelined in chunks
+// of steps over three streams: the copy-in stream uploads the actions of chunk c+1 while the caller's stream replays chunk c (one
+// fused launch per chunk) and the copy-out stream downloads the rewards / flags of chunk c-1.
 int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
                    int32_t ring, float* reward_host, uint8_t* done_host, uint8_t* success_host, qg_stream stream) {
     if (!e || !actions_host) { set_error("null argument"); return QG_ERR_INVALID; }

@@ -329,9 +329,35 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
 // store flavour of the observation / mask slabs (compile-time switch for A/B runs): 0 = st.global.cs (streaming, evict first),
-// 1 = plain st.global, 2 = st.global.wt
+// 1 = plain st.global, 2 = st.global.wt, 3 / 4 = L2 cache hint evict_last / evict_unchanged
+// Measured (replay, 65 536 envs, profiles/r1_v22_store_policy.txt): plain stores are 2.4 % faster than .cs on C3 (also at 1 M envs) and
+// 1.3 % on C4, 0.7-0.9 % slower on C1 / C5; evict_unchanged equals plain, evict_last is 4 % slower.  A persisting-L2 window over the
+// action stream is much worse (40 MB set aside: -20 %): the write stream lives off the L2 capacity it can buffer in.
 #ifndef QG_STORE
-#define QG_STORE 0
+#define QG_STORE 1
+#endif
+#if QG_STORE == 3 || QG_STORE == 4
+__device__ __forceinline__ unsigned long long l2_policy() {
+    unsigned long long pol;
+#if QG_STORE == 3
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#else
+    asm("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+__device__ __forceinline__ void st_hint(float4* p, const float4& v) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(l2_policy()) : "memory");
+}
+__device__ __forceinline__ void st_hint(uint4* p, const uint4& v) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(l2_policy()) : "memory");
+}
+#endif
+// the action / coin streams are read once; evict-first loads (QG_LDCS) were measured: no change (1.620 vs 1.621 ms)
+#ifdef QG_LDCS
+#define QG_LD_STREAM(p) __ldcs(p)
+#else
+#define QG_LD_STREAM(p) (*(p))
 #endif
 template <class V>
 __device__ __forceinline__ void st_slab(V* p, const V& v) {
@@ -339,8 +365,10 @@ __device__ __forceinline__ void st_slab(V* p, const V& v) {
     __stcs(p, v);
 #elif QG_STORE == 1
     *p = v;
-#else
+#elif QG_STORE == 2
     __stwt(p, v);
+#else
+    st_hint(p, v);
 #endif
 }
 __device__ __forceinline__ float4 nibble_to_float4(uint32_t nib) {
@@ -556,8 +584,8 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
     // replay: the next step's action (and coin) is requested before this step's expansion, so its DRAM latency is hidden
     int next_action = -1; uint32_t next_coin = 0;
     if (MODE == MODE_STEP && live) {
-        next_action = a.actions[env];
-        if (a.coins) next_coin = a.coins[env];
+        next_action = QG_LD_STREAM(a.actions + env);
+        if (a.coins) next_coin = QG_LD_STREAM(a.coins + env);
     }
     for (int t = 0; t < a.nsteps; ++t) {
         bool success = (flags & FL_SUCCESS) != 0, enabled = live;
@@ -568,8 +596,8 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 action = next_action;
                 if (a.skip_negative && action < 0) enabled = false;
                 if (t + 1 < a.nsteps) {
-                    next_action = a.actions[(size_t)(t + 1) * a.in_stride + env];
-                    if (a.coins) next_coin = a.coins[(size_t)(t + 1) * a.in_stride + env];
+                    next_action = QG_LD_STREAM(a.actions + (size_t)(t + 1) * a.in_stride + env);
+                    if (a.coins) next_coin = QG_LD_STREAM(a.coins + (size_t)(t + 1) * a.in_stride + env);
                 }
             }
             if (MODE == MODE_SEARCH) {

@@ -11,6 +11,8 @@ struct LaunchGeom {
     unsigned grid;
     size_t smem_bytes;
     int pdl;            // launch with the programmatic-stream-serialization attribute
+    const void* l2_base = nullptr;   // persisting-L2 access window (bytes 0 = none)
+    size_t l2_bytes = 0;
 };
 
 // mode: MODE_STEP / MODE_OBSERVE / MODE_SEARCH;  inv: 0 / 8 / 16 / 32 (see k_step)

@@ -13,9 +13,19 @@ cudaError_t launch_one(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, 
     // waits (griddepcontrol.wait) before it touches the records
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(g.grid); lc.blockDim = dim3(kWarpsPerCta * 32); lc.dynamicSmemBytes = g.smem_bytes; lc.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = at; lc.numAttrs = g.pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (g.pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    if (g.l2_bytes > 0) {
+        at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(g.l2_base);
+        at[na].val.accessPolicyWindow.num_bytes = g.l2_bytes;
+        at[na].val.accessPolicyWindow.hitRatio = 1.0f;
+        at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++na;
+    }
+    lc.attrs = at; lc.numAttrs = na;
     return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV>, c, a);
 }
 
