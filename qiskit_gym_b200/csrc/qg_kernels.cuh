@@ -359,12 +359,14 @@ __device__ __forceinline__ void st_hint(uint4* p, const uint4& v) {
 #else
 #define QG_LD_STREAM(p) (*(p))
 #endif
+// cs (warp uniform): streaming (evict-first) stores.  A replay launch (many steps per launch) is 2.4 % faster with plain stores, a
+// single-step launch 2 % faster with .cs (profiles/r1_v22_store_policy.txt, r1_v23_bench_n1.json): the launch picks (nsteps == 1).
 template <class V>
-__device__ __forceinline__ void st_slab(V* p, const V& v) {
+__device__ __forceinline__ void st_slab(V* p, const V& v, bool cs) {
 #if QG_STORE == 0
-    __stcs(p, v);
+    __stcs(p, v, cs);
 #elif QG_STORE == 1
-    *p = v;
+    if (cs) __stcs(p, v); else *p = v;
 #elif QG_STORE == 2
     __stwt(p, v);
 #else
@@ -403,7 +405,7 @@ __device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t
 // so the loop has no division; the four floats come from the shared-memory table with one 128-bit load.
 template <int MODE>
 __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t* lut, float* out, uint32_t cnt, uint32_t obs, uint32_t en_bits, int lane,
-                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs, uint32_t q4, uint32_t r4) {
+                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs, uint32_t q4, uint32_t r4, bool cs) {
     // 16-byte stores need an aligned slab: always true for the engine's own [B][obs] tensors; a ring slot of an odd-sized
     // batch may start off the grid, then everything goes through the scalar tail loop
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
@@ -423,14 +425,14 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
             for (uint32_t e = 0; e < cnt; ++e, o += 64) {
                 if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
                 const uint32_t w0 = src[e], w1 = src[4 * kStride + e];
-                st_slab(o, lut_get(lut_lane, (w0 >> sh) & 15u));
-                st_slab(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u));
+                st_slab(o, lut_get(lut_lane, (w0 >> sh) & 15u), cs);
+                st_slab(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u), cs);
             }
         } else {
             for (uint32_t e = 0; e < cnt; ++e, o += VPE) {
                 if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
 #pragma unroll 4
-                for (uint32_t k = 0; k < K; ++k) st_slab(o + (k << 5), lut_get(lut_lane, (src[(k << 2) * kStride + e] >> sh) & 15u));
+                for (uint32_t k = 0; k < K; ++k) st_slab(o + (k << 5), lut_get(lut_lane, (src[(k << 2) * kStride + e] >> sh) & 15u), cs);
             }
         }
     } else if (vec_ok && (obs & 31u) == 0) {
@@ -442,13 +444,13 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         if (r4 == 0) {          // VPE divides 32: the lane keeps its word column and only walks the environments
 #pragma unroll 4
             for (uint32_t j = lane; j < total; j += 32) {
-                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u));
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u), cs);
                 src += dstep; e += q4;
             }
         } else {
 #pragma unroll 4
             for (uint32_t j = lane; j < total; j += 32) {
-                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u));
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u), cs);
                 src += dstep; e += q4; v += r4;
                 if (v >= VPE) { v -= VPE; src += dwrap; ++e; }
             }
@@ -461,7 +463,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         for (uint32_t j = lane; j < total; j += 32) {
             if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) {
                 const uint32_t nib = bits[(v >> 3) * kStride + e] >> ((v & 7u) << 2);
-                st_slab(out4 + j, lut_get(lut_lane, nib & 15u));
+                st_slab(out4 + j, lut_get(lut_lane, nib & 15u), cs);
             }
             e += q4; v += r4;
             if (v >= VPE) { v -= VPE; ++e; }
@@ -477,7 +479,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
                 const bool straddle = off + 4u > obs;                 // the float4 ends in environment e+1
                 if (straddle) { const uint32_t k = obs - off; nib = (nib & ((1u << k) - 1u)) | (bits[e + 1] << k); }
                 const bool on = (MODE != MODE_SEARCH) || (((en_bits >> e) & 1u) && (!straddle || ((en_bits >> (e + 1)) & 1u)));
-                if (on) st_slab(out4 + j, lut_get(lut_lane, nib & 15u));
+                if (on) st_slab(out4 + j, lut_get(lut_lane, nib & 15u), cs);
                 else {
                     uint32_t ee = e, oo = off;
                     for (int k = 0; k < 4; ++k) { if ((en_bits >> ee) & 1u) out[(j << 2) + k] = ((nib >> k) & 1u) ? 1.0f : 0.0f; if (++oo == obs) { oo = 0; ++ee; } }
@@ -497,7 +499,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
 // Phase 2b: masks() = [!success; A] per environment (clifford.rs:349-351) as a uint8 [B][A] slab, 16-byte stores.
 // G = bytes per granule that cannot straddle two environments (4 when A % 4 == 0, else 1).
 template <int MODE, int G>
-__device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t A, uint32_t mask_bits, uint32_t en_bits, int lane, uint64_t magic_A) {
+__device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t A, uint32_t mask_bits, uint32_t en_bits, int lane, uint64_t magic_A, bool cs) {
     const uint32_t total = cnt * A, nvec = (reinterpret_cast<uintptr_t>(out) & 15u) ? 0u : (total >> 4);   // whole 16-byte vectors of the (aligned) slab
     if (MODE != MODE_SEARCH) {
         // the usual case: the 32 environments agree (nobody solved yet, or all solved) -> a plain fill of the slab
@@ -505,7 +507,7 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
         if (mask_bits == live || mask_bits == 0u) {
             const uint32_t w = mask_bits ? 0x01010101u : 0u;
             const uint4 w4 = make_uint4(w, w, w, w);
-            for (uint32_t j = lane; j < nvec; j += 32) st_slab(reinterpret_cast<uint4*>(out) + j, w4);
+            for (uint32_t j = lane; j < nvec; j += 32) st_slab(reinterpret_cast<uint4*>(out) + j, w4, cs);
             for (uint32_t b = (nvec << 4) + lane; b < total; b += 32) out[b] = (uint8_t)(w & 1u);
             return;
         }
@@ -524,7 +526,7 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
             if (G == 4) w[k] = bit ? 0x01010101u : 0u; else w[k >> 2] |= bit << ((k & 3) * 8);
             if (++oo == P) { oo = 0; ++ee; }
         }
-        if (MODE != MODE_SEARCH || all_on) st_slab(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]));
+        if (MODE != MODE_SEARCH || all_on) st_slab(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]), cs);
         else {
             uint32_t e2 = e, o2 = off;
             for (int k = 0; k < 16 / G; ++k) {
@@ -744,7 +746,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab --------
         if (a.obs) {
             float* out = a.obs + ((size_t)slot * c.B + (size_t)e0) * c.obs_size;
-            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r);
+            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r, a.nsteps == 1);
             else {
                 // large Permutation (no room for a bit stream in shared memory): one-hot test straight from the packed bytes
                 const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, n = (uint32_t)c.n;
@@ -768,8 +770,8 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         }
         if (a.mask) {
             uint8_t* out = a.mask + ((size_t)slot * c.B + (size_t)e0) * c.A;
-            if ((c.A & 3) == 0) expand_mask<MODE, 4>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
-            else expand_mask<MODE, 1>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
+            if ((c.A & 3) == 0) expand_mask<MODE, 4>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A, a.nsteps == 1);
+            else expand_mask<MODE, 1>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A, a.nsteps == 1);
         }
         if (++slot == a.ring) slot = 0;
         last_en_bits = en_bits;
