@@ -9,6 +9,8 @@
 //   phase 2 (the whole warp, for its 32 environments): the contiguous slab of the dense float observation tensor and
 //       of the uint8 action-mask tensor is produced from the packed bits with 16-byte coalesced streaming stores.
 #pragma once
+#include <type_traits>
+
 #include "qg_common.cuh"
 #include "qg_gf2.cuh"
 
@@ -330,9 +332,11 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\
 
 // store flavour of the observation / mask slabs (compile-time switch for A/B runs): 0 = st.global.cs (streaming, evict first),
 // 1 = plain st.global, 2 = st.global.wt, 3 / 4 = L2 cache hint evict_last / evict_unchanged
-// Measured (replay, 65 536 envs, profiles/r1_v22_store_policy.txt): plain stores are 2.4 % faster than .cs on C3 (also at 1 M envs) and
-// 1.3 % on C4, 0.7-0.9 % slower on C1 / C5; evict_unchanged equals plain, evict_last is 4 % slower.  A persisting-L2 window over the
-// action stream is much worse (40 MB set aside: -20 %): the write stream lives off the L2 capacity it can buffer in.
+// Measured (replay, 65 536 envs, profiles/r1_v22_store_policy.txt): plain stores are 2.4 % faster than .cs on C3 (also at 1 M envs),
+// 0.7-0.9 % slower on C1 / C5 and 2 % slower for single-step launches; evict_unchanged equals plain, evict_last is 4 % slower.  So
+// QG_STORE == 1 uses plain stores only in the whole-row fast path of replay launches (st_rows) and .cs everywhere else.  A
+// persisting-L2 window over the action stream is much worse (40 MB set aside: -20 %): the write stream lives off the L2 capacity it
+// can buffer in.
 #ifndef QG_STORE
 #define QG_STORE 1
 #endif
@@ -359,18 +363,23 @@ __device__ __forceinline__ void st_hint(uint4* p, const uint4& v) {
 #else
 #define QG_LD_STREAM(p) (*(p))
 #endif
-// cs (warp uniform): streaming (evict-first) stores.  A replay launch (many steps per launch) is 2.4 % faster with plain stores, a
-// single-step launch 2 % faster with .cs (profiles/r1_v22_store_policy.txt, r1_v23_bench_n1.json): the launch picks (nsteps == 1).
 template <class V>
-__device__ __forceinline__ void st_slab(V* p, const V& v, bool cs) {
-#if QG_STORE == 0
-    __stcs(p, v, cs);
-#elif QG_STORE == 1
-    if (cs) __stcs(p, v); else *p = v;
+__device__ __forceinline__ void st_slab(V* p, const V& v) {
+#if QG_STORE == 0 || QG_STORE == 1
+    __stcs(p, v);
 #elif QG_STORE == 2
     __stwt(p, v);
 #else
     st_hint(p, v);
+#endif
+}
+// the whole-row fast path of a replay launch (see QG_STORE above): plain stores
+template <bool PLAIN, class V>
+__device__ __forceinline__ void st_rows(V* p, const V& v) {
+#if QG_STORE == 1
+    if (PLAIN) *p = v; else __stcs(p, v);
+#else
+    st_slab(p, v);
 #endif
 }
 __device__ __forceinline__ float4 nibble_to_float4(uint32_t nib) {
@@ -405,7 +414,7 @@ __device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t
 // so the loop has no division; the four floats come from the shared-memory table with one 128-bit load.
 template <int MODE>
 __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t* lut, float* out, uint32_t cnt, uint32_t obs, uint32_t en_bits, int lane,
-                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs, uint32_t q4, uint32_t r4, bool cs) {
+                                           uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs, uint32_t q4, uint32_t r4, bool plain_rows) {
     // 16-byte stores need an aligned slab: always true for the engine's own [B][obs] tensors; a ring slot of an odd-sized
     // batch may start off the grid, then everything goes through the scalar tail loop
     const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
@@ -417,24 +426,28 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         const uint32_t K = obs >> 7, VPE = obs >> 2, sh = ((uint32_t)lane & 7u) << 2;
         const uint32_t* src = bits + ((uint32_t)lane >> 3) * kStride;
         float4* o = out4 + lane;
-        if (K == 2) {
-            // measured dead ends at 65 536 envs (profiles/r1_v15_ablation*.jsonl, r1_v16_ablation_pipe.jsonl): floats from selects
-            // instead of the table (no change), the words of 8 environments read ahead of 16 back-to-back stores (1.7 % slower),
-            // the L1 / shared-memory carve-out (no change), more storing warps per tile (tools/store_pattern_probe.cu: no change)
+        // measured dead ends at 65 536 envs (profiles/r1_v15_ablation*.jsonl, r1_v16_ablation_pipe.jsonl): floats from selects
+        // instead of the table (no change), the words of 8 environments read ahead of 16 back-to-back stores (1.7 % slower),
+        // the L1 / shared-memory carve-out (no change), more storing warps per tile (tools/store_pattern_probe.cu: no change)
+        auto rows = [&](auto plain) {
+            constexpr bool PLAIN = decltype(plain)::value;
+            if (K == 2) {
 #pragma unroll 4
-            for (uint32_t e = 0; e < cnt; ++e, o += 64) {
-                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
-                const uint32_t w0 = src[e], w1 = src[4 * kStride + e];
-                st_slab(o, lut_get(lut_lane, (w0 >> sh) & 15u), cs);
-                st_slab(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u), cs);
-            }
-        } else {
-            for (uint32_t e = 0; e < cnt; ++e, o += VPE) {
-                if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+                for (uint32_t e = 0; e < cnt; ++e, o += 64) {
+                    if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
+                    const uint32_t w0 = src[e], w1 = src[4 * kStride + e];
+                    st_rows<PLAIN>(o, lut_get(lut_lane, (w0 >> sh) & 15u));
+                    st_rows<PLAIN>(o + 32, lut_get(lut_lane, (w1 >> sh) & 15u));
+                }
+            } else {
+                for (uint32_t e = 0; e < cnt; ++e, o += VPE) {
+                    if (MODE == MODE_SEARCH && !((en_bits >> e) & 1u)) continue;
 #pragma unroll 4
-                for (uint32_t k = 0; k < K; ++k) st_slab(o + (k << 5), lut_get(lut_lane, (src[(k << 2) * kStride + e] >> sh) & 15u), cs);
+                    for (uint32_t k = 0; k < K; ++k) st_rows<PLAIN>(o + (k << 5), lut_get(lut_lane, (src[(k << 2) * kStride + e] >> sh) & 15u));
+                }
             }
-        }
+        };
+        if (plain_rows) rows(std::true_type{}); else rows(std::false_type{});
     } else if (vec_ok && (obs & 31u) == 0) {
         // whole words per environment: a lane's nibble position inside its word never changes (r4 is a multiple of 8)
         const uint32_t VPE = obs >> 2, total = cnt * VPE, sh = ((uint32_t)lane & 7u) << 2;
@@ -444,13 +457,13 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         if (r4 == 0) {          // VPE divides 32: the lane keeps its word column and only walks the environments
 #pragma unroll 4
             for (uint32_t j = lane; j < total; j += 32) {
-                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u), cs);
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u));
                 src += dstep; e += q4;
             }
         } else {
 #pragma unroll 4
             for (uint32_t j = lane; j < total; j += 32) {
-                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u), cs);
+                if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) st_slab(out4 + j, lut_get(lut_lane, (*src >> sh) & 15u));
                 src += dstep; e += q4; v += r4;
                 if (v >= VPE) { v -= VPE; src += dwrap; ++e; }
             }
@@ -463,7 +476,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         for (uint32_t j = lane; j < total; j += 32) {
             if (MODE != MODE_SEARCH || ((en_bits >> e) & 1u)) {
                 const uint32_t nib = bits[(v >> 3) * kStride + e] >> ((v & 7u) << 2);
-                st_slab(out4 + j, lut_get(lut_lane, nib & 15u), cs);
+                st_slab(out4 + j, lut_get(lut_lane, nib & 15u));
             }
             e += q4; v += r4;
             if (v >= VPE) { v -= VPE; ++e; }
@@ -479,7 +492,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
                 const bool straddle = off + 4u > obs;                 // the float4 ends in environment e+1
                 if (straddle) { const uint32_t k = obs - off; nib = (nib & ((1u << k) - 1u)) | (bits[e + 1] << k); }
                 const bool on = (MODE != MODE_SEARCH) || (((en_bits >> e) & 1u) && (!straddle || ((en_bits >> (e + 1)) & 1u)));
-                if (on) st_slab(out4 + j, lut_get(lut_lane, nib & 15u), cs);
+                if (on) st_slab(out4 + j, lut_get(lut_lane, nib & 15u));
                 else {
                     uint32_t ee = e, oo = off;
                     for (int k = 0; k < 4; ++k) { if ((en_bits >> ee) & 1u) out[(j << 2) + k] = ((nib >> k) & 1u) ? 1.0f : 0.0f; if (++oo == obs) { oo = 0; ++ee; } }
@@ -499,7 +512,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
 // Phase 2b: masks() = [!success; A] per environment (clifford.rs:349-351) as a uint8 [B][A] slab, 16-byte stores.
 // G = bytes per granule that cannot straddle two environments (4 when A % 4 == 0, else 1).
 template <int MODE, int G>
-__device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t A, uint32_t mask_bits, uint32_t en_bits, int lane, uint64_t magic_A, bool cs) {
+__device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t A, uint32_t mask_bits, uint32_t en_bits, int lane, uint64_t magic_A) {
     const uint32_t total = cnt * A, nvec = (reinterpret_cast<uintptr_t>(out) & 15u) ? 0u : (total >> 4);   // whole 16-byte vectors of the (aligned) slab
     if (MODE != MODE_SEARCH) {
         // the usual case: the 32 environments agree (nobody solved yet, or all solved) -> a plain fill of the slab
@@ -507,7 +520,7 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
         if (mask_bits == live || mask_bits == 0u) {
             const uint32_t w = mask_bits ? 0x01010101u : 0u;
             const uint4 w4 = make_uint4(w, w, w, w);
-            for (uint32_t j = lane; j < nvec; j += 32) st_slab(reinterpret_cast<uint4*>(out) + j, w4, cs);
+            for (uint32_t j = lane; j < nvec; j += 32) st_slab(reinterpret_cast<uint4*>(out) + j, w4);
             for (uint32_t b = (nvec << 4) + lane; b < total; b += 32) out[b] = (uint8_t)(w & 1u);
             return;
         }
@@ -526,7 +539,7 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
             if (G == 4) w[k] = bit ? 0x01010101u : 0u; else w[k >> 2] |= bit << ((k & 3) * 8);
             if (++oo == P) { oo = 0; ++ee; }
         }
-        if (MODE != MODE_SEARCH || all_on) st_slab(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]), cs);
+        if (MODE != MODE_SEARCH || all_on) st_slab(reinterpret_cast<uint4*>(out) + j, make_uint4(w[0], w[1], w[2], w[3]));
         else {
             uint32_t e2 = e, o2 = off;
             for (int k = 0; k < 16 / G; ++k) {
@@ -746,7 +759,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab --------
         if (a.obs) {
             float* out = a.obs + ((size_t)slot * c.B + (size_t)e0) * c.obs_size;
-            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r, a.nsteps == 1);
+            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r, a.nsteps > 1);
             else {
                 // large Permutation (no room for a bit stream in shared memory): one-hot test straight from the packed bytes
                 const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, n = (uint32_t)c.n;
@@ -770,8 +783,8 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         }
         if (a.mask) {
             uint8_t* out = a.mask + ((size_t)slot * c.B + (size_t)e0) * c.A;
-            if ((c.A & 3) == 0) expand_mask<MODE, 4>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A, a.nsteps == 1);
-            else expand_mask<MODE, 1>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A, a.nsteps == 1);
+            if ((c.A & 3) == 0) expand_mask<MODE, 4>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
+            else expand_mask<MODE, 1>(out, (uint32_t)cnt, (uint32_t)c.A, mask_bits, en_bits, lane, a.magic_A);
         }
         if (++slot == a.ring) slot = 0;
         last_en_bits = en_bits;
