@@ -65,6 +65,23 @@ __global__ void k_stgk(float* ring, int R, long B, int obs, int steps, int delay
     }
 }
 
+// strided tiles: warp w owns the environments w, w + W, w + 2W, .. (W = number of warps), so the rows the W warps write at the same time
+// are neighbours in memory (one contiguous W * obs * 4-byte region per k) instead of 32 KB apart
+__global__ void k_stg_strided(float* ring, int R, long B, int obs, int steps, int delay_ns) {
+    const int lane = threadIdx.x & 31;
+    const long W = B / 32, w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= W) return;
+    const int per_env4 = obs / 4;             // float4 per env row
+    for (int t = 0; t < steps; ++t) {
+        busy_ns(delay_ns);
+        const float4 v = make_float4((float)(t & 1), 0.f, 1.f, (float)(lane & 1));
+        for (int k = 0; k < 32; ++k) {
+            float4* out = reinterpret_cast<float4*>(ring + ((size_t)(t % R) * B + (w + W * k)) * obs);
+            for (int j = lane; j < per_env4; j += 32) __stcs(out + j, v);
+        }
+    }
+}
+
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
@@ -136,6 +153,7 @@ int main(int argc, char** argv) {
     const double bytes = (double)slot * steps;
     timeit("fill", [&] { for (int t = 0; t < steps; ++t) k_fill<<<148 * 8, 256>>>(reinterpret_cast<float4*>(ring + (size_t)(t % R) * B * obs), slot / 16); }, bytes);
     timeit("stg", [&] { k_stg<<<grid, wpc * 32>>>(ring, R, B, obs, steps, delay); }, bytes);
+    timeit("stg_strided", [&] { k_stg_strided<<<grid, wpc * 32>>>(ring, R, B, obs, steps, delay); }, bytes);
     for (int skew = 5000; skew <= 80000; skew *= 4) {
         char nm[24]; snprintf(nm, sizeof nm, "stg_skew%d", skew);
         timeit(nm, [&] { k_stg<<<grid, wpc * 32>>>(ring, R, B, obs, steps, delay, skew); }, bytes);
