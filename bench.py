@@ -485,7 +485,8 @@ def run_collector(args, dev, local, rank, world):
     out.update({"envs_per_gpu": B, "decisions": T,
                 "note": "RolloutCollector.collect: reset_select + observe (dense f32) + PyTorch BasicPolicy 512/256 forward (f32 cuBLAS) + softmax + "
                         "qg_collect_step + log-prob gather per decision, qg_gae at the end; difficulty 64, random-init policy",
-                "tf32_policy": dict(leg("tf32"), note="same collector with matmul_precision='tf32' (the policy's GEMMs on tensor cores, f32 accumulate)")})
+                "tf32_policy": dict(leg("tf32"), note="same collector with matmul_precision='tf32' (the policy's GEMMs on tensor cores, f32 accumulate)"),
+                "bf16_policy": dict(leg("bf16"), note="same collector with matmul_precision='bf16' (torch.autocast)")})
     return out
 
 
