@@ -13,4 +13,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-collector --synth-searches 1 > $O/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_search_fused -c 1 -f -o $O/${TAG}_search_fused \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-per-step --no-packed --no-collector --synth-searches 1 > $O/${TAG}_ncu_search.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_step -s 3 -c 1 -f -o $O/${TAG}_step \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-per-step --no-packed --no-collector --no-synth > $O/${TAG}_ncu_step.log 2>&1
 tail -3 $O/${TAG}_tests.txt; cat $O/${TAG}_smoke.txt | tail -2; head -c 600 $O/${TAG}_bench_n1.json
