@@ -158,3 +158,33 @@ def test_data_parallel_helpers_gloo():
     g = net.weight.grad.clone()
     ppo.sync_gradients(list(net.parameters()))
     assert torch.equal(g, net.weight.grad) and ppo.agree_min(5) == 5 and ppo.mean_over_ranks(2.0) == 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["lf", "clifford", "pauli"])
+@pytest.mark.parametrize("algo", ["PPO", "AZ"])
+def test_learn_runs_for_every_env_kind(kind, algo):
+    """A few iterations of each algorithm on each of the other env kinds (twists on, add_perms on for PauliNetwork): finite losses,
+    sane bookkeeping, and the trained policy still synthesises through RLSynthesis.synth."""
+    from qiskit_gym_b200 import gyms
+    from qiskit_gym_b200.rl import RLSynthesis
+
+    torch.manual_seed(1)
+    tri = [(0, 1), (1, 0), (1, 2), (2, 1)]
+    if kind == "lf":
+        env = gyms.LinearFunctionGym.from_coupling_map(tri, basis_gates=("CX",), max_depth=32)
+    elif kind == "clifford":
+        env = gyms.CliffordGym.from_coupling_map(tri, basis_gates=("H", "S", "CX"), max_depth=32)
+    else:
+        env = gyms.PauliGym.from_coupling_map(tri, basis_gates=("H", "S", "SX", "CX"), max_depth=32)
+    if algo == "PPO":
+        cfg = {"collecting": {"num_episodes": 128}, "training": {"num_epochs": 2}, "evals": {"ppo_deterministic": {"num_episodes": 32}}}
+    else:
+        cfg = {"collecting": {"num_episodes": 64, "num_mcts_searches": 6}, "training": {"num_epochs": 2}, "learning": {"diff_metric": "m"},
+               "evals": {"m": {"num_episodes": 16, "num_mcts_searches": 4}}}
+    rls = RLSynthesis(env, cfg, {"embedding_size": 32, "common_layers": [32]}, device=0, algorithm_cls=f"twisterl.rl.{algo}")
+    hist = rls.learn(initial_difficulty=2, num_iterations=3)
+    assert len(hist) == 3
+    for h in hist:
+        assert np.isfinite(h["loss"]) and h["samples"] > 0 and h["episodes"] > 0 and 0.0 <= h["collect_success"] <= 1.0
+        assert all(0.0 <= v <= 1.0 for k, v in h.items() if k.startswith("eval/"))
