@@ -14,7 +14,10 @@ constexpr int kPolConsumers = kPolHalf * kPolHalves;   // 16 compute warps
 constexpr int kPolMaxWidth = 1024;    // widest layer (4 features per thread)
 constexpr int kPolThreads = kPolConsumers + 32;   // + 1 producer warp
 constexpr int kPolMaxLayers = 8;
-constexpr int kPolStages = 3;        // weight tiles in flight
+#ifndef QG_POL_STAGES
+#define QG_POL_STAGES 3
+#endif
+constexpr int kPolStages = QG_POL_STAGES;   // weight tiles in flight (4 stages measured: 23.3 vs 22.8 us per decision, no gain)
 constexpr int kPolTileFloats = 8192; // 32 KB per weight tile (16 KB tiles: +12 % time per decision; 64 KB x 2 stages: -4 % but the widest networks no longer fit)
 constexpr int kPolPartFloats = kPolMaxWidth * 8;   // partial sums handed between the thread groups: 1024 features (or 16 warps x 64 features) x 8 rows
 
