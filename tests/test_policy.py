@@ -72,6 +72,8 @@ def test_packed_observation_equals_dense_and_oracle(name, B):
     ((16, 16), 72, 512, (256,), (), 0.5),
     ((20, 25), 104, 300, (200, 100), (50,), 0.3),
     ((3, 3), 2, 1024, (), (), 0.5),
+    ((30, 40), 20, 600, (300,), (), 0.5),        # dense, 1 200 entries: the rows' change lists exceed the list capacity (row groups), 2 feature passes
+    ((50, 60), 10, 128, (64,), (), 0.4),         # more entries per row than the default capacity
 ])
 def test_fused_policy_matches_torch(obs_shape, A, emb, common, pol_layers, density):
     from qiskit_gym_b200.policy import FusedPolicy, pack_obs_bits
