@@ -264,11 +264,21 @@ QG_API int qg_search_step_bits(qg_engine* e, const float* weights_dev, int32_t d
  * instead of recomputing it, with bit-identical results.  The other layers are f32 FMA chains over ascending input index. */
 QG_API int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features,
                             const float* const* weights_host, const float* const* biases_host, qg_policy** out);
+/* The same with the BasicPolicy's value head (a single Linear from the last common layer to one output, examples/models/{*}.pt
+ * `value.0.weight [1][in]`, `value.0.bias`): it is evaluated as one more output of the last layer, outside the softmax, and read with
+ * qg_policy_forward_bits_value.  value_weight_host: float[in_features of the last layer], or NULL for no value head. */
+QG_API int qg_policy_create_value(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features,
+                                  const float* const* weights_host, const float* const* biases_host,
+                                  const float* value_weight_host, float value_bias, qg_policy** out);
 QG_API void qg_policy_destroy(qg_policy* p);
 QG_API int32_t qg_policy_num_actions(const qg_policy* p);
+QG_API int32_t qg_policy_has_value(const qg_policy* p);
 /* probs_dev float[B][num_actions] (softmax) and / or logits_dev float[B][num_actions]; either may be NULL. */
 QG_API int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev,
                                   float* logits_dev, qg_stream stream);
+/* ... and values_dev float[B] (the value head's output; the policy must have been created with one); any of the three may be NULL. */
+QG_API int qg_policy_forward_bits_value(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev,
+                                        float* logits_dev, float* values_dev, qg_stream stream);
 
 /* The whole rollout search in ONE launch: every CTA owns 8 rollouts and loops  policy (packed observation -> action weights) ->
  * sample / arg-max + fused step -> next packed observation  until its rollouts are final or max_decisions decisions were taken;

@@ -26,7 +26,8 @@ SYMBOLS = [
     "qg_read_metrics", "qg_read_errors", "qg_get_state_host", "qg_solution_host", "qg_search_begin",
     "qg_search_step", "qg_search_best", "qg_read_returns", "qg_reset_select", "qg_collect_step", "qg_gae", "qg_twist_gather",
     "qg_obs_words", "qg_step_bits", "qg_replay_bits", "qg_observe_bits", "qg_search_step_bits",
-    "qg_policy_create", "qg_policy_destroy", "qg_policy_num_actions", "qg_policy_forward_bits",
+    "qg_policy_create", "qg_policy_create_value", "qg_policy_destroy", "qg_policy_num_actions", "qg_policy_has_value", "qg_policy_forward_bits",
+    "qg_policy_forward_bits_value",
     "qg_step_slots", "qg_copy_records", "qg_mcts_begin", "qg_mcts_select", "qg_mcts_backup", "qg_mcts_root_weights", "qg_search_run",
 ]
 
@@ -117,6 +118,9 @@ def lib():
     L.qg_policy_destroy.restype = None
     L.qg_policy_num_actions.argtypes = [vp]
     L.qg_policy_forward_bits.argtypes = [vp, vp, i64, vp, vp, vp]
+    L.qg_policy_create_value.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_float, C.POINTER(vp)]
+    L.qg_policy_has_value.argtypes = [vp]
+    L.qg_policy_forward_bits_value.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     L.qg_step_slots.argtypes = [vp, i64] + [vp] * 9 + [vp]
     L.qg_copy_records.argtypes = [vp, vp, vp, i64, vp]
     treep = C.POINTER(_abi.QgMctsTree)

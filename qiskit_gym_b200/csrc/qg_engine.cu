@@ -774,7 +774,7 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
                   int32_t* decisions_dev, qg_stream stream) {
     if (!e || !pol || !obs_bits_dev || !weights_dev) { set_error("null argument"); return QG_ERR_INVALID; }
     if (pol->device != e->device) { set_error("qg_search_run: policy and engine live on different devices"); return QG_ERR_INVALID; }
-    if (pol->d.obs_size != e->L.obs_size || pol->d.width[pol->d.num_layers - 1] != e->L.A) { set_error("qg_search_run: the policy's observation size / action count do not match the env"); return QG_ERR_INVALID; }
+    if (pol->d.obs_size != e->L.obs_size || pol->d.num_actions != e->L.A) { set_error("qg_search_run: the policy's observation size / action count do not match the env"); return QG_ERR_INVALID; }
     if (e->L.kind == QG_ENV_PERMUTATION && e->L.OW == 0) { set_error("packed observations need num_qubits <= 64 for Permutation"); return QG_ERR_UNSUPPORTED; }
     if (max_decisions < 0) { set_error("qg_search_run: negative decision budget"); return QG_ERR_INVALID; }
     if (e->B == 0 || max_decisions == 0) return QG_OK;

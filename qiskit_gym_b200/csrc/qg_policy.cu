@@ -27,7 +27,8 @@
 
 namespace qg {
 
-__global__ void __launch_bounds__(kPolThreads) k_policy_mlp(const __grid_constant__ PolicyDev p, const uint32_t* bits, int64_t B, float* probs, float* logits_out) {
+__global__ void __launch_bounds__(kPolThreads) k_policy_mlp(const __grid_constant__ PolicyDev p, const uint32_t* bits, int64_t B, float* probs, float* logits_out,
+                                                            float* values_out) {
     extern __shared__ __align__(128) float sm[];
     const PolicySmem ps = policy_smem_carve(p, sm);
     policy_init_barriers(ps, threadIdx.x);
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(kPolThreads) k_policy_mlp(const __grid_constan
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     __syncthreads();                               // barriers initialised
     int G = 0;
-    policy_forward_rows(p, ps, bits, (int64_t)blockIdx.x * kPolRows, B, probs, logits_out, G);
+    policy_forward_rows(p, ps, bits, (int64_t)blockIdx.x * kPolRows, B, probs, logits_out, G, 0, -1, nullptr, nullptr, 0, values_out);
 }
 
 }  // namespace qg
@@ -64,15 +65,22 @@ void qg_policy_destroy(qg_policy* p) {
 
 int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features, const float* const* weights_host,
                      const float* const* biases_host, qg_policy** out) {
+    return qg_policy_create_value(device, obs_size, num_layers, out_features, weights_host, biases_host, nullptr, 0.0f, out);
+}
+
+int qg_policy_create_value(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features, const float* const* weights_host,
+                           const float* const* biases_host, const float* value_weight_host, float value_bias, qg_policy** out) {
     if (!out) { set_error("null out"); return QG_ERR_INVALID; }
     *out = nullptr;
     if (obs_size < 1 || obs_size > 65535) { set_error("qg_policy_create: obs_size must be in [1, 65535]"); return QG_ERR_UNSUPPORTED; }
     if (num_layers < 1 || num_layers > kPolMaxLayers || !out_features || !weights_host || !biases_host) { set_error("qg_policy_create: 1..8 layers with weights and biases"); return QG_ERR_INVALID; }
     int maxw = 0;
+    const int extra = value_weight_host ? 1 : 0;            // the value head rides along as one more output of the last layer
     for (int l = 0; l < num_layers; ++l) {
-        if (out_features[l] < 1 || out_features[l] > kPolMaxWidth) { set_error("qg_policy_create: layer widths must be in [1, 1024]"); return QG_ERR_UNSUPPORTED; }
+        const int o = out_features ? out_features[l] + (l == num_layers - 1 ? extra : 0) : 0;
+        if (out_features[l] < 1 || o > kPolMaxWidth) { set_error("qg_policy_create: layer widths must be in [1, 1024]"); return QG_ERR_UNSUPPORTED; }
         if (!weights_host[l] || !biases_host[l]) { set_error("qg_policy_create: null layer"); return QG_ERR_INVALID; }
-        maxw = std::max(maxw, out_features[l]);
+        maxw = std::max(maxw, o);
     }
     int ndev = 0;
     POL_CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -86,10 +94,13 @@ int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const
     d.act0_floats = maxw * kPolRows;
     d.act1_floats = maxw * kPolRows;
     for (int l = 0; l < num_layers; ++l) {
-        const int in = l == 0 ? obs_size : out_features[l - 1], o = out_features[l], os = (o + 3) / 4 * 4;
+        const bool last = l == num_layers - 1;
+        const int in = l == 0 ? obs_size : out_features[l - 1], o0 = out_features[l], o = o0 + (last ? extra : 0), os = (o + 3) / 4 * 4;
         d.width[l] = o; d.stride[l] = os;
-        std::vector<float> t((size_t)in * os, 0.0f);
-        for (int j = 0; j < o; ++j) for (int k = 0; k < in; ++k) t[(size_t)k * os + j] = weights_host[l][(size_t)j * in + k];   // torch Linear.weight is [out][in]
+        std::vector<float> t((size_t)in * os, 0.0f), bias(o, 0.0f);
+        for (int j = 0; j < o0; ++j) for (int k = 0; k < in; ++k) t[(size_t)k * os + j] = weights_host[l][(size_t)j * in + k];   // torch Linear.weight is [out][in]
+        std::memcpy(bias.data(), biases_host[l], (size_t)o0 * 4);
+        if (last && extra) { for (int k = 0; k < in; ++k) t[(size_t)k * os + o0] = value_weight_host[k]; bias[o0] = value_bias; }
         if (l == 0) {
             // fixed point for the exact (order-independent) first-layer sum: the largest |weight| lands just below 2^30
             float mx = 0.0f;
@@ -103,11 +114,12 @@ int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const
         cudaError_t ce = cudaMalloc(&w, t.size() * 4);
         if (ce == cudaSuccess) { p->bufs.push_back(w); ce = cudaMalloc(&b, (size_t)o * 4); }
         if (ce == cudaSuccess) { p->bufs.push_back(b); ce = cudaMemcpy(w, t.data(), t.size() * 4, cudaMemcpyHostToDevice); }
-        if (ce == cudaSuccess) ce = cudaMemcpy(b, biases_host[l], (size_t)o * 4, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(b, bias.data(), (size_t)o * 4, cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) { set_error(std::string("qg_policy_create: ") + cudaGetErrorString(ce)); qg_policy_destroy(p); return QG_ERR_CUDA; }
         d.wt[l] = l == 0 ? nullptr : w; d.bias[l] = b;
         if (l == 0) d.w0q = reinterpret_cast<const int32_t*>(w);
     }
+    d.num_actions = out_features[num_layers - 1];
     p->smem = policy_smem_bytes(d);
     if (p->smem > 210 * 1024) { set_error("qg_policy_create: the network needs more shared memory than one SM has"); qg_policy_destroy(p); return QG_ERR_UNSUPPORTED; }
     {
@@ -119,10 +131,17 @@ int qg_policy_create(int32_t device, int32_t obs_size, int32_t num_layers, const
     return QG_OK;
 }
 
-int32_t qg_policy_num_actions(const qg_policy* p) { return p ? p->d.width[p->d.num_layers - 1] : 0; }
+int32_t qg_policy_num_actions(const qg_policy* p) { return p ? p->d.num_actions : 0; }
+int32_t qg_policy_has_value(const qg_policy* p) { return (p && p->d.width[p->d.num_layers - 1] > p->d.num_actions) ? 1 : 0; }
 
 int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev, float* logits_dev, qg_stream stream) {
-    if (!p || !obs_bits_dev || (!probs_dev && !logits_dev)) { set_error("null argument"); return QG_ERR_INVALID; }
+    return qg_policy_forward_bits_value(p, obs_bits_dev, batch, probs_dev, logits_dev, nullptr, stream);
+}
+
+int qg_policy_forward_bits_value(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev, float* logits_dev, float* values_dev,
+                                 qg_stream stream) {
+    if (!p || !obs_bits_dev || (!probs_dev && !logits_dev && !values_dev)) { set_error("null argument"); return QG_ERR_INVALID; }
+    if (values_dev && !qg_policy_has_value(p)) { set_error("qg_policy_forward_bits_value: the policy was created without a value head"); return QG_ERR_INVALID; }
     if (batch < 0) { set_error("qg_policy_forward_bits: negative batch"); return QG_ERR_INVALID; }
     if (batch == 0) return QG_OK;
     int cur = -1;
@@ -134,7 +153,7 @@ int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, int64_t b
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at; lc.numAttrs = 1;
-    POL_CUDA_OK(cudaLaunchKernelEx(&lc, k_policy_mlp, p->d, obs_bits_dev, batch, probs_dev, logits_dev));
+    POL_CUDA_OK(cudaLaunchKernelEx(&lc, k_policy_mlp, p->d, obs_bits_dev, batch, probs_dev, logits_dev, values_dev));
     return QG_OK;
 }
 

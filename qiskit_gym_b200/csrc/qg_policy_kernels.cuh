@@ -30,6 +30,7 @@ struct PolicyDev {
     const int32_t* w0q;                  // first layer's transposed weights in fixed point: w0q[k][j] = rint(W0[j][k] * 2^w0_shift), [obs_size][stride[0]]
     float w0_scale;                      // 2^-w0_shift
     int32_t act0_floats, act1_floats;    // activation buffers ([feature][row])
+    int32_t num_actions;                 // outputs of the last layer that are action logits; one more (width - 1) is the value head's output when present
 };
 
 // ---- mbarrier / bulk-copy primitives (weights stream L2 -> shared memory with cp.async.bulk, no register staging) ------
@@ -448,7 +449,7 @@ __device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int t
 // row_base = row0 for the global [B][A] tensor or 0 for a CTA-private (shared-memory) buffer.
 __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const PolicySmem& ps, const uint32_t* bits, int64_t row0, int64_t B,
                                                     float* probs, float* logits_out, int& G, int pass = 0, int64_t probs_row_base = -1,
-                                                    long long* acc0 = nullptr, const uint32_t* stream = nullptr, int stream_rows = 0) {
+                                                    long long* acc0 = nullptr, const uint32_t* stream = nullptr, int stream_rows = 0, float* values_out = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = tid >= kPolConsumers;
     float* const tiles = ps.tiles; float* const act0 = ps.act0; float* const act1 = ps.act1;
@@ -516,7 +517,8 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
     if (warp < kPolRows) {
         const int64_t row = row0 + warp;
         if (row < B) {
-            const int A = p.width[p.num_layers - 1];
+            const int A = p.num_actions;           // (a value head, when present, is output A of the last layer: not part of the softmax)
+            if (values_out && lane == 0) values_out[row] = p.width[p.num_layers - 1] > A ? src[(size_t)A * kPolRows + warp] : 0.0f;
             float mx = -INFINITY;
             for (int a = lane; a < A; a += 32) mx = fmaxf(mx, src[(size_t)a * kPolRows + warp]);
 #pragma unroll

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_const
 template <int KIND>
 cudaError_t launch_search_fused(const DevCfg& c, const StepArgs& a, const PolicyDev& p, int max_decisions, int32_t* decisions_out, size_t step_smem_bytes, long long* acc0,
                                 const uint32_t* first_bits, cudaStream_t st) {
-    const size_t smem = policy_smem_bytes(p) + step_smem_bytes + (size_t)kPolRows * p.width[p.num_layers - 1] * 4;
+    const size_t smem = policy_smem_bytes(p) + step_smem_bytes + (size_t)kPolRows * p.num_actions * 4;
     cudaError_t e = cudaFuncSetAttribute(k_search_fused<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((c.B + kPolRows - 1) / kPolRows);

@@ -60,10 +60,13 @@ class MCTSSearch:
     R * (num_mcts_searches + 1) records for the tree nodes."""
 
     def __init__(self, env_kind, num_qubits, gateset, policy: torch.nn.Module, num_rollouts: int, num_mcts_searches: int, C: float = 2 ** 0.5,
-                 device=None, max_depth: int = 128, use_cuda_graph: bool = True, **env_kwargs):
+                 device=None, max_depth: int = 128, use_cuda_graph: bool = True, policy_backend: str = "auto", **env_kwargs):
         """use_cuda_graph: a decision's launches (root evaluation, then per simulation PUCT descent -> clone + step -> policy -> back-up)
-        are captured once and replayed: the whole decision as one graph up to 128 simulations, one graph per simulation beyond."""
-        assert num_mcts_searches >= 1
+        are captured once and replayed: the whole decision as one graph up to 128 simulations, one graph per simulation beyond.
+        policy_backend: "fused" = priors and values of the root / the leaves from packed observations in one kernel (policy.FusedPolicy
+        with the value head; re-created whenever the module's weights change), "torch" = the PyTorch module on dense observations, "auto" =
+        fused when the policy has the simple head layout and the env can pack its observations."""
+        assert num_mcts_searches >= 1 and policy_backend in ("auto", "fused", "torch")
         env_kwargs.setdefault("add_perms", False)
         self.env = BatchedEnv(env_kind, num_qubits, gateset, num_rollouts, device=device, max_depth=max_depth, **env_kwargs)
         pool_kwargs = dict(env_kwargs, track_solution=False)
@@ -83,9 +86,21 @@ class MCTSSearch:
         self.weights = torch.zeros((self.R, A), dtype=torch.float32, device=dev)
         self.num_active = torch.zeros(1, dtype=torch.int32, device=dev)
         self.hook = None            # tests: hook(kind, decision, simulation, tensors...) sees the policy outputs the trees consumed
+        from .policy import simple_value_head
+        can_fuse = simple_value_head(self.policy) is not None and not (env_kind == 0 and num_qubits > 64)      # (no packed observations for n > 64 permutations)
+        if policy_backend == "fused" and not can_fuse:
+            raise NotImplementedError("policy_backend='fused' needs single-Linear action / value heads")
+        self.backend = "fused" if (policy_backend != "torch" and can_fuse) else "torch"
+        self.fused = None
+        if self.backend == "fused":
+            self.root_bits = self.env.new_obs_bits()
+            self.leaf_bits = torch.zeros((self.R, self.env.obs_words()), dtype=torch.int32, device=dev)
+            self.pri = torch.zeros((self.R, A), dtype=torch.float32, device=dev)
+            self.val = torch.zeros(self.R, dtype=torch.float32, device=dev)
         self.use_graph = bool(use_cuda_graph)
         self._graphs = None         # (root graph or None, simulation graph or None, whole-decision graph or None)
         self._graph_policy = None
+        self._fused_for = None
         self._stream = torch.cuda.Stream(device=dev)
 
     def _policy(self, obs):
@@ -93,11 +108,24 @@ class MCTSSearch:
             logits, value = self.policy(obs)
             return torch.softmax(logits.float(), dim=-1).contiguous(), value.float().reshape(-1).contiguous()
 
+    def _fused_policy(self):
+        from .policy import FusedPolicy, weights_version
+        if self.fused is None or self.fused.version != weights_version(self.policy) or self._fused_for is not self.policy:
+            self.fused = FusedPolicy(self.policy, device=self.env.device, with_value=True)
+            self._fused_for = self.policy
+            self._graphs = None                    # a graph holds the old handle
+        return self.fused
+
     def _root(self, decision: int = 0):
         env, pool, tree = self.env, self.pool, self.tree
-        env.observe()
         _, done, _, _ = env.status()
-        prior, _ = self._policy(env.obs)
+        if self.backend == "fused":
+            env.observe_bits(self.root_bits)
+            self.fused.forward_bits(self.root_bits, probs=self.pri, values=self.val)
+            prior = self.pri
+        else:
+            env.observe()
+            prior, _ = self._policy(env.obs)
         if self.hook:
             self.hook("root", decision, -1, prior, None)
         pool.copy_records_from(env, self.root_slots)
@@ -106,8 +134,13 @@ class MCTSSearch:
     def _simulation(self, decision: int = 0, s: int = 0):
         pool, tree = self.pool, self.tree
         tree.select(self.c_puct, self.src, self.dst, self.act)
-        pool.step_slots(self.src, self.dst, self.act, obs=self.leaf_obs, reward=self.leaf_reward, done=self.leaf_done)
-        p, v = self._policy(self.leaf_obs)
+        if self.backend == "fused":
+            pool.step_slots(self.src, self.dst, self.act, obs_bits=self.leaf_bits, reward=self.leaf_reward, done=self.leaf_done)
+            self.fused.forward_bits(self.leaf_bits, probs=self.pri, values=self.val)
+            p, v = self.pri, self.val
+        else:
+            pool.step_slots(self.src, self.dst, self.act, obs=self.leaf_obs, reward=self.leaf_reward, done=self.leaf_done)
+            p, v = self._policy(self.leaf_obs)
         if self.hook:
             self.hook("leaf", decision, s, p, v)
         tree.backup(p, v, self.leaf_reward, self.leaf_done)
@@ -143,6 +176,8 @@ class MCTSSearch:
 
     def decide(self, decision: int = 0):
         """One decision's tree search for every rollout; leaves the root visit weights in self.weights."""
+        if self.backend == "fused":
+            self._fused_policy()
         if not self.use_graph or self.hook is not None:
             return self._decide_eager(decision)
         if self._graphs is None or self._graph_policy is not self.policy:      # (a graph holds the policy's parameter tensors)

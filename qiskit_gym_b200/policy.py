@@ -26,8 +26,24 @@ def action_layers(policy: torch.nn.Module):
     return layers
 
 
+def simple_value_head(policy: torch.nn.Module):
+    """The value head as (weight [in], bias) when it is a single Linear fed by the same activations as a single-Linear action head (the
+    reference's default BasicPolicy and all of its example checkpoints: policy_layers = value_layers = []), else None."""
+    act = [m for m in policy.action if isinstance(m, torch.nn.Linear)]
+    val = [m for m in getattr(policy, "value", []) if isinstance(m, torch.nn.Linear)]
+    if len(act) == 1 and len(val) == 1 and val[0].out_features == 1 and val[0].in_features == act[0].in_features:
+        return val[0]
+    return None
+
+
+def weights_version(policy: torch.nn.Module) -> int:
+    """Changes whenever a parameter of the module is updated in place (optimizer steps, load_state_dict)."""
+    return sum(int(p._version) for p in policy.parameters())
+
+
 class FusedPolicy:
-    def __init__(self, policy: torch.nn.Module, device=None):
+    def __init__(self, policy: torch.nn.Module, device=None, with_value: bool = False):
+        """with_value: also evaluate the value head (forward_bits(..., values=...)); needs the simple head layout (simple_value_head)."""
         if not torch.cuda.is_available():
             raise RuntimeError("qiskit_gym_b200 needs a CUDA device (no CPU fallback)")
         self.device_index = torch.cuda.current_device() if device is None else (device.index if isinstance(device, torch.device) else int(device))
@@ -40,12 +56,23 @@ class FusedPolicy:
         self.obs_size = int(ws[0].shape[1])
         self.obs_words = (self.obs_size + 31) // 32
         self.num_actions = int(ws[-1].shape[0])
+        self.version = weights_version(policy)
         n = len(ws)
         widths = (C.c_int32 * n)(*[int(w.shape[0]) for w in ws])
         wp = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
         bp = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
         h = C.c_void_p()
-        check(lib().qg_policy_create(self.device_index, self.obs_size, n, widths, wp, bp, C.byref(h)))
+        self.has_value = False
+        if with_value:
+            head = simple_value_head(policy)
+            if head is None:
+                raise NotImplementedError("FusedPolicy(with_value=True) needs single-Linear action and value heads on the same activations")
+            vw = np.ascontiguousarray(head.weight.detach().cpu().numpy().reshape(-1), dtype=np.float32)
+            vb = float(head.bias.detach().cpu().numpy().reshape(-1)[0])
+            check(lib().qg_policy_create_value(self.device_index, self.obs_size, n, widths, wp, bp, vw.ctypes.data_as(C.c_void_p), C.c_float(vb), C.byref(h)))
+            self.has_value = True
+        else:
+            check(lib().qg_policy_create(self.device_index, self.obs_size, n, widths, wp, bp, C.byref(h)))
         self._h = h
 
     def __del__(self):
@@ -57,17 +84,23 @@ class FusedPolicy:
                 pass
             self._h = None
 
-    def forward_bits(self, obs_bits: torch.Tensor, probs: torch.Tensor | None = None, logits: torch.Tensor | None = None):
-        """obs_bits int32 [B, obs_words] (BatchedEnv.observe_bits / step_bits) -> softmax action weights f32 [B, A]."""
+    def forward_bits(self, obs_bits: torch.Tensor, probs: torch.Tensor | None = None, logits: torch.Tensor | None = None,
+                     values: torch.Tensor | None = None):
+        """obs_bits int32 [B, obs_words] (BatchedEnv.observe_bits / step_bits) -> softmax action weights f32 [B, A]
+        (and the value head's output f32 [B] into `values` when given)."""
         assert obs_bits.is_cuda and obs_bits.element_size() == 4 and obs_bits.is_contiguous() and obs_bits.shape[-1] == self.obs_words
         B = obs_bits.numel() // self.obs_words
-        if probs is None and logits is None:
+        if probs is None and logits is None and values is None:
             probs = torch.empty((B, self.num_actions), dtype=torch.float32, device=obs_bits.device)
         for t in (probs, logits):
             assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == B * self.num_actions)
+        assert values is None or (self.has_value and values.dtype == torch.float32 and values.is_contiguous() and values.numel() == B)
         st = C.c_void_p(torch.cuda.current_stream(obs_bits.device).cuda_stream)
-        check(lib().qg_policy_forward_bits(self._h, _dptr(obs_bits), B, _dptr(probs), _dptr(logits), st))
-        return probs if probs is not None else logits
+        if values is None:
+            check(lib().qg_policy_forward_bits(self._h, _dptr(obs_bits), B, _dptr(probs), _dptr(logits), st))
+        else:
+            check(lib().qg_policy_forward_bits_value(self._h, _dptr(obs_bits), B, _dptr(probs), _dptr(logits), _dptr(values), st))
+        return probs if probs is not None else (logits if logits is not None else values)
 
 
 def pack_obs_bits(obs: torch.Tensor) -> torch.Tensor:

@@ -101,6 +101,20 @@ def test_fused_policy_matches_torch(obs_shape, A, emb, common, pol_layers, densi
         assert torch.allclose(logits.double(), ref_logits, rtol=1e-4, atol=2e-5), (B, (logits.double() - ref_logits).abs().max())
         assert torch.allclose(probs.double(), ref_probs, rtol=1e-4, atol=1e-6)
         assert torch.allclose(probs.sum(dim=1), torch.ones(B, device=dev), atol=1e-5)
+    if not pol_layers:
+        # the value head rides along as one more output of the last layer (qg_policy_create_value): same logits, values of the module
+        fv = FusedPolicy(pol, device=dev, with_value=True)
+        values = torch.empty(B, dtype=torch.float32, device=dev)
+        probs2 = torch.empty((B, A), dtype=torch.float32, device=dev)
+        fv.forward_bits(bits, probs=probs2, values=values)
+        with torch.no_grad():
+            _, ref_v = pol.double()(dense.to(dev).double())
+            pol.float()
+        assert torch.allclose(values.double(), ref_v.reshape(-1), rtol=1e-4, atol=2e-5), (values.double() - ref_v.reshape(-1)).abs().max()
+        assert torch.allclose(probs2.double(), ref_probs, rtol=1e-4, atol=1e-6)
+    else:
+        with pytest.raises(NotImplementedError):
+            FusedPolicy(pol, device=dev, with_value=True)
 
 
 @pytest.mark.gpu
