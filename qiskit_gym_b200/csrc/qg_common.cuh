@@ -59,6 +59,8 @@ struct DevCfg {
     const uint32_t* pgen;     // PauliNetwork reset generator tables (see k_reset_pauli)
     uint64_t seed; int64_t first_id;
     uint32_t magic_n;         // ceil(2^32 / n): exact division of obs offsets by n (Permutation expander)
+    int32_t row_shift;        // LinearFunction / Clifford: log2(D) when D is a power of two <= 32 (a row then lies inside one word at bit offset
+                              // (r << row_shift) & 31 and the row primitives are one load / shift / xor / store), else -1
 };
 
 // ---- Philox4x32-10: key = seed, counter = (env lo, env hi, draw index, stream) ----------------
@@ -107,6 +109,25 @@ template <class Wd>
 __device__ __forceinline__ uint32_t get_bit(const Wd& W, int o) { return (W[o >> 5] >> (o & 31)) & 1u; }
 
 // row primitives on a dense bit matrix whose rows are `rb` bits wide
+// ... rows that never straddle a word (rb = 1 << sh <= 32): the warp-uniform fast path of the LinearFunction / Clifford gates
+template <class Wd>
+__device__ __forceinline__ uint32_t row_get_pow2(const Wd& W, int sh, int r) {
+    const int o = r << sh;
+    const uint32_t v = W[o >> 5] >> (o & 31);
+    return sh == 5 ? v : (v & ((1u << (1 << sh)) - 1u));
+}
+template <class Wd>
+__device__ __forceinline__ void row_xor_pow2(const Wd& W, int sh, int dst, int src) {
+    const int o = dst << sh;
+    W[o >> 5] ^= row_get_pow2(W, sh, src) << (o & 31);
+}
+template <class Wd>
+__device__ __forceinline__ void row_swap_pow2(const Wd& W, int sh, int a, int b) {
+    const uint32_t d = row_get_pow2(W, sh, a) ^ row_get_pow2(W, sh, b);
+    const int oa = a << sh, ob = b << sh;
+    W[oa >> 5] ^= d << (oa & 31);
+    W[ob >> 5] ^= d << (ob & 31);              // (after the first store: a and b may share a word)
+}
 template <class Wd>
 __device__ __forceinline__ void row_xor(const Wd& W, int rb, int dst, int src) {   // row dst ^= row src (dst==src zeroes it)
     for (int c0 = 0; c0 < rb; c0 += 32) {

@@ -307,6 +307,12 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     d.qperms = (const uint8_t*)(e->ws + p.qperms); d.aperms = (const uint16_t*)(e->ws + p.aperms); d.pgen = (const uint32_t*)(e->ws + p.pgen);
     d.seed = 0; d.first_id = 0;
     d.magic_n = (uint32_t)(((1ull << 32) + (uint32_t)L.n - 1) / (uint32_t)L.n);
+    d.row_shift = -1;
+    if ((L.kind == QG_ENV_LINEAR_FUNCTION || L.kind == QG_ENV_CLIFFORD) && L.D >= 1 && L.D <= 32 && (L.D & (L.D - 1)) == 0) {
+        int sh = 0; while ((1 << sh) < L.D) ++sh;
+        d.row_shift = sh;
+    }
+    if (const char* v = std::getenv("QG_ROW_POW2")) { if (std::atoi(v) == 0) d.row_shift = -1; }      // A/B runs
     e->staged = (uint32_t*)(e->ws + p.staged);
     e->snap = (uint32_t*)(e->ws + p.snap);
     e->io_actions = (int32_t*)(e->ws + p.io_actions); e->io_coins = e->ws + p.io_coins; e->io_reward = (float*)(e->ws + p.io_reward);

@@ -103,10 +103,27 @@ __device__ __forceinline__ void apply_gate_state(const DevCfg& c, const Wd& S, i
         if (kind == QG_SWAP) { const uint32_t a = get8(S, q0), b = get8(S, q1); set8(S, q0, b); set8(S, q1, a); }
     } else if (KIND == QG_ENV_LINEAR_FUNCTION) {
         if (q0 == q1) return;
+        if (c.row_shift >= 0) {
+            if (kind == QG_CX) row_xor_pow2(S, c.row_shift, q1, q0);
+            else if (kind == QG_SWAP) row_swap_pow2(S, c.row_shift, q0, q1);
+            return;
+        }
         if (kind == QG_CX) row_xor(S, c.D, q1, q0);
         else if (kind == QG_SWAP) row_swap(S, c.D, q0, q1);
     } else if (KIND == QG_ENV_CLIFFORD) {
         const int n = c.n, D = c.D;
+        if (c.row_shift >= 0) {
+            const int sh = c.row_shift;
+            switch (kind) {
+                case QG_H: row_swap_pow2(S, sh, q0, n + q0); break;
+                case QG_S: case QG_SDG: row_xor_pow2(S, sh, n + q0, q0); break;
+                case QG_SX: case QG_SXDG: row_xor_pow2(S, sh, q0, n + q0); break;
+                case QG_CX: if (q0 != q1) { row_xor_pow2(S, sh, q1, q0); row_xor_pow2(S, sh, n + q0, n + q1); } break;
+                case QG_CZ: if (q0 != q1) { row_xor_pow2(S, sh, n + q0, q1); row_xor_pow2(S, sh, n + q1, q0); } break;
+                case QG_SWAP: if (q0 != q1) { row_swap_pow2(S, sh, q0, q1); row_swap_pow2(S, sh, n + q0, n + q1); } break;
+            }
+            return;
+        }
         switch (kind) {
             case QG_H: row_swap(S, D, q0, n + q0); break;
             case QG_S: case QG_SDG: row_xor(S, D, n + q0, q0); break;
@@ -125,8 +142,9 @@ __device__ __forceinline__ bool solved_state(const DevCfg& c, const Wd& S) {
         for (int i = 0; i < c.n; ++i) if (get8(S, i) != (uint32_t)i) return false;
         return true;
     } else {
+        if (S[0] != __ldg(c.ident)) return false;          // the usual case ends here (a scrambled state rarely shares its first word with the identity)
         uint32_t diff = 0;
-        for (int w = 0; w < c.SW; ++w) diff |= S[w] ^ __ldg(c.ident + w);
+        for (int w = 1; w < c.SW; ++w) diff |= S[w] ^ __ldg(c.ident + w);
         return diff == 0;
     }
 }
