@@ -74,31 +74,30 @@ def decode_key(key: int):
 
 
 def reduce_best(local_key: int, local_solution, group=None, device=None):
-    """Cross-rank best-rollout reduction: int64 MAX all-reduce of the packed key, then the owner of the winning
-    rollout broadcasts its action list.  Works with any torch.distributed backend (NCCL on GPUs, gloo in tests)."""
+    """Cross-rank best-rollout reduction in two collectives: an all-gather of (packed key, solution length) — the owner of the winning
+    rollout is the rank holding the largest key; keys are unique, they embed the global rollout id — then the owner broadcasts its action
+    list.  Works with any torch.distributed backend (NCCL on GPUs, gloo in tests)."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_key, local_solution
     dev = device if device is not None else torch.device("cpu")
-    k = torch.tensor([local_key], dtype=torch.int64, device=dev)
-    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
-    best = int(k.item())
-    # the owner is the (unique) rank whose local key equals the global best
-    mine = 1 if (best == local_key and best != 0) else 0
-    owner = torch.tensor([dist.get_rank(group) if mine else -1], dtype=torch.int64, device=dev)
-    dist.all_reduce(owner, op=dist.ReduceOp.MAX, group=group)
-    src = int(owner.item())
-    if src < 0:
-        return best, None
-    sol = local_solution if (mine and local_solution is not None) else []
-    n = torch.tensor([len(sol) if dist.get_rank(group) == src else 0], dtype=torch.int64, device=dev)
-    dist.broadcast(n, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
-    buf = torch.zeros(int(n.item()), dtype=torch.int64, device=dev)
-    if dist.get_rank(group) == src:
-        buf.copy_(torch.tensor(sol, dtype=torch.int64))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sol = list(local_solution) if local_solution is not None else []
+    mine = torch.tensor([local_key, len(sol)], dtype=torch.int64, device=dev)
+    allk = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allk, mine, group=group) if dev.type == "cuda" else dist.all_gather(list(allk.unbind(0)), mine, group=group)
+    table = allk.tolist()
+    best = max(k for k, _ in table)
+    if best == 0:
+        return 0, None
+    src = next(r for r, (k, _) in enumerate(table) if k == best)       # (the lowest rank on the impossible tie)
+    n = int(table[src][1])
+    buf = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+    if rank == src and n:
+        buf[:n] = torch.tensor(sol, dtype=torch.int64)
     dist.broadcast(buf, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
-    return best, [int(v) for v in buf.tolist()]
+    return best, [int(v) for v in buf[:n].tolist()]
 
 
 class RolloutSearch:
