@@ -20,6 +20,13 @@ def config_table():
     add("clifford3_allgates", CLIFF, line_edges(3), ALL_GATES)
     add("clifford5_allgates", CLIFF, line_edges(5), ALL_GATES)
     add("clifford20_line", CLIFF, line_edges(20), ("H", "S", "SX", "CX", "CZ", "SWAP"))
+    # power-of-two row widths (the one-word row fast path of the LinearFunction / Clifford gates), every gate kind
+    add("lf4_swap", LF, line_edges(4), ("CX", "SWAP"))
+    add("lf8_swap", LF, line_edges(8), ("CX", "SWAP"))
+    add("lf32_line", LF, line_edges(32), ("CX", "SWAP"))
+    add("clifford4_allgates", CLIFF, line_edges(4), ALL_GATES)
+    add("clifford8_allgates", CLIFF, line_edges(8), ALL_GATES)
+    add("clifford16_allgates", CLIFF, line_edges(16), ALL_GATES)
     add("pauli3_line", PAULI, line_edges(3), ALL_GATES, max_rotations=3)
     add("pauli6_line", PAULI, line_edges(6), ALL_GATES, max_rotations=4, final_pauli_layers=8)
     t["perm5_mixed"] = (PERM, 5, [("SWAP", (0, 1)), ("H", (2,)), ("CX", (1, 2)), ("SWAP", (3, 4)), ("SWAP", (2, 3)), ("CZ", (0, 4))], {})

@@ -223,6 +223,14 @@ def test_step_host_pinned_and_pageable(pinned):
         assert np.array_equal(env.obs.reshape(B, -1).cpu().numpy().astype(np.uint8), ref["obs"][t])
 
 
+@pytest.mark.parametrize("name", ["lf4_swap", "lf8_swap", "lf32_line", "clifford4_allgates", "clifford8_allgates", "clifford16_allgates"])
+@pytest.mark.parametrize("inv", [False, True])
+def test_step_parity_power_of_two_rows(name, inv):
+    """Row widths 4 .. 32 (a row inside one word: row_xor_pow2 / row_swap_pow2) with every gate kind, single steps and replay."""
+    run_parity(name, B=130, T=30, add_inverts=inv, seed=9)
+    run_replay_parity(name, B=70, T=24, add_inverts=inv, seed=10)
+
+
 @pytest.mark.parametrize("name", ["clifford20_line", "lf40_line"])
 def test_step_parity_wide_rows(name):
     run_parity(name, B=70, T=24, add_inverts=True, seed=5)
