@@ -113,15 +113,27 @@ __device__ __forceinline__ void apply_gate_state(const DevCfg& c, const Wd& S, i
     } else if (KIND == QG_ENV_CLIFFORD) {
         const int n = c.n, D = c.D;
         if (c.row_shift >= 0) {
+            // every gate is at most two row operations  A ^= B  or  A <-> B  on disjoint row pairs; written with selects so that a warp
+            // whose lanes hold different gate kinds runs ONE routine instead of one switch arm per kind:
+            //   H: q <-> n+q        S/Sdg: n+q ^= q        SX/SXdg: q ^= n+q
+            //   CX: t ^= c, n+c ^= n+t        CZ: n+a ^= b, n+b ^= a        SWAP: a <-> b, n+a <-> n+b
             const int sh = c.row_shift;
-            switch (kind) {
-                case QG_H: row_swap_pow2(S, sh, q0, n + q0); break;
-                case QG_S: case QG_SDG: row_xor_pow2(S, sh, n + q0, q0); break;
-                case QG_SX: case QG_SXDG: row_xor_pow2(S, sh, q0, n + q0); break;
-                case QG_CX: if (q0 != q1) { row_xor_pow2(S, sh, q1, q0); row_xor_pow2(S, sh, n + q0, n + q1); } break;
-                case QG_CZ: if (q0 != q1) { row_xor_pow2(S, sh, n + q0, q1); row_xor_pow2(S, sh, n + q1, q0); } break;
-                case QG_SWAP: if (q0 != q1) { row_swap_pow2(S, sh, q0, q1); row_swap_pow2(S, sh, n + q0, n + q1); } break;
-            }
+            const bool two = kind >= QG_CX, swp = kind == QG_H || kind == QG_SWAP, en = !two || q0 != q1;
+            const bool sx = kind == QG_SX || kind == QG_SXDG;
+            int A0, B0, A1, B1;
+            if (!two) { A0 = (kind == QG_H || sx) ? q0 : n + q0; B0 = (kind == QG_H || sx) ? n + q0 : q0; A1 = B1 = 0; }
+            else if (kind == QG_CX) { A0 = q1; B0 = q0; A1 = n + q0; B1 = n + q1; }
+            else if (kind == QG_CZ) { A0 = n + q0; B0 = q1; A1 = n + q1; B1 = q0; }
+            else { A0 = q0; B0 = q1; A1 = n + q0; B1 = n + q1; }
+            const uint32_t ra0 = row_get_pow2(S, sh, A0), rb0 = row_get_pow2(S, sh, B0);
+            const uint32_t ra1 = row_get_pow2(S, sh, A1), rb1 = row_get_pow2(S, sh, B1);
+            const uint32_t d0 = ra0 ^ rb0, d1 = ra1 ^ rb1;
+            const uint32_t xa0 = en ? (swp ? d0 : rb0) : 0u, xb0 = (en && swp) ? d0 : 0u;
+            const uint32_t xa1 = (en && two) ? (swp ? d1 : rb1) : 0u, xb1 = (en && two && swp) ? d1 : 0u;
+            { const int o = A0 << sh; S[o >> 5] ^= xa0 << (o & 31); }
+            { const int o = B0 << sh; S[o >> 5] ^= xb0 << (o & 31); }
+            { const int o = A1 << sh; S[o >> 5] ^= xa1 << (o & 31); }
+            { const int o = B1 << sh; S[o >> 5] ^= xb1 << (o & 31); }
             return;
         }
         switch (kind) {
