@@ -1,7 +1,3 @@
-    // replay stagger (warp k of an SM starting k slab-times late so that the warps do not alternate between the step logic and the
-    // expansion in lock-step): measured on the final kernel, 1.600 ms with it and 1.594 ms without (65 536 envs): off unless asked for
-    e->stagger_ns = 0;
-    if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
 // qg_engine.cu — implementation of the C ABI declared in include/qg_engine.h.
 #include <algorithm>
 #include <cstdio>
@@ -270,11 +266,10 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     if (const char* v = std::getenv("QG_INV_REG")) e->inv_bucket_enabled = std::atoi(v) != 0;
     if (const char* v = std::getenv("QG_INV_SYMPLECTIC")) e->all_symplectic = std::atoi(v) != 0;   // 0: never use the transpose shortcut
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
-    {   // replay stagger: the time one warp's observation + mask slab takes at the SM's share of the write bandwidth
-        const double slab = 32.0 * (4.0 * L.obs_size + L.A + 6.0), sm_bw = 6.6e12 / e->num_sms;
-        e->stagger_ns = (int)(slab / sm_bw * 1e9);
-        if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
-    }
+    // replay stagger (warp k of an SM starting k slab-times late so that the warps do not alternate between the step logic and the
+    // expansion in lock-step): measured on the final kernel, 1.600 ms with it and 1.594 ms without (65 536 envs): off unless asked for
+    e->stagger_ns = 0;
+    if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
     std::vector<uint32_t> pg;
     if (cfg->env_kind == QG_ENV_PAULI_NETWORK) pauli_gen_tables(cfg, pg);
     const WsPlan p = plan_ws(L, batch, e->nperms, (int64_t)pg.size());
