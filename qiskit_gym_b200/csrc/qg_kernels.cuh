@@ -112,19 +112,19 @@ __device__ __forceinline__ void apply_gate_state(const DevCfg& c, const Wd& S, i
         else if (kind == QG_SWAP) row_swap(S, c.D, q0, q1);
     } else if (KIND == QG_ENV_CLIFFORD) {
         const int n = c.n, D = c.D;
+        // every gate is at most two row operations  A ^= B  or  A <-> B  on disjoint row pairs; written with selects so that a warp
+        // whose lanes hold different gate kinds runs ONE routine instead of one switch arm per kind:
+        //   H: q <-> n+q        S/Sdg: n+q ^= q        SX/SXdg: q ^= n+q
+        //   CX: t ^= c, n+c ^= n+t        CZ: n+a ^= b, n+b ^= a        SWAP: a <-> b, n+a <-> n+b
+        const bool two = kind >= QG_CX, swp = kind == QG_H || kind == QG_SWAP, en = !two || q0 != q1;
+        const bool sx = kind == QG_SX || kind == QG_SXDG;
+        int A0, B0, A1, B1;
+        if (!two) { A0 = (kind == QG_H || sx) ? q0 : n + q0; B0 = (kind == QG_H || sx) ? n + q0 : q0; A1 = B1 = 0; }
+        else if (kind == QG_CX) { A0 = q1; B0 = q0; A1 = n + q0; B1 = n + q1; }
+        else if (kind == QG_CZ) { A0 = n + q0; B0 = q1; A1 = n + q1; B1 = q0; }
+        else { A0 = q0; B0 = q1; A1 = n + q0; B1 = n + q1; }
         if (c.row_shift >= 0) {
-            // every gate is at most two row operations  A ^= B  or  A <-> B  on disjoint row pairs; written with selects so that a warp
-            // whose lanes hold different gate kinds runs ONE routine instead of one switch arm per kind:
-            //   H: q <-> n+q        S/Sdg: n+q ^= q        SX/SXdg: q ^= n+q
-            //   CX: t ^= c, n+c ^= n+t        CZ: n+a ^= b, n+b ^= a        SWAP: a <-> b, n+a <-> n+b
             const int sh = c.row_shift;
-            const bool two = kind >= QG_CX, swp = kind == QG_H || kind == QG_SWAP, en = !two || q0 != q1;
-            const bool sx = kind == QG_SX || kind == QG_SXDG;
-            int A0, B0, A1, B1;
-            if (!two) { A0 = (kind == QG_H || sx) ? q0 : n + q0; B0 = (kind == QG_H || sx) ? n + q0 : q0; A1 = B1 = 0; }
-            else if (kind == QG_CX) { A0 = q1; B0 = q0; A1 = n + q0; B1 = n + q1; }
-            else if (kind == QG_CZ) { A0 = n + q0; B0 = q1; A1 = n + q1; B1 = q0; }
-            else { A0 = q0; B0 = q1; A1 = n + q0; B1 = n + q1; }
             const uint32_t ra0 = row_get_pow2(S, sh, A0), rb0 = row_get_pow2(S, sh, B0);
             const uint32_t ra1 = row_get_pow2(S, sh, A1), rb1 = row_get_pow2(S, sh, B1);
             const uint32_t d0 = ra0 ^ rb0, d1 = ra1 ^ rb1;
@@ -136,14 +136,17 @@ __device__ __forceinline__ void apply_gate_state(const DevCfg& c, const Wd& S, i
             { const int o = B1 << sh; S[o >> 5] ^= xb1 << (o & 31); }
             return;
         }
-        switch (kind) {
-            case QG_H: row_swap(S, D, q0, n + q0); break;
-            case QG_S: case QG_SDG: row_xor(S, D, n + q0, q0); break;
-            case QG_SX: case QG_SXDG: row_xor(S, D, q0, n + q0); break;
-            case QG_CX: if (q0 != q1) { row_xor(S, D, q1, q0); row_xor(S, D, n + q0, n + q1); } break;
-            case QG_CZ: if (q0 != q1) { row_xor(S, D, n + q0, q1); row_xor(S, D, n + q1, q0); } break;
-            case QG_SWAP: if (q0 != q1) { row_swap(S, D, q0, q1); row_swap(S, D, n + q0, n + q1); } break;
-        }
+        // rows of any width (they may straddle words): the same two operations, 32 bits of a row at a time
+        auto row_op = [&](int A, int B, bool on) {
+            for (int c0 = 0; c0 < D; c0 += 32) {
+                const int len = min(32, D - c0);
+                const uint32_t rb = get_bits(S, B * D + c0, len), d = get_bits(S, A * D + c0, len) ^ rb;
+                xor_bits(S, A * D + c0, len, on ? (swp ? d : rb) : 0u);
+                xor_bits(S, B * D + c0, len, (on && swp) ? d : 0u);
+            }
+        };
+        row_op(A0, B0, en);
+        row_op(A1, B1, en && two);
     }
 }
 
