@@ -36,9 +36,9 @@ STATE_BYTES = {"C1_perm_grid3": 104, "C2_lf8_line": 96, "C3_clifford8_full": 144
 # dram__bytes_read.sum + dram__bytes_write.sum of one replay launch, from the committed ncu --set full capture (profiles/), keyed by
 # (config, envs per GPU, env-steps per launch); None where no capture exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r1_v25_clifford8_ncu_full.txt: 39.8 MB read + 8 999.1 MB written by one k_step<2,0> nsteps=128 launch (the launch's last
+    # profiles/r1_v28_clifford8_ncu_full.txt: 39.7 MB read + 9 009.3 MB written by one k_step<2,0> nsteps=128 launch (the launch's last
     # ~0.1-0.2 GB of dirty lines are still in the 126 MB L2 when the counters stop, hence slightly below the algorithmic 9.28 GB)
-    ("C3_clifford8_full", 65536, 128): 39777024 + 8999081000,
+    ("C3_clifford8_full", 65536, 128): 39720448 + 9009255000,
 }
 METRIC = "batched env-steps/sec (CliffordGym 8q all-to-all {H,S,CX})"
 UNIT = "env-steps/s"
