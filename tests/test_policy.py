@@ -176,3 +176,32 @@ def test_persistent_search_equals_two_kernel_search(name, deterministic, inverts
     assert np.array_equal(a[2], b[2])
     assert all(np.array_equal(x, y) for x, y in zip(a[3], b[3]))
     assert np.array_equal(a[4], b[4])
+
+
+def test_fixed_point_first_layer_is_at_least_as_accurate_as_f32():
+    """The first layer's arithmetic (qg_policy.cu: weights -> int32 with the largest |weight| just below 2^30, int64 sums, one rounding to
+    f32, f32 bias add), restated with numpy: against the exact (float64) sum its error is below that of a sequential float32 sum of the
+    same terms, for trained-looking and for badly scaled weights."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    for scale, obs, width, density in ((0.05, 729, 512, 0.04), (1.0, 256, 512, 0.5), (30.0, 500, 300, 0.3), (1e-3, 64, 64, 0.5)):
+        w = (rng.standard_normal((obs, width)) * scale).astype(np.float32)
+        w[0, 0] = np.float32(8.0 * scale)                                   # an outlier sets the fixed-point scale
+        bias = (rng.standard_normal(width) * scale).astype(np.float32)
+        mx = float(np.abs(w).max())
+        shift = min(30 - int(np.frexp(mx)[1]), 120)
+        q = np.rint(np.ldexp(w.astype(np.float64), shift)).astype(np.int64)
+        assert np.abs(q).max() < 2**30
+        err_fixed, err_f32 = [], []
+        for _ in range(8):
+            on = rng.random(obs) < density
+            exact = w[on].astype(np.float64).sum(axis=0) + bias.astype(np.float64)
+            acc = q[on].sum(axis=0)                                          # exact integers, any order
+            fixed = (np.float32(acc.astype(np.float64)) * np.float32(np.ldexp(1.0, -shift))).astype(np.float32) + bias
+            seq = np.zeros(width, np.float32)
+            for row in w[on]:
+                seq = (seq + row).astype(np.float32)
+            seq = (seq + bias).astype(np.float32)
+            err_fixed.append(np.abs(fixed.astype(np.float64) - exact).max())
+            err_f32.append(np.abs(seq.astype(np.float64) - exact).max())
+        assert max(err_fixed) <= max(err_f32) * 1.01 + 1e-12, (scale, max(err_fixed), max(err_f32))
+        assert max(err_fixed) <= 2e-5 * max(1.0, mx * 8)
