@@ -782,7 +782,6 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
     if (pol->d.obs_size != e->L.obs_size || pol->d.num_actions != e->L.A) { set_error("qg_search_run: the policy's observation size / action count do not match the env"); return QG_ERR_INVALID; }
     if (e->L.kind == QG_ENV_PERMUTATION && e->L.OW == 0) { set_error("packed observations need num_qubits <= 64 for Permutation"); return QG_ERR_UNSUPPORTED; }
     if (max_decisions < 0) { set_error("qg_search_run: negative decision budget"); return QG_ERR_INVALID; }
-    if (e->B == 0 || max_decisions == 0) return QG_OK;
     CUDA_OK(cudaSetDevice(e->device));
     StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic;      // (no packed-observation output: the kernel keeps the bit stream on chip)
     a.nsteps = 1; a.ring = 1; a.pdl_mode = 0; a.num_sms = e->num_sms;
@@ -791,6 +790,7 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
     a.magic_ow = magic40(((uint32_t)e->L.obs_size + 31u) / 32u);
     const size_t step_smem = (size_t)e->sm_warp_words * 4 + 16;
     if (policy_smem_bytes(pol->d) + step_smem > 220 * 1024) { set_error("qg_search_run: policy + env do not fit one SM's shared memory"); return QG_ERR_UNSUPPORTED; }
+    if (e->B == 0 || max_decisions == 0) return QG_OK;          // (after every support check: a zero-decision call is the caller's probe)
     cudaStream_t st = (cudaStream_t)stream;
     // the policy's first-layer accumulators, one set per CTA of 8 rollouts (grown on first use; a launch in flight on another stream
     // with the same policy handle must not overlap a growing call: one host thread per handle, like the engine)

@@ -29,6 +29,7 @@ class _RawEnv:
         self._act = torch.zeros(1, dtype=torch.int32, device=self._env.device)
         self._coin = torch.zeros(1, dtype=torch.uint8, device=self._env.device)
         self._needs_coin = bool(self._env.cfg.add_inverts)
+        self._perm_raw = torch.zeros(1, dtype=torch.int32, device=self._env.device)      # bit pattern of the uint32 draw
 
     # ---- Env trait surface -------------------------------------------------------------
     def obs_shape(self):
@@ -70,7 +71,12 @@ class _RawEnv:
         self._env.step(self._act, coins=coins, obs=False, mask=False)
 
     def observe(self):
-        obs = self._env.observe()
+        perm_raw = None
+        if self._KIND == _abi.ENV_PAULI_NETWORK and self._env.cfg.add_perms:
+            # pauli.rs:656-660 draws a fresh qubit permutation from thread_rng on every observe(): the raw 32-bit draw comes from the OS
+            self._perm_raw.fill_(int.from_bytes(os.urandom(4), "little") - (1 << 31))
+            perm_raw = self._perm_raw
+        obs = self._env.observe(perm_raw=perm_raw)
         return torch.nonzero(obs.reshape(-1), as_tuple=False).reshape(-1).tolist()
 
     def masks(self):

@@ -378,6 +378,7 @@ class AlphaZero(Trainer):
         ms.policy = self.policy.eval()
         dev, A = self.device, env.num_actions()
         obs_buf = torch.empty((T, B) + tuple(env.obs_shape()), dtype=torch.float32, device=dev)
+        self._bit_shifts = torch.arange(32, dtype=torch.int32, device=dev)
         pi = torch.zeros((T, B, A), dtype=torch.float32, device=dev)
         actions = torch.full((T, B), -1, dtype=torch.int32, device=dev)
         rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
@@ -386,8 +387,15 @@ class AlphaZero(Trainer):
         for t in range(T):
             s = decision_seed(self.seed + 104729 * self.rank, self.counter)
             env.reset_select(s, self.rank * B)
-            w = ms.decide(t)                         # observes into env.obs, grows the trees, leaves N(a) / sum N in ms.weights
-            obs_buf[t].copy_(env.obs)
+            w = ms.decide(t)                         # grows the trees from the root observation, leaves N(a) / sum N in ms.weights
+            if ms.backend == "fused":
+                # the fused backend observes into packed bits only (ms.root_bits): the training sample is what the root evaluation saw
+                # (for PauliNetwork with add_perms that includes the qubit permutation observe() picked)
+                bits = ms.root_bits.reshape(B, -1)
+                dense = ((bits.unsqueeze(-1) >> self._bit_shifts) & 1).reshape(B, -1)[:, :obs_buf[t].numel() // B]
+                obs_buf[t].copy_(dense.reshape(obs_buf[t].shape))
+            else:
+                obs_buf[t].copy_(env.obs)
             pi[t].copy_(w)
             env.collect_step(w, s, deterministic=False, obs=False, chosen=actions[t], reward=rewards[t], done=dones[t], success=succ[t])
             self.counter += 1

@@ -16,8 +16,8 @@ import json
 
 import torch
 
-from . import gyms
 from .search import BasicPolicy, RolloutSearch
+from .specs import SynthSpec
 
 _ENV_KINDS = {"PermutationEnv": 0, "LinearFunctionEnv": 1, "CliffordEnv": 2, "PauliNetworkEnv": 3}
 
@@ -55,9 +55,7 @@ class RLSynthesis:
     def from_config_json(cls, config_path, model_path=None, device=None):
         """rl/synthesis.py:54-77: `{env_cls, env, policy_cls, policy, algorithm_cls, algorithm}`."""
         full = json.load(open(config_path))
-        env_cls = full["env_cls"].split(".")[-1]
-        assert env_cls in gyms.SYNTH_ENVS, f"Synth env class {full['env_cls']} not supported, should be {list(gyms.SYNTH_ENVS.keys())}"
-        env = gyms.SYNTH_ENVS[env_cls].from_json(full["env"])
+        env = SynthSpec.from_json(full["env_cls"], full["env"])      # Qiskit-free problem spec (specs.py); a reference *Gym object works too
         return cls(env, full.get("algorithm"), full.get("policy"), model_path, device=device,
                    policy_cls=full.get("policy_cls", "twisterl.nn.BasicPolicy"), algorithm_cls=full.get("algorithm_cls", "twisterl.rl.PPO"))
 
@@ -84,13 +82,25 @@ class RLSynthesis:
 
     # ---- synthesis ------------------------------------------------------------------------------------
     def _search(self, num_searches: int) -> RolloutSearch:
+        from .policy import weights_version
         rs = self._searches.get(num_searches)
+        if rs is not None and getattr(rs, "fused", None) is not None and rs.fused.version != weights_version(self.policy):
+            rs = None                                    # the cached search captured older weights (load_state_dict after the first synth)
         if rs is None:
             cfg = dict(self.env_config)
             kind = _ENV_KINDS[self.env.cls_name]
             kw = {k: v for k, v in cfg.items() if k not in ("num_qubits", "gateset", "max_depth", "add_perms")}
-            rs = RolloutSearch(kind, cfg["num_qubits"], cfg["gateset"], self.policy, num_searches, device=self.device,
-                               max_depth=cfg.get("max_depth", 128), add_perms=False, **kw)
+
+            def make(backend):
+                return RolloutSearch(kind, cfg["num_qubits"], cfg["gateset"], self.policy, num_searches, device=self.device,
+                                     max_depth=cfg.get("max_depth", 128), add_perms=False, policy_backend=backend, **kw)
+            try:
+                rs = make("persistent")
+                rs.check_supported()
+            except NotImplementedError:
+                # outside the one-launch search's limits (Permutation wider than 64 qubits, a layer wider than 1024, policy + env larger
+                # than one SM's shared memory): the PyTorch policy on dense observations has none of them
+                rs = make("torch")
             self._searches[num_searches] = rs
         return rs
 
@@ -135,8 +145,13 @@ class RLSynthesis:
         kind = _ENV_KINDS[self.env.cls_name]
         kw = {k: v for k, v in cfg.items() if k not in ("num_qubits", "gateset")}
         trainer = (ppo.PPO if algo == "PPO" else ppo.AlphaZero)(kind, cfg["num_qubits"], cfg["gateset"], self.policy, self.rl_config, device=self.device, seed=seed, **kw)
+        if hasattr(self.env, "difficulty"):
+            self.env.difficulty = initial_difficulty                # rl/synthesis.py:129 (a reference *Gym object; a SynthSpec owns no env)
         try:
             return trainer.learn(initial_difficulty=initial_difficulty, num_iterations=num_iterations, tb_path=tb_path, log=log)
+        except KeyboardInterrupt:
+            # rl/synthesis.py:137-139: stopping a run by hand keeps the policy trained so far (metrics.jsonl under tb_path holds the history)
+            return getattr(trainer, "history", None)
         finally:
             self.policy = trainer.policy.eval()
             self._searches = {}

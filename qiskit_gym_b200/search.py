@@ -128,6 +128,12 @@ class RolloutSearch:
         self._stream = torch.cuda.Stream(device=dev)
         self._decisions = torch.zeros((self.B + 7) // 8, dtype=torch.int32, device=dev)
 
+    def check_supported(self):
+        """Raises NotImplementedError (QG_ERR_UNSUPPORTED) now rather than in the first solve() when the one-launch search cannot run
+        this env / policy pair: a zero-decision qg_search_run goes through all of its checks without launching anything."""
+        if self.backend == "persistent":
+            self.env.search_run(self.fused, self.obs_bits, self.probs, 0, deterministic=True, decisions=self._decisions)
+
     def _iteration(self, deterministic):
         if self.backend == "fused":
             self.fused.forward_bits(self.obs_bits, probs=self.probs)

@@ -1,5 +1,6 @@
-"""Gymnasium-facing wrappers (gyms.py) and RLSynthesis (rl.py) on the GPU, driven with the reference's own trained
-checkpoints (tests/golden/models = /root/reference/examples/models)."""
+"""RLSynthesis (rl.py) over problem specs (specs.SynthSpec) on the GPU, driven with the reference's own trained checkpoints
+(tests/golden/models = /root/reference/examples/models).  The Gymnasium wrapper contract is covered by tests/test_reference_python.py,
+which runs the reference's own adapters.py."""
 import json
 import os
 
@@ -13,41 +14,6 @@ from tests.test_wire import random_gates, unitary
 
 pytestmark = pytest.mark.gpu
 MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models")
-
-
-def test_gym_wrapper_contract():
-    """adapters.py:36-105: spaces, dense int8 observation, (obs, reward, terminated, truncated, info), final-state assertion,
-    attribute forwarding and `difficulty` propagation — on the LinearFunction walk-through of the reference notebook."""
-    from qiskit_gym_b200 import gyms
-    k = json.load(open(os.path.join(os.path.dirname(MODELS), "notebook_kats.json")))
-    gs = [(g, tuple(q)) for g, q in k["lf3_gateset"]]
-    edges = sorted({q for _, q in gs})
-    env = gyms.LinearFunctionGym.from_coupling_map(edges, basis_gates=("CX", "SWAP"), add_inverts=False, add_perms=False)
-    assert type(env).__name__ == "LinearFunctionGym" and env.cls_name == "LinearFunctionEnv"
-    assert env.config["gateset"] == gs
-    assert env.observation_space.shape == (3, 3) and env.action_space.n == env.num_actions()
-    assert env.to_json()["num_qubits"] == 3
-    env.difficulty = 5
-    assert env._raw_env.difficulty == 5 and env.difficulty == 5
-    obs, info = env.reset(seed=1)
-    assert obs.shape == (3, 3) and obs.dtype == np.int8 and info == {}
-    ref = orc.OracleEnv(H.LF, 3, env.config["gateset"], add_inverts=False, add_perms=False)
-    start = [1, 1, 0, 0, 1, 0, 0, 1, 1]
-    env.set_state(start); ref.set_state(start)
-    for a in (0, 5, 2, 1, 7, 3):
-        if ref.is_final():
-            break
-        obs, r, term, trunc, info = env.step(a)
-        ref.step(a)
-        want = np.zeros(9, dtype=np.int8); want[ref.observe()] = 1
-        assert np.array_equal(obs.reshape(-1), want) and trunc is False and info == {}
-        assert np.float32(r).view(np.uint32) == np.float32(ref.reward()).view(np.uint32) and term == ref.is_final()
-    env.set_state([1, 0, 0, 0, 1, 0, 0, 0, 1])
-    assert env.is_final()
-    with pytest.raises(AssertionError):
-        env.step(0)
-    env2 = gyms.LinearFunctionGym.from_json(env.to_json())
-    assert env2.config == env.config
 
 
 @pytest.mark.parametrize("name", ["perm_square_3x3", "lf_5_line", "clifford_3q_custom"])

@@ -1,4 +1,4 @@
-"""Wire formats either side of the hot path (qiskit_gym_b200/wire.py, gyms.py), CPU only.
+"""Wire formats either side of the hot path (qiskit_gym_b200/wire.py, specs.py), CPU only.
 
 The encoders are checked against the oracle's env semantics (a target encoded with get_state and then driven with the
 target's own gates must end in the solved state — that is what makes the synthesised circuit equal the target, reference
@@ -232,27 +232,18 @@ def test_pauli_network_state_layout():
 
 def test_from_coupling_map_orders_match_the_notebook():
     """gateset orderings printed by the reference notebook (tests/golden/notebook_kats.json)."""
-    from qiskit_gym_b200 import gyms
+    from qiskit_gym_b200.specs import SynthSpec
     k = json.load(open(os.path.join(GOLD, "notebook_kats.json")))
-
-    class Probe(gyms.BaseSynthesisEnv):
-        allowed_gates = ["CX", "SWAP"]
-
-        def __init__(self, num_qubits, gateset, difficulty=1, depth_slope=2, max_depth=128, add_inverts=True):
-            self.kw = dict(num_qubits=num_qubits, gateset=gateset, difficulty=difficulty, depth_slope=depth_slope, max_depth=max_depth,
-                           add_inverts=add_inverts)
-
-        def get_state(self, input):
-            return input
-
     want = [(g, tuple(q)) for g, q in k["perm_grid3_gateset"]]
-    p = Probe.from_coupling_map(H.W.GRID3, basis_gates=("SWAP",), difficulty=3, metrics_weights={"n_cnots": 1.0})
-    assert p.kw["gateset"] == want and p.kw["num_qubits"] == 9 and p.kw["difficulty"] == 3
+    p = SynthSpec.from_coupling_map("PermutationEnv", H.W.GRID3, basis_gates=("SWAP",), difficulty=3, metrics_weights={"n_cnots": 1.0})
+    assert p.config["gateset"] == want and p.config["num_qubits"] == 9 and p.config["difficulty"] == 3
+    assert p.obs_shape() == [9, 9] and p.num_actions() == 12 and p.cls_name == "PermutationEnv"
     want = [(g, tuple(q)) for g, q in k["lf3_gateset"]]
     edges = sorted({tuple(q) for _, q in want})
-    assert Probe.from_coupling_map(edges, basis_gates=tuple(dict.fromkeys(g for g, _ in want))).kw["gateset"] == want
-    with pytest.raises(AssertionError):
-        Probe.from_coupling_map(edges, basis_gates=("H",))
-    assert Probe.from_json({"num_qubits": 2, "gateset": [("CX", (0, 1))], "bogus": 1}).kw["num_qubits"] == 2
-    assert set(gyms.SYNTH_ENVS) == {"CliffordEnv", "LinearFunctionEnv", "PermutationEnv", "PauliNetworkEnv"}
-    assert gyms.SYNTH_ENVS["PauliNetworkEnv"].allowed_gates == wire.ONE_Q_GATES + wire.TWO_Q_GATES
+    assert SynthSpec.from_coupling_map("LinearFunctionEnv", edges, basis_gates=tuple(dict.fromkeys(g for g, _ in want))).config["gateset"] == want
+    with pytest.raises(ValueError):
+        SynthSpec.from_coupling_map("LinearFunctionEnv", edges, basis_gates=("H",))
+    with pytest.raises(ValueError):
+        SynthSpec("BogusEnv", {"num_qubits": 2, "gateset": [("CX", (0, 1))]})
+    again = SynthSpec.from_json("qiskit_gym.envs.synthesis.LinearFunctionEnv", {"num_qubits": 2, "gateset": [["CX", [0, 1]]], "bogus": 1})
+    assert again.config["num_qubits"] == 2 and again.obs_shape() == [2, 2]

@@ -8,7 +8,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from qiskit_gym_b200 import gyms  # noqa: E402
+from qiskit_gym_b200.specs import SynthSpec  # noqa: E402
 from qiskit_gym_b200.rl import RLSynthesis  # noqa: E402
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -21,12 +21,12 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 line4 = [(0, 1), (1, 2), (2, 3)]
 both = line4 + [(b, a) for a, b in line4]
 if which == "perm4":
-    env = gyms.PermutationGym.from_coupling_map(line4, difficulty=1, depth_slope=2, max_depth=32)
+    env = SynthSpec.from_coupling_map("PermutationEnv", line4, difficulty=1, depth_slope=2, max_depth=32)
 elif which == "lf4":
-    env = gyms.LinearFunctionGym.from_coupling_map(both, basis_gates=("CX",), difficulty=1, depth_slope=2, max_depth=64)
+    env = SynthSpec.from_coupling_map("LinearFunctionEnv", both, basis_gates=("CX",), difficulty=1, depth_slope=2, max_depth=64)
 else:
     tri = [(0, 1), (1, 0), (1, 2), (2, 1)]
-    env = gyms.CliffordGym.from_coupling_map(tri, basis_gates=("H", "S", "CX"), difficulty=1, depth_slope=2, max_depth=64)
+    env = SynthSpec.from_coupling_map("CliffordEnv", tri, basis_gates=("H", "S", "CX"), difficulty=1, depth_slope=2, max_depth=64)
 torch.manual_seed(0)
 cfg = {"collecting": {"num_episodes": int(os.environ.get("EPISODES", 512))}, "training": {"num_epochs": 4}, "optimizer": {"lr": float(os.environ.get("LR", 2e-3))},
        "learning": {"diff_max": 32}, "evals": {"ppo_deterministic": {"num_episodes": 128}, "ppo_10": {"num_episodes": 128, "deterministic": False, "num_searches": 10}}}
