@@ -36,9 +36,13 @@ STATE_BYTES = {"C1_perm_grid3": 104, "C2_lf8_line": 96, "C3_clifford8_full": 144
 # dram__bytes_read.sum + dram__bytes_write.sum of one replay launch, from the committed ncu --set full capture (profiles/), keyed by
 # (config, envs per GPU, env-steps per launch); None where no capture exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r1_v28_clifford8_ncu_full.txt: 39.7 MB read + 9 009.3 MB written by one k_step<2,0> nsteps=128 launch (the launch's last
-    # ~0.1-0.2 GB of dirty lines are still in the 126 MB L2 when the counters stop, hence slightly below the algorithmic 9.28 GB)
-    ("C3_clifford8_full", 65536, 128): 39720448 + 9009255000,
+    # profiles/r2_v0_ncu_configs.txt (one k_step nsteps=128 replay launch per config, 65 536 envs): read + written.  The launch's last
+    # ~0.1-0.2 GB of dirty lines are still in the 126 MB L2 when the counters stop, hence slightly below the algorithmic bytes.
+    ("C1_perm_grid3", 65536, 128): 38928384 + 2848343000,
+    ("C2_lf8_line", 65536, 128): 38083584 + 2292807000,
+    ("C3_clifford8_full", 65536, 128): 39889408 + 8994898000,
+    ("C4_pauli10_line", 65536, 128): 45969664 + 17651953000,
+    ("C5_perm27_heavyhex", 65536, 128): 44717824 + 24592722000,
 }
 METRIC = "batched env-steps/sec (CliffordGym 8q all-to-all {H,S,CX})"
 UNIT = "env-steps/s"
@@ -47,7 +51,7 @@ UNIT = "env-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C3_clifford8_full")
@@ -63,6 +67,8 @@ def parse_args():
     ap.add_argument("--no-collector", action="store_true", help="skip the policy-in-the-loop collector leg (collector.RolloutCollector)")
     ap.add_argument("--synth-rollouts", type=int, default=1000, help="num_searches per GPU of the synth leg")
     ap.add_argument("--synth-searches", type=int, default=5, help="timed searches of the synth leg")
+    ap.add_argument("--tile-envs", type=int, default=0, help="qg_config.tile_envs of the env-step legs: 0 = automatic, 16 or 32 (A/B runs)")
+    ap.add_argument("--synth-all-backends", action="store_true", help="also time the two-kernel and PyTorch-policy searches")
     return ap.parse_args()
 
 
@@ -72,7 +78,8 @@ def workload(args):
     return kind, n, gateset, dict(kw)
 
 
-def config_json(args, n_gpus, extra=None):
+def config_json(args, n_gpus):
+    """The workload description: a function of the command line only, so that this arm and `--impl reference` print the same dict."""
     c = {
         "workload": f"{args.config}: BASELINE.json config, {args.envs} envs per GPU x {args.episode_steps} env-steps per step "
                     f"(set_state targets: identity scrambled by 256 random gates; uniform random actions; add_inverts={bool(args.add_inverts)}, "
@@ -80,8 +87,6 @@ def config_json(args, n_gpus, extra=None):
         "envs_per_gpu": args.envs, "env_steps_per_step": args.episode_steps, "n_gpus": n_gpus,
         "l2_policy": "observation tensor rotates over buffers totalling > 2x L2 (126 MB); every launch writes a slab larger than it can keep resident",
     }
-    if extra:
-        c.update(extra)
     return c
 
 
@@ -176,7 +181,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    envs = args.cpu_sample_envs or calibrate_cpu_envs(args, 1.0, threads)   # ~1 s of CPU work per step
+    envs = args.cpu_sample_envs or args.envs          # the same batch as the GPU arm: one step = envs x episode_steps env-steps
     r = cpu_run(args, envs, steps=args.steps, warmup=args.warmup, threads=threads)
     sample = f"{envs} envs x {args.episode_steps} env-steps per step, oracle C++ port of the Rust core (step+observe+masks+reward+is_final per env-step), {threads} host threads"
     line = {
@@ -184,7 +189,7 @@ def run_reference(args):
         "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (byte-per-bit GF(2)) + f32 reward", "data": "synthetic",
-        "config": config_json(args, args.gpus, {"reference_sample": sample}),
+        "config": config_json(args, args.gpus),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -206,6 +211,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from qiskit_gym_b200._lib import lib as _qg_lib
+    _qg_lib().qg_bind_thread_to_device(local)          # the thread that drives the engine runs on the GPU's NUMA node (no-op where sysfs hides the topology)
     if world > 1:
         # whatever NCCL_DEBUG level the box sets (the version banner included) goes to a file: stdout carries the JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/qg_bench_nccl.%h.%p.log")
@@ -217,7 +224,7 @@ def run_ours(args):
     pk = dict(kw)
     if kind != W.PAULI:
         pk["add_inverts"] = bool(args.add_inverts)
-    env = BatchedEnv(kind, n, gateset, B, device=local, max_depth=T, add_perms=False, **pk)
+    env = BatchedEnv(kind, n, gateset, B, device=local, max_depth=T, add_perms=False, tile_envs=args.tile_envs, **pk)
     obs_size = int(np.prod(env.obs_shape()))
     # synthetic inputs (seeded per global env id range so shards differ but are reproducible)
     targets = W.random_targets(kind, n, gateset, B, 20261017 + 3 + 1000 * rank, scramble=256)
@@ -332,13 +339,8 @@ def run_ours(args):
     # ---- e2e: the same episode through the host-buffer C-ABI calls ---------------------------------------
     e2e = None
     if not args.no_e2e:
-        pin_a = torch.from_numpy(actions_h).pin_memory()
-        a_np = pin_a.numpy()
-        pin_c = None if coins is None else coins.cpu().pin_memory()
-        c_np = None if pin_c is None else pin_c.numpy()
-        rew = torch.empty((T, B), dtype=torch.float32).pin_memory(); don = torch.empty((T, B), dtype=torch.uint8).pin_memory(); suc = torch.empty((T, B), dtype=torch.uint8).pin_memory()
-        rew_np, don_np, suc_np = rew.numpy(), don.numpy(), suc.numpy()
         Ke = max(1, min(K, 10))
+        tiles = env.flag_words()
 
         def host_timed(fn, reps):
             with torch.cuda.stream(stream):
@@ -359,8 +361,45 @@ def run_ours(args):
                 t_ms = float(t2.item())
             return t_ms
 
+        e2e_packed = None
+        if A <= 256:
+            # packed wire format (qg_replay_host_packed): uint8 actions in; f32 reward + 2 bits per env-step of is_final / success out;
+            # pinned buffers on the GPU's NUMA node (qg_host_alloc)
+            h_a8 = env.host_buffer((T, B), np.uint8); h_a8[:] = actions_h.astype(np.uint8)
+            h_rw = env.host_buffer((T, B), np.float32)
+            h_db = env.host_buffer((tiles, T), np.uint32); h_sb = env.host_buffer((tiles, T), np.uint32)
+            h_c8 = None
+            if coins is not None:
+                h_c8 = env.host_buffer((T, B), np.uint8); h_c8[:] = coins.cpu().numpy()
+
+            def episode_host_packed():
+                env.restore()
+                env.replay_host_packed(h_a8, h_db, h_sb, reward=h_rw, coins=h_c8, obs=obs_ring, mask=mask_ring)
+                return float(h_rw[T - 1, 0]) + float(h_db[0, T - 1] & 1)
+
+            rew_dev_tb = torch.empty((T, B), dtype=torch.float32, device=dev)
+
+            def episode_host_flags_only():
+                # learner on the device: rewards stay in HBM (for a device-side return / qg_gae), only the flags travel
+                env.restore()
+                env.replay_host_packed(h_a8, h_db, h_sb, reward_dev=rew_dev_tb, coins=h_c8, obs=obs_ring, mask=mask_ring)
+                return float(h_db[0, T - 1] & 1)
+
+            pms = host_timed(episode_host_packed, Ke)
+            fms = host_timed(episode_host_flags_only, Ke)
+            e2e_packed = {"value": world * B * T * Ke / (pms * 1e-3), "ms": pms,
+                          "h2d": T * B * (1 + (1 if h_c8 is not None else 0)), "d2h": T * B * 4 + 2 * tiles * T * 4,
+                          "flags_only": world * B * T * Ke / (fms * 1e-3), "numa_node": getattr(env, "numa_node", -1)}
+
+        pin_a = torch.from_numpy(actions_h).pin_memory()
+        a_np = pin_a.numpy()
+        pin_c = None if coins is None else coins.cpu().pin_memory()
+        c_np = None if pin_c is None else pin_c.numpy()
+        rew = torch.empty((T, B), dtype=torch.float32).pin_memory(); don = torch.empty((T, B), dtype=torch.uint8).pin_memory(); suc = torch.empty((T, B), dtype=torch.uint8).pin_memory()
+        rew_np, don_np, suc_np = rew.numpy(), don.numpy(), suc.numpy()
+
         def episode_host():
-            # whole episode in one call: actions H2D, chunked fused launches, reward/done/success D2H, pipelined (qg_replay_host)
+            # the round-1 wire format (qg_replay_host): int32 actions, f32 reward + u8 done + u8 success
             env.restore()
             env.replay_host(a_np, rew_np, don_np, suc_np, coins=c_np, obs=obs_ring, mask=mask_ring)
             return float(rew_np[T - 1, 0])
@@ -377,14 +416,18 @@ def run_ours(args):
         ems = host_timed(episode_host, Ke)
         Ks = max(1, min(K, 3))
         ems_ps = host_timed(episode_host_per_step, Ks)
-        e2e = {"value": world * B * T * Ke / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": T * B * (4 + (1 if c_np is not None else 0)), "d2h_bytes_per_step": T * B * 6,
-               "note": "qg_replay_host with pinned host buffers: int32 actions [T][B] are read by the kernel from host memory over PCIe (one step ahead), "
-                       "f32 reward + u8 done + u8 success [T][B] are written by the kernel to host memory, one launch per episode (obs+mask stay on "
-                       "the device for the policy); the call returns after the stream is synchronised, i.e. when every byte has arrived",
+        wide = world * B * T * Ke / (ems * 1e-3)
+        e2e = {"value": e2e_packed["value"] if e2e_packed else wide, "unit": UNIT,
+               "h2d_bytes_per_step": e2e_packed["h2d"] if e2e_packed else T * B * (4 + (1 if c_np is not None else 0)),
+               "d2h_bytes_per_step": e2e_packed["d2h"] if e2e_packed else T * B * 6,
+               "note": ("qg_replay_host_packed, pinned NUMA-local host buffers: uint8 actions [T][B] read by the kernel over PCIe one step ahead; f32 reward [T][B] and the "
+                        "is_final / success bit planes uint32[B/32][T] written by the kernel to host memory; one launch per episode, obs + mask stay on the device; "
+                        "the call returns when the stream is synchronised") if e2e_packed else "qg_replay_host (int32 actions; f32 reward, u8 done, u8 success)",
                "steps": Ke,
-               "per_step_sync": {"value": world * B * T * Ks / (ems_ps * 1e-3), "unit": UNIT, "steps": Ks,
-                                 "note": "qg_step_host: one synchronous call per env-step with pinned host buffers (host-side collector): the kernel reads the actions and writes reward / done / success over PCIe itself (zero copy), one launch + one stream synchronisation per env-step"}}
+               "flags_only_value": e2e_packed["flags_only"] if e2e_packed else None,        # rewards kept on the device
+               "int32_u8_format_value": wide,                                              # round-1 wire format: 10 B per env-step
+               "per_step_sync_value": world * B * T * Ks / (ems_ps * 1e-3),                # qg_step_host: one synchronous call per env-step
+               "host_numa_node": e2e_packed["numa_node"] if e2e_packed else -1}
 
     synth = None if args.no_synth else run_synth(args, dev, local, rank, world)
     collector = None if args.no_collector else run_collector(args, dev, local, rank, world)
@@ -423,19 +466,25 @@ def run_ours(args):
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:          # the CPU figure is reported beside the 1-GPU run only
         threads = os.cpu_count() or 1
-        envs = args.cpu_sample_envs or calibrate_cpu_envs(args, 12.0, threads)
-        r = cpu_run(args, envs, threads=threads)
-        envs1 = max(256, envs // (4 * threads) // 64 * 64)          # ~3 s on one thread (one thread and all threads)
+        envs = args.cpu_sample_envs or B                       # the GPU arm's own batch; passes repeated until ~12 s of CPU work
+        probe = cpu_run(args, envs, threads=threads)
+        passes = max(1, min(40, int(12.0 / max(probe["seconds"], 1e-3))))
+        r = cpu_run(args, envs, steps=passes, threads=threads)
+        envs1 = max(256, int(probe["value"] / threads * 3.0 / T) // 64 * 64)          # ~3 s on one thread (one thread and all threads)
         r1 = cpu_run(args, envs1, threads=1)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{envs} envs x {T} env-steps (same config, targets and action distribution), oracle C++ port of the Rust core, "
-                                  f"per env-step step+observe+masks+reward+is_final, {threads} host threads, {r['seconds']:.1f} s",
+                        "sample": f"{passes} passes of {envs} envs x {T} env-steps (the GPU arm's batch, targets and action stream distribution), oracle C++ port of the "
+                                  f"Rust core, per env-step step+observe+masks+reward+is_final, {threads} host threads, {r['seconds']:.1f} s",
                         "single_thread": {"value": r1["value"], "unit": UNIT, "cores": 1, "sample": f"{envs1} envs x {T} env-steps, {r1['seconds']:.1f} s"}}
+    if e2e is not None and synth is not None:
+        # (the driver's parser keeps scalar keys of `e2e`: the second BASELINE.json metric rides there as well as in `synth`)
+        e2e["synth_weak_rollouts_per_s"] = synth["value"]
+        e2e["synth_strong_rollouts_per_s"] = synth["strong"]["value"]
     line = {
         "metric": METRIC if args.config == "C3_clifford8_full" else f"batched env-steps/sec ({args.config})",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (GF(2)) + f32 reward/obs", "data": "synthetic",
-        "config": config_json(args, world, {"obs_buffers": nbuf, "cuda_graph": True}),
+        "config": config_json(args, world), "obs_buffers": nbuf, "cuda_graph": True, "tile_envs": args.tile_envs,
         "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "per_step_launch": per_step, "cpu_baseline": cpu_baseline,
         "packed_obs": packed, "synth": synth, "collector": collector, "engine_error_flags": errs,
     }
@@ -482,22 +531,49 @@ def run_collector(args, dev, local, rank, world):
         episodes, _ = ro.episode_stats()
         return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "ms_per_decision": ms / T, "episodes_finished": episodes}
 
+    def leg_packed():
+        col = RolloutCollector(env, pol, use_twists=False, seed=rank)
+        col.collect_packed(4)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ro = col.collect_packed(T)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        episodes, _ = ro.episode_stats()
+        return {"value": world * B * T / (ms * 1e-3), "unit": UNIT, "ms_per_decision": ms / T, "episodes_finished": episodes}
+
     out = leg("f32")
     out.update({"envs_per_gpu": B, "decisions": T,
                 "note": "RolloutCollector.collect: reset_select + observe (dense f32) + PyTorch BasicPolicy 512/256 forward (f32 cuBLAS) + softmax + "
                         "qg_collect_step + log-prob gather per decision, qg_gae at the end; difficulty 64, random-init policy",
                 "tf32_policy": dict(leg("tf32"), note="same collector with matmul_precision='tf32' (the policy's GEMMs on tensor cores, f32 accumulate)"),
                 "bf16_policy": dict(leg("bf16"), note="same collector with matmul_precision='bf16' (torch.autocast)")})
+    try:
+        out["tensor_core_packed"] = dict(leg_packed(), note="RolloutCollector.collect_packed: packed-bit observations + the policy on tcgen05 tensor cores "
+                                                           "(qg_policy_tc_forward_bits: f16 hi+lo split operands, f32 accumulate, logits within 1e-4 of the f32 module) + qg_collect_step")
+    except Exception as ex:          # (reported, not hidden: the leg is the newest kernel)
+        out["tensor_core_packed"] = {"error": repr(ex)[:300]}
     return out
 
 
 def run_synth(args, dev, local, rank, world):
-    """Second BASELINE.json metric: synth rollouts/sec on configs[4] (PermutationGym 27q heavy-hex, num_searches = 1000 per GPU,
-    weak-scaled): policy-guided rollouts on the device (BasicPolicy-shaped MLP 729->512->256->{28,1}, torch.manual_seed(0) init, sampling),
-    every decision = policy forward + softmax + one fused qg_search_step, best rollout reduced on the GPU and across ranks (one int64
-    MAX all-reduce + broadcast of the winner).  Wall time of whole searches, max over ranks."""
+    """Second BASELINE.json metric: synth rollouts/sec on configs[4] (PermutationGym 27q heavy-hex, `num_searches = 1000`): policy-guided
+    rollouts on the device (BasicPolicy-shaped MLP 729->512->256->{28,1}, torch.manual_seed(0) init, sampling), the whole search one launch of
+    qg_search_run, the best rollout reduced on the GPU and across ranks by qg_search_finish (one NCCL all-gather + on-GPU pick through the
+    C ABI's own communicator).  Two readings of "across 1/2/4/8 GPUs": WEAK = 1000 rollouts per GPU (1000 x N per search), STRONG = ONE
+    1000-rollout search split over the N GPUs (1000 / N rollouts each, global rollout ids, the same winner for every N).  Wall time of
+    whole solve() calls, max over ranks."""
     import torch
     import torch.distributed as dist
+    from qiskit_gym_b200 import engine
     from qiskit_gym_b200 import workloads as W
     from qiskit_gym_b200.search import BasicPolicy, RolloutSearch
 
@@ -506,20 +582,22 @@ def run_synth(args, dev, local, rank, world):
     rng = np.random.Generator(np.random.PCG64(20261017 + 5))
     targets = [rng.permutation(n).astype(np.int64).tolist() for _ in range(args.synth_searches + 1)]
     shallow = list(range(n)); shallow[0], shallow[1] = shallow[1], shallow[0]      # one SWAP away: exercises the success / early-exit path
+    comm = engine.nccl_comm_create(local) if world > 1 else None
 
-    def leg(backend):
+    def leg(backend, rollouts, use_comm=True):
         torch.manual_seed(0)
         pol = BasicPolicy([n, n], len(gateset), embedding_size=512, common_layers=(256,))
-        rs = RolloutSearch(kind, n, gateset, pol, R, device=local, max_depth=128, add_inverts=False, policy_backend=backend)
-        rs.solve(targets[0], deterministic=False, seed=0, first_rollout_id=rank * R)    # warm-up: graph capture, cuBLAS
-        res_sh = rs.solve(shallow, deterministic=False, seed=1, first_rollout_id=rank * R)
+        rs = RolloutSearch(kind, n, gateset, pol, rollouts, device=local, max_depth=128, add_inverts=False, policy_backend=backend)
+        c = comm if use_comm else None
+        rs.solve(targets[0], deterministic=False, seed=0, first_rollout_id=rank * rollouts, comm=c)    # warm-up: graph capture, cuBLAS
+        res_sh = rs.solve(shallow, deterministic=False, seed=1, first_rollout_id=rank * rollouts, comm=c)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         its = 0
         for i in range(args.synth_searches):
-            r = rs.solve(targets[1 + i], deterministic=False, seed=2 + i, first_rollout_id=rank * R)
+            r = rs.solve(targets[1 + i], deterministic=False, seed=2 + i, first_rollout_id=rank * rollouts, comm=c)
             its += r.iterations
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
@@ -527,24 +605,32 @@ def run_synth(args, dev, local, rank, world):
             t = torch.tensor([sec], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
-        total = world * R * args.synth_searches
-        return {"value": total / sec, "unit": "rollouts/s", "decisions_per_search": its / max(args.synth_searches, 1),
+        total = world * rollouts * args.synth_searches
+        return {"value": total / sec, "unit": "rollouts/s", "rollouts_per_gpu": rollouts, "rollouts_per_search": world * rollouts,
+                "decisions_per_search": its / max(args.synth_searches, 1),
                 "us_per_decision": 1e6 * sec / max(its, 1), "ms_per_search": 1e3 * sec / max(args.synth_searches, 1),
                 "shallow_target": {"success": bool(res_sh.success), "circuit_len": None if res_sh.actions is None else len(res_sh.actions),
-                                   "decisions": res_sh.iterations, "ms": 1e3 * res_sh.seconds}}
+                                   "key": int(res_sh.key), "decisions": res_sh.iterations, "ms": 1e3 * res_sh.seconds}}
 
-    persistent = leg("persistent")
-    fused = leg("fused")
-    torch_leg = leg("torch")
-    out = {"metric": "synth rollouts/sec (PermutationGym 27q heavy-hex, num_searches=1000 per GPU)", "rollouts_per_search_per_gpu": R, "searches": args.synth_searches}
-    out.update(persistent)
+    out = {"metric": "synth rollouts/sec (PermutationGym 27q heavy-hex, num_searches=1000)", "searches": args.synth_searches}
+    out.update(leg("persistent", R))
+    out["scaling"] = "weak: num_searches = 1000 per GPU"
     out["policy_backend"] = ("persistent: the whole search is ONE launch of qg_search_run (each CTA owns 8 rollouts and loops packed observation -> "
-                             "fused policy network -> Philox sample + env step); identical decisions to the two-kernel path")
-    out["two_kernel"] = dict(fused, note="qg_policy_forward_bits + qg_search_step_bits per decision, CUDA graph, PDL")
-    out["torch_policy"] = dict(torch_leg, note="same search with the PyTorch BasicPolicy on dense f32 observations (cuBLAS GEMMs + softmax + qg_search_step)")
+                             "fused policy network -> Philox sample + env step); cross-GPU best by qg_search_finish (NCCL all-gather + on-GPU pick)")
+    if R % world == 0:
+        out["strong"] = dict(leg("persistent", R // world), scaling=f"strong: ONE num_searches = {R} search split over {world} GPU(s), {R // world} rollouts each",
+                             note="latency-bound: a search is <= 128 sequential decisions whatever the number of rollouts per GPU, so splitting one search shortens "
+                                  "nothing but the per-decision work; the winner (key, actions) is identical for every GPU count (tools/multi_gpu_parity.py)")
+    else:
+        out["strong"] = {"value": None, "note": f"{R} rollouts do not split evenly over {world} GPUs"}
+    if args.synth_all_backends:
+        out["two_kernel"] = dict(leg("fused", R, use_comm=False), note="qg_policy_forward_bits + qg_search_step_bits per decision, CUDA graph, PDL; torch.distributed reduction")
+        out["torch_policy"] = dict(leg("torch", R, use_comm=False), note="same search with the PyTorch BasicPolicy on dense f32 observations (cuBLAS GEMMs + softmax + qg_search_step)")
     out["note"] = ("uniform random 27-permutations, random-init policy (no checkpoint exists for this map): rollouts run to max_depth=128; "
-                   "time is host wall clock over whole solve() calls (set_state broadcast, CUDA-graph replays, on-GPU best reduction, "
-                   "cross-rank all-reduce), max over ranks")
+                   "time is host wall clock over whole solve() calls (set_state broadcast, one search launch, on-GPU best reduction, "
+                   "cross-rank all-gather), max over ranks")
+    if comm is not None:
+        engine.nccl_comm_destroy(comm)
     return out
 
 

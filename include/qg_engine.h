@@ -71,6 +71,7 @@ typedef struct qg_config {
     float pauli_layer_reward;
     /* engine extras */
     int32_t solution_capacity;    /* entries kept per env; 0 = max_depth (+ rotations for Pauli) */
+    int32_t tile_envs;            /* envs per warp tile of the step kernel: 0 = chosen per launch from the batch size, or 16 / 32 */
 } qg_config;
 
 /* error flag bits reported by qg_read_errors (situations where the reference panics) */
@@ -199,6 +200,45 @@ QG_API int qg_get_state_host(qg_engine* e, int64_t env, uint8_t* out_host, int64
 /* Env::solution (solution ++ reverse(solution_inv); PauliNetwork rotation words as pauli.rs:685-719). */
 QG_API int qg_solution_host(qg_engine* e, int64_t env, uint32_t* out_host, int32_t cap, int32_t* len, qg_stream stream);
 
+/* Env::solution of MANY envs in one kernel + one copy (clifford.rs:376-381 / pauli.rs:685-719 for `count` envs starting at `first`):
+ * row i of out [count][cap] holds the merged action list of env first + i (solution ++ reverse(solution_inv); PauliNetwork words as logged),
+ * len[i] its length; a solution longer than `cap` sets len[i] = -(length) and writes nothing.  The _dev form is asynchronous on the stream and
+ * writes device buffers; the _host form stages through engine-owned device buffers (grown on first use) and synchronises. */
+QG_API int qg_solutions(qg_engine* e, int64_t first, int64_t count, uint32_t* out_dev, int32_t cap, int32_t* len_dev, qg_stream stream);
+QG_API int qg_solutions_host(qg_engine* e, int64_t first, int64_t count, uint32_t* out_host, int32_t cap, int32_t* len_host, qg_stream stream);
+
+/* ---- packed host wire format -------------------------------------------------------------------------------------------------
+ * qg_replay_host with the narrowest streams the data allows (the host link is what bounds a multi-GPU node end to end):
+ *  actions8_host  uint8[num_steps][B]      one byte per action (needs num_actions <= 256; a value >= num_actions is the reference's no-op)
+ *  reward_host    float[num_steps][B] or NULL (NULL: rewards stay on the device: pass reward_dev to keep them for a device-side return / qg_gae)
+ *  reward_dev     float[num_steps][B] or NULL
+ *  done_bits_host, success_bits_host  uint32[ceil(B/32)][num_steps] (success may be NULL): bit (env % 32) of word [env / 32][t] = is_final /
+ *                 success of env after step t: 2 bits per env-step, each tile's 32 consecutive steps written as one 128-byte line
+ * Buffers must be pinned (qg_host_alloc, cudaHostAlloc, cudaHostRegister): the kernel reads / writes them over PCIe itself, one launch per
+ * episode; QG_ERR_INVALID for pageable memory.  Observations / masks go to the device ring as in qg_replay. */
+QG_API int qg_replay_host_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host,
+                                 float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_host, float* reward_dev,
+                                 uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream);
+/* The device-resident form of the same formats (actions8_dev uint8[num_steps][B], bit planes on the device). */
+QG_API int qg_replay_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_dev, const uint8_t* coins_dev,
+                            float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_dev,
+                            uint32_t* done_bits_dev, uint32_t* success_bits_dev, qg_stream stream);
+/* Pinned host memory on the NUMA node the GPU hangs off (sysfs numa_node of its PCI function): the calling thread is bound to that node's
+ * CPUs and its memory policy to that node while the pages are allocated and first touched, then both are restored.  On a multi-GPU host
+ * this keeps every GPU's PCIe traffic on its own socket's memory controllers.  Falls back to plain cudaHostAlloc where the topology cannot
+ * be read.  *numa_node_out (may be NULL) receives the node used, -1 if unknown. */
+QG_API int qg_host_alloc(int32_t device, size_t bytes, void** out_host, int32_t* numa_node_out);
+QG_API int qg_host_free(void* host);
+/* Binds the calling host thread to the CPUs of the GPU's NUMA node (the thread that drives an engine should run there). Returns the node or -1. */
+QG_API int qg_bind_thread_to_device(int32_t device);
+
+/* ---- zero-copy observations for the policy (DLPack) ----------------------------------------------------------------------------
+ * The engine allocates (once) an observation ring float[ring][B][rows][cols] and hands it out as a DLManagedTensor* (DLPack v0.8 ABI, device
+ * kDLCUDA, dtype float32; shape (B, rows, cols) for ring == 1): wrap it in a PyCapsule named "dltensor" for torch.from_dlpack, or consume it
+ * from Rust / C++ directly.  *obs_dev_out receives the same pointer for qg_step / qg_replay's obs_dev argument.  The memory belongs to the
+ * engine (freed by qg_destroy): the tensor must not outlive it; the deleter only frees the descriptor. */
+QG_API int qg_dlpack_obs(qg_engine* e, int32_t ring, void** managed_tensor_out, float** obs_dev_out);
+
 /* ---- synth search (rollout driver pieces around the policy) ---------------------------- */
 /* Starts a search over the engine's B rollouts: zeroes the per-rollout return accumulators.
  * The caller loads the target first (qg_set_state broadcast=1). */
@@ -215,6 +255,21 @@ QG_API int qg_search_step(qg_engine* e, const float* weights_dev, int32_t determ
  * *best_key_host and the winner's local env index to *best_env_host (-1 if B == 0). */
 QG_API int qg_search_best(qg_engine* e, int64_t* best_key_host, int64_t* best_env_host, qg_stream stream);
 QG_API int qg_read_returns(qg_engine* e, float* returns_dev, qg_stream stream);
+/* End of a search sharded over GPUs (rl/synthesis.py:112-126 `solve(..., num_searches)` with the rollouts split over ranks, each rank's
+ * qg_search_begin given its first GLOBAL rollout id): the on-GPU best-rollout reduction of this rank, then — given an NCCL communicator —
+ * ONE all-gather of every rank's (key, solution length, action list) row and an on-GPU pick of the largest key, so that every rank ends with
+ * the same winner without a host decision in between.  comm: an ncclComm_t (qg_nccl_comm_create below, or any communicator of the same NCCL
+ * library whose ranks all make this call), or NULL for a single GPU.  Outputs (host): *best_key_host the winning packed key (0: no rollout),
+ * *success_host, *rollout_id_host its global rollout id, *owner_rank_host, actions_host[0..*len_host) the winner's Env::solution (only when
+ * it succeeded and fits `cap`; *len_host = 0 otherwise).  Identical results for any number of ranks (keys embed the global rollout id). */
+typedef struct ncclComm* qg_nccl_comm;
+QG_API int qg_search_finish(qg_engine* e, qg_nccl_comm comm, int64_t* best_key_host, int32_t* success_host, int64_t* rollout_id_host,
+                            int32_t* owner_rank_host, uint32_t* actions_host, int32_t cap, int32_t* len_host, qg_stream stream);
+/* NCCL plumbing for hosts without torch (the library is loaded with dlopen("libnccl.so.2") on first use; QG_ERR_UNSUPPORTED if absent):
+ * rank 0 makes an id and ships the 128 bytes to the others by any channel; every rank then creates its communicator on its device. */
+QG_API int qg_nccl_unique_id(uint8_t id_out[128]);
+QG_API int qg_nccl_comm_create(const uint8_t id[128], int32_t rank, int32_t world, int32_t device, qg_nccl_comm* out);
+QG_API int qg_nccl_comm_destroy(qg_nccl_comm comm);
 
 /* ---- rollout collector pieces (the data-collection half of twisterl's PPO loop) ------------- */
 /* qg_search_step that also reports the step's reward / is_final / success per env (entries of envs that were already
@@ -279,6 +334,20 @@ QG_API int qg_policy_forward_bits(qg_policy* p, const uint32_t* obs_bits_dev, in
 /* ... and values_dev float[B] (the value head's output; the policy must have been created with one); any of the three may be NULL. */
 QG_API int qg_policy_forward_bits_value(qg_policy* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev,
                                         float* logits_dev, float* values_dev, qg_stream stream);
+
+/* The same network for LARGE batches (the rollout collector: tens of thousands of envs per decision) on the 5th-generation tensor cores
+ * (csrc/qg_policy_tc.cu: tcgen05.mma with tensor-memory accumulators, bulk-copy operand pipeline).  Every f32 value travels as two f16
+ * halves (hi + lo, 22 significant bits) and every product as hi*hi + hi*lo + lo*hi with f32 accumulation, so logits stay within the f32
+ * module's 1e-4 tolerance.  Arguments as qg_policy_create_value; max_batch sizes the activation buffers (allocated once, here); at most
+ * 127 actions; sm_100 only (QG_ERR_UNSUPPORTED elsewhere).  forward: probs / logits float[B][num_actions], values float[B] (any may be NULL). */
+typedef struct qg_policy_tc qg_policy_tc;
+QG_API int qg_policy_tc_create(int32_t device, int32_t obs_size, int32_t num_layers, const int32_t* out_features,
+                               const float* const* weights_host, const float* const* biases_host,
+                               const float* value_weight_host, float value_bias, int64_t max_batch, qg_policy_tc** out);
+QG_API void qg_policy_tc_destroy(qg_policy_tc* p);
+QG_API int32_t qg_policy_tc_num_actions(const qg_policy_tc* p);
+QG_API int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev, float* logits_dev,
+                                     float* values_dev, qg_stream stream);
 
 /* The whole rollout search in ONE launch: every CTA owns 8 rollouts and loops  policy (packed observation -> action weights) ->
  * sample / arg-max + fused step -> next packed observation  until its rollouts are final or max_decisions decisions were taken;

@@ -45,6 +45,7 @@ class QgConfig(C.Structure):
         ("final_pauli_layers", C.c_int32),
         ("pauli_layer_reward", C.c_float),
         ("solution_capacity", C.c_int32),
+        ("tile_envs", C.c_int32),
     ]
 
 
@@ -124,6 +125,7 @@ def make_config(
     final_pauli_layers: int | None = None,
     pauli_layer_reward: float | None = None,
     solution_capacity: int = 0,
+    tile_envs: int = 0,
 ) -> QgConfig:
     """Resolves the pyo3 `None` defaults exactly like the reference constructors
     (permutation.rs:277-299, pauli.rs:743-775; MetricsWeights::from_hashmap metrics.rs:169-184)."""
@@ -153,6 +155,7 @@ def make_config(
     cfg.final_pauli_layers = (int(max_rotations) + 2) if final_pauli_layers is None else int(final_pauli_layers)
     cfg.pauli_layer_reward = 0.01 if pauli_layer_reward is None else float(pauli_layer_reward)
     cfg.solution_capacity = int(solution_capacity)
+    cfg.tile_envs = int(tile_envs)
     cfg._keepalive = gates  # the struct only borrows the pointer
     return cfg
 

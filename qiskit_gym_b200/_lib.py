@@ -29,6 +29,9 @@ SYMBOLS = [
     "qg_policy_create", "qg_policy_create_value", "qg_policy_destroy", "qg_policy_num_actions", "qg_policy_has_value", "qg_policy_forward_bits",
     "qg_policy_forward_bits_value",
     "qg_step_slots", "qg_copy_records", "qg_mcts_begin", "qg_mcts_select", "qg_mcts_backup", "qg_mcts_root_weights", "qg_search_run",
+    "qg_solutions", "qg_solutions_host", "qg_replay_host_packed", "qg_replay_packed", "qg_host_alloc", "qg_host_free", "qg_bind_thread_to_device",
+    "qg_dlpack_obs", "qg_search_finish", "qg_nccl_unique_id", "qg_nccl_comm_create", "qg_nccl_comm_destroy",
+    "qg_policy_tc_create", "qg_policy_tc_destroy", "qg_policy_tc_num_actions", "qg_policy_tc_forward_bits",
 ]
 
 
@@ -129,6 +132,23 @@ def lib():
     L.qg_mcts_backup.argtypes = [treep, vp, vp, vp, vp, vp]
     L.qg_mcts_root_weights.argtypes = [treep, vp, vp]
     L.qg_search_run.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    L.qg_solutions.argtypes = [vp, i64, i64, vp, i32, vp, vp]
+    L.qg_solutions_host.argtypes = [vp, i64, i64, vp, i32, vp, vp]
+    L.qg_replay_host_packed.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.qg_replay_packed.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.qg_host_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), C.POINTER(i32)]
+    L.qg_host_free.argtypes = [vp]
+    L.qg_bind_thread_to_device.argtypes = [i32]
+    L.qg_dlpack_obs.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.qg_search_finish.argtypes = [vp, vp, C.POINTER(i64), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), vp, i32, C.POINTER(i32), vp]
+    L.qg_nccl_unique_id.argtypes = [vp]
+    L.qg_nccl_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    L.qg_nccl_comm_destroy.argtypes = [vp]
+    L.qg_policy_tc_create.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_float, i64, C.POINTER(vp)]
+    L.qg_policy_tc_destroy.argtypes = [vp]
+    L.qg_policy_tc_destroy.restype = None
+    L.qg_policy_tc_num_actions.argtypes = [vp]
+    L.qg_policy_tc_forward_bits.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     _lib = L
     return L
 

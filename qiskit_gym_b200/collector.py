@@ -48,6 +48,16 @@ class Rollout:
     advantages: torch.Tensor     # f32 [T, B]
     returns: torch.Tensor        # f32 [T, B]
     twist: torch.Tensor | None   # i32 [T, B]          twist index used for the decision
+    obs_bits: torch.Tensor | None = None   # i32 [T, B, obs_words]  packed observations (collect_packed: `obs` is None, unpack with unpack_obs)
+
+    def unpack_obs(self, t0: int = 0, t1: int | None = None) -> torch.Tensor:
+        """Dense f32 observations of decisions t0 .. t1-1 from the packed bits (for the update step of a trainer)."""
+        bits = self.obs_bits[t0:t1]
+        shifts = torch.arange(32, dtype=torch.int32, device=bits.device)
+        dense = ((bits.unsqueeze(-1) >> shifts) & 1).reshape(bits.shape[0], bits.shape[1], -1)
+        return dense[..., : self.obs_size].float()
+
+    obs_size: int = 0
 
     def episode_stats(self):
         """(episodes finished, fraction of them that ended in success) over the rollout."""
@@ -128,6 +138,42 @@ class RolloutCollector:
             else:
                 logits, value = self.policy(obs)
             return torch.softmax(logits.float(), dim=-1), value.float().reshape(-1)
+
+    def collect_packed(self, num_steps: int, deterministic: bool = False) -> Rollout:
+        """The large-batch collection path: packed-bit observations (32x less observation traffic than dense f32) and the policy on the
+        tensor cores (policy.TensorCorePolicy, tcgen05).  Per decision: reset_select -> observe_bits -> qg_policy_tc_forward_bits (softmax
+        weights + value) -> qg_collect_step; log-probabilities and GAE once at the end.  No twists on this path."""
+        from .policy import TensorCorePolicy, weights_version
+        env, T, B = self.env, int(num_steps), self.env.batch
+        dev, A = env.device, env.num_actions()
+        if self.num_twists:
+            raise NotImplementedError("collect_packed does not apply twists (construct the collector with use_twists=False)")
+        tcp = getattr(self, "_tcp", None)
+        if tcp is None or tcp.version != weights_version(self.policy) or tcp.max_batch < B:
+            tcp = self._tcp = TensorCorePolicy(self.policy, max_batch=B, device=dev, with_value=True)
+        ow = env.obs_words()
+        bits = torch.empty((T + 1, B, ow), dtype=torch.int32, device=dev)
+        probs = torch.empty((T, B, A), dtype=torch.float32, device=dev)
+        actions = torch.full((T, B), -1, dtype=torch.int32, device=dev)
+        rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
+        dones = torch.zeros((T, B), dtype=torch.bool, device=dev)
+        succ = torch.zeros((T, B), dtype=torch.bool, device=dev)
+        values = torch.zeros((T + 1, B), dtype=torch.float32, device=dev)
+        for t in range(T):
+            s = decision_seed(self.seed, self.counter)
+            env.reset_select(s, self.first_env_id)
+            env.observe_bits(bits[t])
+            tcp.forward_bits(bits[t], probs=probs[t], values=values[t])
+            env.collect_step(probs[t], s, deterministic=deterministic, obs=False, chosen=actions[t], reward=rewards[t], done=dones[t], success=succ[t])
+            self.counter += 1
+        env.observe_bits(bits[T])
+        tcp.forward_bits(bits[T], values=values[T])
+        valid = actions >= 0
+        a = actions.long().clamp_(min=0)
+        logp = torch.log(probs.gather(2, a[..., None]).squeeze(2).clamp_min(1e-38))
+        adv, ret = gae(rewards, values, dones, self.gamma, self.lam, valid)
+        return Rollout(obs=None, actions=actions, policy_actions=a, logp=logp, values=values, rewards=rewards, dones=dones, successes=succ, valid=valid,
+                       advantages=adv, returns=ret, twist=None, obs_bits=bits[:T], obs_size=env._obs_size)
 
     def collect(self, num_steps: int, deterministic: bool = False) -> Rollout:
         env, T, B = self.env, int(num_steps), self.env.batch

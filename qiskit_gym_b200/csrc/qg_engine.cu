@@ -7,59 +7,13 @@
 #include <string>
 #include <vector>
 
-#include "qg_host.hpp"
+#include "qg_engine_priv.hpp"
 #include "qg_aux_kernels.cuh"
-#include "qg_launch.hpp"
 #include "qg_policy_host.hpp"
 
 using namespace qg;
 
-struct qg_twists { Twists t; };
-
-struct qg_engine {
-    qg_config cfg{};                 // gateset pointer re-targeted at `gates`
-    std::vector<qg_gate> gates;
-    Layout L;
-    DevCfg dc{};
-    int device = 0;
-    int64_t B = 0, Bpad = 0;
-    bool owns_ws = false;
-    uint8_t* ws = nullptr;
-    // workspace carve-outs
-    uint32_t* staged = nullptr;      // [Bpad][PW]
-    uint32_t* snap = nullptr;        // [W][Bpad] snapshot of the records
-    bool has_snap = false;
-    int32_t* io_actions = nullptr; uint8_t* io_coins = nullptr; float* io_reward = nullptr; uint8_t* io_done = nullptr; uint8_t* io_success = nullptr;
-    unsigned long long* best = nullptr;
-    // pinned host staging
-    uint32_t* h_staged = nullptr; int64_t h_staged_words = 0;
-    unsigned long long* h_best = nullptr;
-    size_t smem_bytes = 0; int sm_warp_words = 0, sm_scr = 0, sm_obs = 0;
-    uint64_t magic_obs = 0, magic_A = 0; uint32_t magic_vpe = 0, magic_a4 = 0;
-    int nperms = 0;
-    int pdl_mode = 2;                // QG_PDL=0|1|2 in the environment: programmatic dependent launch variants (see StepArgs)
-    int stagger_ns = 0, num_sms = 148;
-    size_t l2_persist_bytes = 0;
-    bool all_symplectic = true;      // Clifford: every state loaded so far is symplectic (identity at construction, resets, checked set_state payloads)
-    bool inv_bucket_enabled = true;  // QG_INV_REG=0 in the environment forces the generic shared-memory Gauss-Jordan (A/B runs)
-    // qg_replay_host pipeline (allocated on first use): two chunk buffers, copy-in / copy-out streams
-    int rp_chunk = 0;
-    int32_t* rp_actions[2] = {nullptr, nullptr}; uint8_t* rp_coins[2] = {nullptr, nullptr};
-    float* rp_reward[2] = {nullptr, nullptr}; uint8_t* rp_done[2] = {nullptr, nullptr}; uint8_t* rp_success[2] = {nullptr, nullptr};
-    cudaStream_t rp_in = nullptr, rp_out = nullptr;
-    cudaEvent_t rp_ev_in[2] = {nullptr, nullptr}, rp_ev_run[2] = {nullptr, nullptr}, rp_ev_out[2] = {nullptr, nullptr}, rp_ev_start = nullptr;
-};
-
 namespace {
-
-#define CUDA_OK(expr)                                                                          \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
-        if (_e != cudaSuccess) {                                                               \
-            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
-            return QG_ERR_CUDA;                                                                \
-        }                                                                                      \
-    } while (0)
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 inline uint64_t magic40(uint32_t d) { return ((1ull << 40) + d - 1) / d; }
@@ -101,7 +55,18 @@ int prepare_kernels(qg_engine* e) {   // kernel attributes (shared-memory carve-
     }
     return QG_OK;
 }
-int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t logical_batch = -1) {
+}  // namespace
+
+// The device-side address of a pinned (page-locked) host buffer — under unified addressing such memory is mapped into the device's address
+// space, so a kernel can read / write it over PCIe — or nullptr for pageable memory.
+void* qg::mapped_host(const void* h) {
+    if (!h) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t logical_batch) {
     // logical_batch >= 0: the launch covers that many logical envs addressed through a.src_slot / a.dst_slot (qg_step_slots)
     const int64_t LB = logical_batch >= 0 ? logical_batch : e->B;
     if (LB == 0) return QG_OK;
@@ -112,7 +77,25 @@ int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t log
     if (a.ring <= 0) a.ring = 1;
     a.pdl_mode = e->pdl_mode; a.num_sms = e->num_sms;
     a.stagger_ns = (mode == MODE_STEP && a.nsteps >= 8) ? e->stagger_ns : 0;
-    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    // tile size.  Measured at 65 536 envs (profiles/r2_v2_tile_sweep.txt): 16-env tiles (twice the warps, lanes 16..31 idle in the step logic)
+    // lose 2-14 % in replay launches for every config and in single-step launches of the small observations (C1 / C2 / C3), but a single-step
+    // launch of a large observation gains (C4 0.53 -> 0.58, C5 0.68 -> 0.82 of the roofline): its warps each store 60-90 KB per step, and half-size
+    // tiles let the first stores start after half the step logic.  Host-packed launches keep 32 (16-env tiles halve the PCIe transaction sizes).
+    const int64_t tiles32 = (LB + 31) / 32;
+    int epw = (mode != MODE_OBSERVE && a.nsteps <= 1 && e->L.obs_size >= 384 && !a.done_bits && tiles32 <= (int64_t)e->num_sms * 20) ? 16 : 32;
+    if (e->cfg.tile_envs == 16 || e->cfg.tile_envs == 32) epw = e->cfg.tile_envs;
+    if (e->epw_forced == 16 || e->epw_forced == 32) epw = e->epw_forced;
+    if (mode == MODE_OBSERVE) epw = 32;
+    const int stride = epw + 1;
+    const int lay_words = e->L.W + e->L.SCR + e->L.OW;
+    const int cat_w = e->cat_words ? (e->cat_words * epw + 31) / 32 : 0;
+    a.sm_scr = e->L.W * stride; a.sm_obs = (e->L.W + e->L.SCR) * stride;
+    // Permutation builds the concatenated stream straight from the state: it takes the place of the per-environment stream O (which such a
+    // launch does not build unless packed observations are requested as well); the other kinds gather it from O into a region of its own
+    const bool cat_in_O = e->L.kind == QG_ENV_PERMUTATION && !a.obs_bits && cat_w <= e->L.OW * stride;
+    a.sm_cat = (cat_w && a.obs && mode != MODE_SEARCH && !a.skip_negative) ? (cat_in_O ? a.sm_obs : lay_words * stride) : -1;
+    a.sm_warp_words = lay_words * stride + ((a.sm_cat >= 0 && !cat_in_O) ? cat_w : 0);
+    a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     { const uint32_t vpe = (uint32_t)e->L.obs_size / 4; a.exp_q = vpe ? 32u / vpe : 0u; a.exp_r = vpe ? 32u - a.exp_q * vpe : 0u; }
     a.symplectic = e->all_symplectic ? 1 : 0;
@@ -120,10 +103,10 @@ int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t log
     if (a.obs_bits && e->L.kind == QG_ENV_PERMUTATION && e->L.OW == 0) { set_error("packed observations need num_qubits <= 64 for Permutation"); return QG_ERR_UNSUPPORTED; }
     if (a.obs && (reinterpret_cast<uintptr_t>(a.obs) & 15)) { set_error("obs_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
     if (a.mask && (reinterpret_cast<uintptr_t>(a.mask) & 15)) { set_error("mask_dev must be 16-byte aligned"); return QG_ERR_INVALID; }
-    const int64_t tiles = (LB + 31) / 32;
+    const int64_t tiles = (LB + epw - 1) / epw;
     DevCfg dc = e->dc;
     dc.B = LB;
-    LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), e->smem_bytes, a.pdl_mode ? 1 : 0};
+    LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), ((size_t)kLutWords + (size_t)a.sm_warp_words * kWarpsPerCta) * 4, a.pdl_mode ? 1 : 0, epw};
     if (e->l2_persist_bytes > 0 && mode == MODE_STEP && a.nsteps > 1 && a.actions) {
         // replay: keep the resident action stream in L2 (persisting window) so that the launch's DRAM traffic is writes only
         g.l2_base = a.actions; g.l2_bytes = std::min<size_t>((size_t)a.nsteps * (size_t)a.in_stride * 4, e->l2_persist_bytes);
@@ -140,6 +123,8 @@ int launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t log
     }
     return QG_OK;
 }
+
+namespace {
 
 int launch_load(qg_engine* e, int64_t first, int64_t count, int broadcast, uint32_t depth_init, cudaStream_t st) {
     if (count <= 0) return QG_OK;
@@ -254,6 +239,7 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     e->cfg = *cfg; e->gates.assign(cfg->gateset, cfg->gateset + cfg->num_gates); e->cfg.gateset = e->gates.data();
     e->L = L; e->device = device; e->B = batch; e->Bpad = align_up(std::max<int64_t>(batch, 1), 32);
     e->nperms = (int)tw.act_perms.size();
+#ifdef QG_TOOLS_KNOBS      // A/B switches for tools/ builds (make EXTRA=-DQG_TOOLS_KNOBS); the product library reads no environment variables
     if (const char* v = std::getenv("QG_PDL")) e->pdl_mode = std::atoi(v);
     if (const char* v = std::getenv("QG_L2_PERSIST_MB")) {                 // A/B runs: persisting-L2 window over the replay's action stream
         int mx = 0, win = 0;
@@ -265,11 +251,12 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     }
     if (const char* v = std::getenv("QG_INV_REG")) e->inv_bucket_enabled = std::atoi(v) != 0;
     if (const char* v = std::getenv("QG_INV_SYMPLECTIC")) e->all_symplectic = std::atoi(v) != 0;   // 0: never use the transpose shortcut
+    if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
+    if (const char* v = std::getenv("QG_EPW")) e->epw_forced = std::atoi(v);
+#endif
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
     // replay stagger (warp k of an SM starting k slab-times late so that the warps do not alternate between the step logic and the
     // expansion in lock-step): measured on the final kernel, 1.600 ms with it and 1.594 ms without (65 536 envs): off unless asked for
-    e->stagger_ns = 0;
-    if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
     std::vector<uint32_t> pg;
     if (cfg->env_kind == QG_ENV_PAULI_NETWORK) pauli_gen_tables(cfg, pg);
     const WsPlan p = plan_ws(L, batch, e->nperms, (int64_t)pg.size());
@@ -285,7 +272,10 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     // shared-memory plan: each warp owns [W | SCR | OW] words x kStride for its 32 envs
     const int words = L.W + L.SCR + L.OW;
     e->sm_warp_words = words * kStride; e->sm_scr = L.W * kStride; e->sm_obs = (L.W + L.SCR) * kStride;
-    e->smem_bytes = ((size_t)kLutWords + (size_t)e->sm_warp_words * kWarpsPerCta) * 4;
+    // observations that are not whole words per environment are expanded from the tile's concatenated bit stream (expand_cat): obs words per
+    // 32-env tile; a Permutation too wide for a bit stream (OW == 0) keeps the direct byte test
+    e->cat_words = ((L.obs_size & 31) != 0 && !(L.kind == QG_ENV_PERMUTATION && L.OW == 0)) ? L.obs_size : 0;
+    e->smem_bytes = ((size_t)kLutWords + (size_t)(e->sm_warp_words + e->cat_words) * kWarpsPerCta) * 4;      // the largest layout a launch may ask for
     if (e->smem_bytes > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
     e->magic_obs = magic40((uint32_t)L.obs_size); e->magic_A = magic40((uint32_t)L.A);
     auto magic32 = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
@@ -311,7 +301,9 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
         int sh = 0; while ((1 << sh) < L.D) ++sh;
         d.row_shift = sh;
     }
+#ifdef QG_TOOLS_KNOBS
     if (const char* v = std::getenv("QG_ROW_POW2")) { if (std::atoi(v) == 0) d.row_shift = -1; }      // A/B runs
+#endif
     e->staged = (uint32_t*)(e->ws + p.staged);
     e->snap = (uint32_t*)(e->ws + p.snap);
     e->io_actions = (int32_t*)(e->ws + p.io_actions); e->io_coins = e->ws + p.io_coins; e->io_reward = (float*)(e->ws + p.io_reward);
@@ -363,6 +355,7 @@ void qg_destroy(qg_engine* e) {
     if (e->rp_ev_start) cudaEventDestroy(e->rp_ev_start);
     if (e->rp_in) cudaStreamDestroy(e->rp_in);
     if (e->rp_out) cudaStreamDestroy(e->rp_out);
+    extras_release(e);
     if (e->owns_ws && e->ws) cudaFree(e->ws);
     delete e;
 }
@@ -469,15 +462,6 @@ int qg_replay(qg_engine* e, int32_t num_steps, const int32_t* actions_dev, const
     return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
 }
 
-// The device-side address of a pinned (page-locked) host buffer — under unified addressing such memory is mapped into the device's address
-// space, so a kernel can read / write it over PCIe — or nullptr for pageable memory.
-static void* mapped_host(const void* h) {
-    if (!h) return nullptr;
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
-}
-
 // Episode replay with HOST buffers.  Pinned buffers: one launch, the kernel accesses them itself.  Pageable buffers: pipelined in chunks
 // of steps over three streams: the copy-in stream uploads the actions of chunk c+1 while the caller's stream replays chunk c (one
 // fused launch per chunk) and the copy-out stream downloads the rewards / flags of chunk c-1.
@@ -489,8 +473,11 @@ int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host,
     CUDA_OK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)e->B;
-    const char* zc = std::getenv("QG_REPLAY_ZEROCOPY");                   // A/B runs: 0 = always stage through device buffers
-    if (!zc || std::atoi(zc) != 0) {
+    bool zero_copy = true;
+#ifdef QG_TOOLS_KNOBS
+    if (const char* zc = std::getenv("QG_REPLAY_ZEROCOPY")) zero_copy = std::atoi(zc) != 0;      // A/B runs: 0 = always stage through device buffers
+#endif
+    if (zero_copy) {
         // pinned host buffers: ONE launch for the whole episode, the kernel reading the actions (one step ahead) and writing reward /
         // done / success over PCIe itself (see qg_step_host); no staging copies, no chunk boundaries.  Measured at 65 536 envs:
         // 5.20 x 10^9 env-steps/s against 4.49 x 10^9 for the chunked copy pipeline below (and 5.09 x 10^9 device resident: the three
@@ -511,7 +498,9 @@ int qg_replay_host(qg_engine* e, int32_t num_steps, const int32_t* actions_host,
         // chunk: about 1 MB of actions per upload, at least 1 and at most 32 steps (the first upload and the last download are not
         // overlapped with compute; measured at 65 536 envs: chunks of 16 / 8 / 4 / 2 steps -> 4.35 / 4.45 / 4.51 / 3.67 x 10^9 env-steps/s)
         e->rp_chunk = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(1 << 20) / std::max<int64_t>((int64_t)B * 4, 1)));
+#ifdef QG_TOOLS_KNOBS
         if (const char* v = std::getenv("QG_REPLAY_CHUNK")) e->rp_chunk = std::max(1, std::atoi(v));      // A/B runs
+#endif
         CUDA_OK(cudaStreamCreateWithFlags(&e->rp_in, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&e->rp_out, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&e->rp_ev_start, cudaEventDisableTiming));
@@ -785,7 +774,7 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
     CUDA_OK(cudaSetDevice(e->device));
     StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic;      // (no packed-observation output: the kernel keeps the bit stream on chip)
     a.nsteps = 1; a.ring = 1; a.pdl_mode = 0; a.num_sms = e->num_sms;
-    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.sm_cat = -1; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4; a.symplectic = e->all_symplectic ? 1 : 0;
     a.magic_ow = magic40(((uint32_t)e->L.obs_size + 31u) / 32u);
     const size_t step_smem = (size_t)e->sm_warp_words * 4 + 16;

@@ -48,6 +48,7 @@ int validate_config(const qg_config* cfg) {
         default: break;
     }
     if (cfg->solution_capacity < 0 || cfg->solution_capacity > 65535) { set_error("solution_capacity must be in [0, 65535]"); return QG_ERR_INVALID; }
+    if (cfg->tile_envs != 0 && cfg->tile_envs != 16 && cfg->tile_envs != 32) { set_error("tile_envs must be 0 (automatic), 16 or 32"); return QG_ERR_INVALID; }
     return QG_OK;
 }
 

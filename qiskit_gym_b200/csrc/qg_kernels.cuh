@@ -18,6 +18,10 @@ namespace qg {
 
 struct StepArgs {
     const int32_t* actions;      // [B]            (MODE_STEP)
+    const uint8_t* actions8;     // [B] or null: the same stream as one byte per action (the packed host wire format, num_actions <= 256); read instead of `actions`
+    uint32_t* done_bits;         // [ceil(B/32)][bits_stride] or null: is_final of tile k (envs 32k..32k+31, bit = env % 32) after step t at [k][bits_t0 + t] ...
+    uint32_t* success_bits;      // ... and success, same layout: 2 bits per env-step instead of two bytes, written as whole 128-byte lines every 32 steps
+    int32_t bits_stride, bits_t0;
     const uint8_t* coins;        // [B] or null
     const uint32_t* perm_raw;    // [B] or null
     const float* weights;        // [B][A]         (MODE_SEARCH)
@@ -41,6 +45,7 @@ struct StepArgs {
     int64_t in_stride;           // elements between consecutive steps of actions / coins / perm_raw
     int64_t out_stride;          // elements between consecutive steps of reward / done / success
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
+    int32_t sm_cat;                          // offset of the tile's concatenated observation bit stream (expand_cat), or -1: not used by this launch
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
     uint64_t magic_ow;                // ceil(2^40/ceil(obs_size/32))        (packed observation)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
@@ -434,6 +439,7 @@ __device__ __forceinline__ float4 lut_get(const uint32_t* lut_lane /* lut + (lan
     return *reinterpret_cast<const float4*>(lut_lane + (nib << 5));
 }
 // 4 bits at bit offset `off` of environment e's observation bit stream (words at bits[w * kStride + e])
+template <int kStride>
 __device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t e, uint32_t off) {
     const uint32_t w = off >> 5, s = off & 31u;
     const uint32_t lo = bits[w * kStride + e];
@@ -441,11 +447,61 @@ __device__ __forceinline__ uint32_t stream_nibble(const uint32_t* bits, uint32_t
     return __funnelshift_r(lo, hi, s);
 }
 
+// ---- the tile's observations as ONE bit stream ------------------------------------------------------------------------------------
+// The warp's slab of the [B][obs] float tensor is contiguous, so bit (e * obs + i) of the concatenation of its environments' observation
+// bits is float number (e * obs + i) of the slab, whatever obs is.  With the concatenated stream in shared memory (cnt * obs / 32 words)
+// the expansion is the same loop for every observation size: lane l always holds nibble (l & 7) of words (l >> 3) + 4k — one LDS
+// (broadcast within a quarter warp), a shift, one table load and one 16-byte store per 512 bytes — instead of the per-float4
+// (environment, offset) bookkeeping that observations which are not whole words per environment used to need (C1: 81, C4: 500, C5: 729
+// entries: 40 instructions per store before, 5 after; ncu instruction counts in profiles/r2_*).
+// cat_gather builds the stream from the per-environment streams bits[word * kStride + env] (any obs; used by PauliNetwork); Permutation sets
+// its n one-hot bits per environment straight into the concatenated stream (cat_onehot), skipping the per-environment stream altogether.
+template <int kStride>
+__device__ __forceinline__ void cat_gather(const uint32_t* bits, uint32_t* cat, uint32_t cnt, uint32_t obs, uint64_t magic_obs, int lane) {
+    const uint32_t total = cnt * obs, nwords = (total + 31u) >> 5;
+    for (uint32_t W = lane; W < nwords; W += 32) {
+        uint32_t e = fastdiv40(W << 5, magic_obs), off = (W << 5) - e * obs, v = 0, filled = 0;
+        while (filled < 32u && e < cnt) {
+            const uint32_t len = min(32u - filled, obs - off), w = off >> 5, sft = off & 31u;
+            const uint32_t lo = bits[w * kStride + e], hi = (sft + len > 32u) ? bits[(w + 1) * kStride + e] : 0u;
+            uint32_t x = __funnelshift_r(lo, hi, sft);
+            if (len < 32u) x &= (1u << len) - 1u;
+            v |= x << filled;
+            filled += len; off += len;
+            if (off == obs) { off = 0; ++e; }
+        }
+        cat[W] = v;
+    }
+    __syncwarp();
+}
+template <class Wd>
+__device__ __forceinline__ void cat_onehot(const DevCfg& c, const Wd& S, uint32_t* cat, uint32_t cnt, bool live, int lane) {
+    const uint32_t obs = (uint32_t)c.obs_size, nwords = (cnt * obs + 31u) >> 5;
+    for (uint32_t W = lane; W < nwords; W += 32) cat[W] = 0;
+    __syncwarp();
+    if (live) {
+        uint32_t bit = (uint32_t)lane * obs;                      // row i of env `lane` starts at bit lane * obs + i * n (permutation.rs:241-243)
+        for (int i = 0; i < c.n; ++i, bit += (uint32_t)c.n) { const uint32_t b = bit + get8(S, i); atomicOr(cat + (b >> 5), 1u << (b & 31u)); }
+    }
+    __syncwarp();
+}
+template <bool PLAIN>
+__device__ __forceinline__ void expand_cat(const uint32_t* cat, const uint32_t* lut, float* out, uint32_t total /* cnt * obs floats */, int lane) {
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    const uint32_t nvec = vec_ok ? (total >> 2) : 0u, sh = ((uint32_t)lane & 7u) << 2;
+    const uint32_t* const lut_lane = lut + ((lane & 7) << 2);
+    const uint32_t* src = cat + ((uint32_t)lane >> 3);
+    float4* o = reinterpret_cast<float4*>(out) + lane;
+#pragma unroll 4
+    for (uint32_t j = lane; j < nvec; j += 32, src += 4, o += 32) st_rows<PLAIN>(o, lut_get(lut_lane, (*src >> sh) & 15u));
+    for (uint32_t f = (nvec << 2) + lane; f < total; f += 32) out[f] = ((cat[f >> 5] >> (f & 31u)) & 1u) ? 1.0f : 0.0f;
+}
+
 // Phase 2a: bits -> floats.  The warp's slab out[0 .. cnt*obs_size) is contiguous in the [B][obs_size] tensor; lane l
 // stores the float4 number l, l+32, ... (512 contiguous bytes per warp instruction).  (e, v) = (environment, float4 within
 // the environment) of a lane's float4 is tracked incrementally: advancing 32 float4s adds (q, r) with one conditional wrap,
 // so the loop has no division; the four floats come from the shared-memory table with one 128-bit load.
-template <int MODE>
+template <int MODE, int kStride>
 __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t* lut, float* out, uint32_t cnt, uint32_t obs, uint32_t en_bits, int lane,
                                            uint32_t magic_obs4 /*ceil(2^32/(obs/4)) or 0*/, uint64_t magic_obs, uint32_t q4, uint32_t r4, bool plain_rows) {
     // 16-byte stores need an aligned slab: always true for the engine's own [B][obs] tensors; a ring slot of an odd-sized
@@ -521,7 +577,7 @@ __device__ __forceinline__ void expand_obs(const uint32_t* bits, const uint32_t*
         if (nvec) {
 #pragma unroll 2
             for (uint32_t j = lane; j < nvec; j += 32) {
-                uint32_t nib = stream_nibble(bits, e, off);
+                uint32_t nib = stream_nibble<kStride>(bits, e, off);
                 const bool straddle = off + 4u > obs;                 // the float4 ends in environment e+1
                 if (straddle) { const uint32_t k = obs - off; nib = (nib & ((1u << k) - 1u)) | (bits[e + 1] << k); }
                 const bool on = (MODE != MODE_SEARCH) || (((en_bits >> e) & 1u) && (!straddle || ((en_bits >> (e + 1)) & 1u)));
@@ -601,10 +657,14 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
 // no output tensor is given, the records are not written back to global memory (tile_writeback does that once, at the end), the running
 // return is kept in ret_local[lane] (shared memory) instead of c.ret, and a resident Permutation's one-hot stream is patched (4 bits per
 // SWAP) instead of rebuilt.
-template <int KIND, int MODE, int INV>
+// EPW: environments per warp tile (32, or 16: twice the warps for the same batch, lanes 16..31 idle in phase 1 and at work in phase 2 —
+// at 65 536 environments that is 28 instead of 14 warps per SM to overlap one warp's latency-bound step logic with the others' stores).
+// The tile's shared-memory words are laid out [word][EPW + 1].
+template <int KIND, int MODE, int INV, int EPW = 32>
 __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a, uint32_t* const wbase, const uint32_t* const lut, const int lane,
                                               const int64_t e0, const int cnt, const bool resident = false, const float* const weights_tile = nullptr,
                                               const bool fused = false, float* const ret_local = nullptr) {
+    constexpr int kStride = EPW + 1;       // (shadows the namespace constant: everything below indexes the tile with this launch's stride)
     typedef SmWords<kStride> Wd;
     const int64_t env = e0 + lane;
     const bool live = lane < cnt;
@@ -613,6 +673,10 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
     const Wd SCR{wbase + a.sm_scr + lane}, O{wbase + a.sm_obs + lane};
     const bool obs_from_O = (KIND == QG_ENV_PAULI_NETWORK) || (KIND == QG_ENV_PERMUTATION && c.OW > 0);
     const uint32_t* const obs_bits = wbase + (obs_from_O ? a.sm_obs : c.off_state * kStride);
+    // dense observations that are not whole words per environment go through the tile's concatenated bit stream (expand_cat); search /
+    // slot launches, whose tiles may skip environments, keep the per-element path
+    const bool use_cat = MODE != MODE_SEARCH && a.obs && a.sm_cat >= 0 && !a.skip_negative && !fused;
+    uint32_t* const cat = wbase + (a.sm_cat >= 0 ? a.sm_cat : 0);
     uint32_t last_en_bits = 0;
     if (live && !resident) {
         const uint32_t* src = c.rec + (a.src_slot ? (int64_t)a.src_slot[env] : env);
@@ -631,10 +695,12 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
 
     // replay: the next step's action (and coin) is requested before this step's expansion, so its DRAM latency is hidden
     int next_action = -1; uint32_t next_coin = 0;
+    auto load_action = [&](size_t idx) { return a.actions8 ? (int)QG_LD_STREAM(a.actions8 + idx) : (int)QG_LD_STREAM(a.actions + idx); };
     if (MODE == MODE_STEP && live) {
-        next_action = QG_LD_STREAM(a.actions + env);
+        next_action = load_action((size_t)env);
         if (a.coins) next_coin = QG_LD_STREAM(a.coins + env);
     }
+    uint32_t acc_done = 0, acc_succ = 0;             // lane l: the tile's is_final / success ballots of step (t & ~31) + l (a.done_bits)
     for (int t = 0; t < a.nsteps; ++t) {
         bool success = (flags & FL_SUCCESS) != 0, enabled = live;
         const uint32_t coin_in = next_coin;
@@ -644,7 +710,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 action = next_action;
                 if (a.skip_negative && action < 0) enabled = false;
                 if (t + 1 < a.nsteps) {
-                    next_action = QG_LD_STREAM(a.actions + (size_t)(t + 1) * a.in_stride + env);
+                    next_action = load_action((size_t)(t + 1) * a.in_stride + env);
                     if (a.coins) next_coin = QG_LD_STREAM(a.coins + (size_t)(t + 1) * a.in_stride + env);
                 }
             }
@@ -771,7 +837,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 }
                 if (a.obs || a.obs_bits || fused) pn_build_obs(c, S, pr, O, perm_idx);
             }
-            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && (enabled || (fused && !resident)) && (a.obs || a.obs_bits || fused)) {
+            if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && (enabled || (fused && !resident)) && ((a.obs && !use_cat) || a.obs_bits || fused)) {
                 // one-hot rows: bit i*n + state[i] (permutation.rs:241-243)
                 if (oh_full) {
                     for (int w = 0; w < c.OW; ++w) O[w] = 0;
@@ -788,11 +854,37 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         const uint32_t mask_bits = __ballot_sync(0xFFFFFFFFu, live && !success);     // masks() = [!success; A] (clifford.rs:349-351)
         const uint32_t en_bits = __ballot_sync(0xFFFFFFFFu, live && enabled);
         if (MODE == MODE_SEARCH && a.num_active && lane == 0 && en_bits) atomicAdd(a.num_active, __popc(en_bits));
+        if (MODE == MODE_STEP && a.done_bits) {
+            // packed flags: lane (t % 32) keeps this step's two ballots; every 32 steps (and after the last one) the warp writes them as one
+            // coalesced line per plane: done_bits[tile][bits_t0 + t]
+            const uint32_t db = __ballot_sync(0xFFFFFFFFu, live && enabled && (depth == 0 || success));
+            const uint32_t sb = __ballot_sync(0xFFFFFFFFu, live && enabled && success);
+            if (lane == (t & 31)) { acc_done = db; acc_succ = sb; }
+            if ((t & 31) == 31 || t + 1 == a.nsteps) {
+                const int tl = (t & ~31) + lane;
+                if (tl <= t) {
+                    const size_t k = (size_t)(e0 >> 5) * (size_t)a.bits_stride + (size_t)(a.bits_t0 + tl);
+                    if (EPW == 32) {
+                        a.done_bits[k] = acc_done;
+                        if (a.success_bits) a.success_bits[k] = acc_succ;
+                    } else {                         // 16-env tiles: this tile's half of the 32-env word
+                        const size_t h = 2 * k + (size_t)((e0 >> 4) & 1);
+                        reinterpret_cast<uint16_t*>(a.done_bits)[h] = (uint16_t)acc_done;
+                        if (a.success_bits) reinterpret_cast<uint16_t*>(a.success_bits)[h] = (uint16_t)acc_succ;
+                    }
+                }
+            }
+        }
 
         // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab --------
         if (a.obs) {
             float* out = a.obs + ((size_t)slot * c.B + (size_t)e0) * c.obs_size;
-            if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r, a.nsteps > 1);
+            if (use_cat) {
+                if (KIND == QG_ENV_PERMUTATION) cat_onehot(c, S, cat, (uint32_t)cnt, live, lane);
+                else cat_gather<kStride>(obs_bits, cat, (uint32_t)cnt, (uint32_t)c.obs_size, a.magic_obs, lane);
+                if (a.nsteps > 1) expand_cat<true>(cat, lut, out, (uint32_t)cnt * (uint32_t)c.obs_size, lane);
+                else expand_cat<false>(cat, lut, out, (uint32_t)cnt * (uint32_t)c.obs_size, lane);
+            } else if (KIND != QG_ENV_PERMUTATION || c.OW > 0) expand_obs<MODE, kStride>(obs_bits, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_bits, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r, a.nsteps > 1);
             else {
                 // large Permutation (no room for a bit stream in shared memory): one-hot test straight from the packed bytes
                 const uint32_t total = (uint32_t)cnt * (uint32_t)c.obs_size, n = (uint32_t)c.n;
@@ -851,14 +943,14 @@ __device__ __forceinline__ void tile_writeback(const DevCfg& c, const uint32_t* 
 
 // INV: register bucket of the add_inverts inverse (qg_gf2.cuh): 0 = generic shared-memory Gauss-Jordan (or no inverts),
 // 8 / 16 / 32 = matrix dimension bound of the register-resident versions.
-template <int KIND, int MODE, int INV>
+template <int KIND, int MODE, int INV, int EPW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.pdl_mode == 1) pdl_launch_dependents();
-    const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * 32;
+    const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * EPW;
     if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
-    const int cnt = (int)min((int64_t)32, c.B - e0);
+    const int cnt = (int)min((int64_t)EPW, c.B - e0);
     uint32_t* const wbase = smem + kLutWords + (size_t)warp * a.sm_warp_words;
     const uint32_t* const lut = smem;                // nibble -> float4 table, first kLutWords words of the CTA's shared memory
     if (a.obs) lut_fill(smem, lane);
@@ -875,7 +967,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
             __nanosleep(200);
         }
     }
-    step_tile<KIND, MODE, INV>(c, a, wbase, lut, lane, e0, cnt);
+    step_tile<KIND, MODE, INV, EPW>(c, a, wbase, lut, lane, e0, cnt);
 }
 
 // ---- load (set_state / constructor) --------------------------------------------------------------

@@ -11,6 +11,7 @@ struct LaunchGeom {
     unsigned grid;
     size_t smem_bytes;
     int pdl;            // launch with the programmatic-stream-serialization attribute
+    int epw = 32;       // environments per warp tile: 32 or 16 (see step_tile)
     const void* l2_base = nullptr;   // persisting-L2 access window (bytes 0 = none)
     size_t l2_bytes = 0;
 };

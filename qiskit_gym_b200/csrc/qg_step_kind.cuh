@@ -7,8 +7,8 @@
 
 namespace qg {
 
-template <int KIND, int MODE, int INV>
-cudaError_t launch_one(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, cudaStream_t st) {
+template <int KIND, int MODE, int INV, int EPW>
+cudaError_t launch_epw(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, cudaStream_t st) {
     // programmatic dependent launch: the grid may start while its predecessor in the stream drains; the kernel
     // waits (griddepcontrol.wait) before it touches the records
     cudaLaunchConfig_t lc{};
@@ -26,7 +26,14 @@ cudaError_t launch_one(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, 
         ++na;
     }
     lc.attrs = at; lc.numAttrs = na;
-    return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV>, c, a);
+    return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV, EPW>, c, a);
+}
+
+template <int KIND, int MODE, int INV>
+cudaError_t launch_one(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, cudaStream_t st) {
+    // 16-env tiles exist for the stepping modes only (MODE_OBSERVE launches are rare reads)
+    if constexpr (MODE != MODE_OBSERVE) { if (g.epw == 16) return launch_epw<KIND, MODE, INV, 16>(c, a, g, st); }
+    return launch_epw<KIND, MODE, INV, 32>(c, a, g, st);
 }
 
 constexpr bool kind_has_matrix_inverse(int kind) { return kind == QG_ENV_LINEAR_FUNCTION || kind == QG_ENV_CLIFFORD; }
@@ -58,9 +65,15 @@ cudaError_t prepare_one(size_t smem_bytes) {
     // same shared-memory carve-out as the policy kernel (qg_policy.cu): alternating launches of the two in a search do not make
     // the SMs reconfigure their L1 / shared-memory split in between
     int carve = (int)cudaSharedmemCarveoutMaxShared;
+#ifdef QG_TOOLS_KNOBS
     if (const char* v = std::getenv("QG_CARVEOUT")) carve = std::atoi(v);      // A/B runs: -1 = driver default, 0..100 = percent shared
-    cudaError_t e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+#endif
+    cudaError_t e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if constexpr (MODE != MODE_OBSERVE) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
     return e;
 }
 

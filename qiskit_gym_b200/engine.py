@@ -60,6 +60,8 @@ class BatchedEnv:
         if h:
             try:
                 lib().qg_destroy(h)
+                for p in getattr(self, "_host_bufs", []):
+                    lib().qg_host_free(p)
             except Exception:
                 pass
             self._h = None
@@ -238,7 +240,104 @@ class BatchedEnv:
         check(lib().qg_solution_host(self._h, env, buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), self._stream()))
         return [int(v) for v in buf[: n.value]]
 
+    def solutions(self, first: int = 0, count: int | None = None, cap: int | None = None):
+        """Env::solution of envs first .. first+count-1 in one kernel + one copy (qg_solutions_host): a list of action lists."""
+        count = self.batch - first if count is None else int(count)
+        if cap is None:
+            cap = max(int(self.cfg.solution_capacity) or (int(self.cfg.max_depth) + 16), 1)
+        out = np.zeros((max(count, 1), cap), dtype=np.uint32)
+        lens = np.zeros(max(count, 1), dtype=np.int32)
+        check(lib().qg_solutions_host(self._h, first, count, out.ctypes.data_as(C.c_void_p), cap, lens.ctypes.data_as(C.c_void_p), self._stream()))
+        if (lens[:count] < 0).any():
+            raise ValueError(f"a solution is longer than cap={cap}")
+        return [out[i, : lens[i]].astype(np.int64).tolist() for i in range(count)]
+
+    # ------------------------------------------------------------------ packed host wire format / NUMA-local pinned memory
+    def host_buffer(self, shape, dtype) -> np.ndarray:
+        """A pinned host array on the GPU's NUMA node (qg_host_alloc), freed with the engine object."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape))
+        p, node = C.c_void_p(), C.c_int32()
+        check(lib().qg_host_alloc(self.device_index, n * dt.itemsize, C.byref(p), C.byref(node)))
+        self._host_bufs = getattr(self, "_host_bufs", [])
+        self._host_bufs.append(p)
+        self.numa_node = int(node.value)
+        buf = (C.c_uint8 * max(n * dt.itemsize, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+    def flag_words(self) -> int:
+        """Tiles of 32 envs: rows of the packed done / success bit planes uint32[flag_words, T]."""
+        return (self.batch + 31) // 32
+
+    def replay_host_packed(self, actions8: np.ndarray, done_bits: np.ndarray, success_bits: np.ndarray | None = None, reward: np.ndarray | None = None,
+                           reward_dev: torch.Tensor | None = None, coins: np.ndarray | None = None, obs: torch.Tensor | None = None,
+                           mask: torch.Tensor | None = None):
+        """qg_replay_host_packed: uint8 actions [T, B] in; f32 reward [T, B] (host, or kept on the device in reward_dev) and the
+        is_final / success bit planes uint32[ceil(B/32), T] out; pinned buffers (host_buffer) only."""
+        assert actions8.dtype == np.uint8 and actions8.flags.c_contiguous and actions8.shape[-1] == self.batch
+        T = int(actions8.shape[0])
+        ring = 1
+        if obs is not None:
+            ring = obs.numel() // (self.batch * self._obs_size)
+        if mask is not None:
+            mring = mask.numel() // (self.batch * self._A)
+            assert obs is None or mring == ring, "obs and mask rings differ"
+            ring = mring
+        for a_ in (done_bits, success_bits):
+            assert a_ is None or (a_.dtype == np.uint32 and a_.flags.c_contiguous and a_.size == self.flag_words() * T)
+        assert reward is None or (reward.dtype == np.float32 and reward.flags.c_contiguous and reward.size == T * self.batch)
+        assert reward_dev is None or (reward_dev.dtype == torch.float32 and reward_dev.is_contiguous() and reward_dev.numel() == T * self.batch)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib().qg_replay_host_packed(self._h, T, p(actions8), p(coins), _dptr(obs), _dptr(mask), ring, p(reward), _dptr(reward_dev),
+                                          p(done_bits), p(success_bits), self._stream()))
+
+    def replay_packed(self, actions8: torch.Tensor, done_bits: torch.Tensor | None = None, success_bits: torch.Tensor | None = None,
+                      reward: torch.Tensor | None = None, coins: torch.Tensor | None = None, obs: torch.Tensor | None = None, mask: torch.Tensor | None = None):
+        """Device-resident form of the packed formats (qg_replay_packed)."""
+        assert actions8.dtype == torch.uint8 and actions8.is_cuda and actions8.is_contiguous() and actions8.shape[-1] == self.batch
+        T = int(actions8.shape[0])
+        ring = 1
+        if obs is not None:
+            ring = obs.numel() // (self.batch * self._obs_size)
+        if mask is not None:
+            ring = mask.numel() // (self.batch * self._A)
+        check(lib().qg_replay_packed(self._h, T, _dptr(actions8), _dptr(coins), _dptr(obs), _dptr(mask), ring, _dptr(reward),
+                                     _dptr(done_bits), _dptr(success_bits), self._stream()))
+
+    @staticmethod
+    def unpack_flag_bits(bits: np.ndarray, batch: int) -> np.ndarray:
+        """uint32[ceil(B/32), T] bit plane -> uint8[T, B]."""
+        tiles, T = bits.shape
+        b = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(np.uint8)      # [tile, T, 32]
+        return np.ascontiguousarray(b.transpose(1, 0, 2).reshape(T, tiles * 32)[:, :batch])
+
+    # ------------------------------------------------------------------ DLPack
+    def dlpack_obs(self, ring: int = 1) -> torch.Tensor:
+        """The engine-owned observation ring as a torch tensor through a DLPack capsule (qg_dlpack_obs): zero-copy, float32
+        [B, rows, cols] (or [ring, B, rows, cols]); pass it as `obs=` to step / replay.  Must not outlive this object."""
+        import ctypes
+        m, ptr = C.c_void_p(), C.c_void_p()
+        check(lib().qg_dlpack_obs(self._h, int(ring), C.byref(m), C.byref(ptr)))
+        new_capsule = ctypes.pythonapi.PyCapsule_New
+        new_capsule.restype = ctypes.py_object
+        new_capsule.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+        cap = new_capsule(m.value, b"dltensor", None)
+        t = torch.utils.dlpack.from_dlpack(cap)
+        assert t.data_ptr() == ptr.value
+        return t
+
     # ------------------------------------------------------------------ synth search pieces
+    def search_finish(self, comm=None, cap: int | None = None):
+        """End of a (sharded) search: (key, success, global rollout id, owner rank, actions or None) — qg_search_finish.  `comm`: an
+        ncclComm_t handle (nccl_comm_create) or None."""
+        if cap is None:
+            cap = max(int(self.cfg.solution_capacity) or (int(self.cfg.max_depth) + 16), 1)
+        key, ok, rid, owner, n = C.c_int64(), C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        buf = np.zeros(cap, dtype=np.uint32)
+        check(lib().qg_search_finish(self._h, comm, C.byref(key), C.byref(ok), C.byref(rid), C.byref(owner), buf.ctypes.data_as(C.c_void_p), cap,
+                                     C.byref(n), self._stream()))
+        return key.value, bool(ok.value), rid.value, owner.value, ([int(v) for v in buf[: n.value]] if ok.value else None)
+
     def search_begin(self, seed: int = 0, first_rollout_id: int = 0):
         check(lib().qg_search_begin(self._h, C.c_uint64(seed & (2**64 - 1)), first_rollout_id, self._stream()))
 
@@ -345,3 +444,25 @@ class BatchedEnv:
         out = torch.zeros(self.batch, dtype=torch.float32, device=self.device)
         check(lib().qg_read_returns(self._h, _dptr(out), self._stream()))
         return out
+
+
+def nccl_comm_create(device: int, group=None):
+    """An ncclComm_t of the C ABI's own (qg_nccl_comm_create) over the ranks of a torch.distributed group: rank 0 draws the unique id
+    and torch.distributed ships the 128 bytes (any channel would do: a Rust host would use its own)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    idb = (C.c_uint8 * 128)()
+    if rank == 0:
+        check(lib().qg_nccl_unique_id(idb))
+    t = torch.tensor(list(idb), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda(device)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    idb = (C.c_uint8 * 128)(*[int(v) for v in t.cpu().tolist()])
+    comm = C.c_void_p()
+    check(lib().qg_nccl_comm_create(idb, rank, world, int(device), C.byref(comm)))
+    return comm
+
+
+def nccl_comm_destroy(comm):
+    check(lib().qg_nccl_comm_destroy(comm))

@@ -103,6 +103,63 @@ class FusedPolicy:
         return probs if probs is not None else (logits if logits is not None else values)
 
 
+class TensorCorePolicy:
+    """The same network for large batches on tcgen05 tensor cores (`qg_policy_tc_*`, csrc/qg_policy_tc.cu): packed observation bits in,
+    softmax action weights / logits / values out; f16 hi+lo split operands with f32 accumulation (logits within 1e-4 of the f32 module)."""
+
+    def __init__(self, policy: torch.nn.Module, max_batch: int, device=None, with_value: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("qiskit_gym_b200 needs a CUDA device (no CPU fallback)")
+        self.device_index = torch.cuda.current_device() if device is None else (device.index if isinstance(device, torch.device) else int(device))
+        self.device = torch.device("cuda", self.device_index)
+        layers = action_layers(policy)
+        ws = [np.ascontiguousarray(l.weight.detach().cpu().numpy(), dtype=np.float32) for l in layers]
+        bs = [np.ascontiguousarray(l.bias.detach().cpu().numpy(), dtype=np.float32) for l in layers]
+        self.obs_size = int(ws[0].shape[1])
+        self.obs_words = (self.obs_size + 31) // 32
+        self.num_actions = int(ws[-1].shape[0])
+        self.max_batch = int(max_batch)
+        self.version = weights_version(policy)
+        n = len(ws)
+        widths = (C.c_int32 * n)(*[int(w.shape[0]) for w in ws])
+        wp = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
+        bp = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
+        vw, vb = None, 0.0
+        self.has_value = False
+        if with_value:
+            head = simple_value_head(policy)
+            if head is None:
+                raise NotImplementedError("TensorCorePolicy(with_value=True) needs single-Linear action and value heads on the same activations")
+            vwa = np.ascontiguousarray(head.weight.detach().cpu().numpy().reshape(-1), dtype=np.float32)
+            vw, vb = vwa.ctypes.data_as(C.c_void_p), float(head.bias.detach().cpu().numpy().reshape(-1)[0])
+            self.has_value = True
+        h = C.c_void_p()
+        check(lib().qg_policy_tc_create(self.device_index, self.obs_size, n, widths, wp, bp, vw, C.c_float(vb), self.max_batch, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().qg_policy_tc_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward_bits(self, obs_bits: torch.Tensor, probs: torch.Tensor | None = None, logits: torch.Tensor | None = None,
+                     values: torch.Tensor | None = None):
+        assert obs_bits.is_cuda and obs_bits.element_size() == 4 and obs_bits.is_contiguous() and obs_bits.shape[-1] == self.obs_words
+        B = obs_bits.numel() // self.obs_words
+        if probs is None and logits is None and values is None:
+            probs = torch.empty((B, self.num_actions), dtype=torch.float32, device=obs_bits.device)
+        for t in (probs, logits):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == B * self.num_actions)
+        assert values is None or (self.has_value and values.dtype == torch.float32 and values.is_contiguous() and values.numel() == B)
+        st = C.c_void_p(torch.cuda.current_stream(obs_bits.device).cuda_stream)
+        check(lib().qg_policy_tc_forward_bits(self._h, _dptr(obs_bits), B, _dptr(probs), _dptr(logits), _dptr(values), st))
+        return probs if probs is not None else (logits if logits is not None else values)
+
+
 def pack_obs_bits(obs: torch.Tensor) -> torch.Tensor:
     """Dense 0/1 observation [B, ...] -> packed int32 [B, ceil(obs/32)] (host-side helper for tests and tools)."""
     flat = (obs.reshape(obs.shape[0], -1) != 0).cpu().numpy()

@@ -166,8 +166,21 @@ class RolloutSearch:
             self._graphs[deterministic] = g
         return g
 
+    def _local_best(self, comm):
+        """(key, solution or None) of this rank's rollouts — or, with an ncclComm_t of the C ABI (engine.nccl_comm_create), of ALL ranks'
+        rollouts: qg_search_finish does the cross-GPU reduction itself (one all-gather + on-GPU pick), no torch collective."""
+        env = self.env
+        if comm is not None:
+            key, ok, rid, owner, sol = env.search_finish(comm)
+            return key, sol, True
+        key, idx = env.search_best()
+        ok, rid = decode_key(key)
+        return key, (env.solution(idx) if (ok and idx >= 0) else None), False
+
     def solve(self, state, deterministic: bool = False, seed: int = 0, first_rollout_id: int = 0, check_every: int = 8,
-              group=None) -> SearchResult:
+              group=None, comm=None) -> SearchResult:
+        """group: torch.distributed group for the Python-side cross-rank reduction (reduce_best); comm: an ncclComm_t handle for the
+        C-side one (qg_search_finish); with neither, and torch.distributed initialised, the default group is used."""
         env = self.env
         t0 = time.perf_counter()
         if self.backend == "persistent":
@@ -176,11 +189,9 @@ class RolloutSearch:
                 env.search_begin(seed, first_rollout_id)
                 self._observe()
                 env.search_run(self.fused, self.obs_bits, self.probs, self.max_depth, deterministic=deterministic, decisions=self._decisions)
-                key, idx = env.search_best()
-                ok, rid = decode_key(key)
-                sol = env.solution(idx) if (ok and idx >= 0) else None
+                key, sol, reduced = self._local_best(comm)
                 its = int(self._decisions.max().item())
-            return self._finish(key, sol, its, t0, group)
+            return self._finish(key, sol, its, t0, group, reduced)
         with torch.cuda.stream(self._stream):
             env.set_state(state)                         # broadcast: every rollout starts from the target
             if self.use_graph:
@@ -197,12 +208,10 @@ class RolloutSearch:
                 its += 1
                 if its % check_every == 0 and int(self.num_active.item()) == 0:
                     break
-            key, idx = env.search_best()
-            ok, rid = decode_key(key)
-            sol = env.solution(idx) if (ok and idx >= 0) else None
-        return self._finish(key, sol, its, t0, group)
+            key, sol, reduced = self._local_best(comm)
+        return self._finish(key, sol, its, t0, group, reduced)
 
-    def _finish(self, key, sol, its, t0, group):
+    def _finish(self, key, sol, its, t0, group, reduced=False):
         env = self.env
         ok, rid = decode_key(key)
         world = 1
@@ -210,7 +219,8 @@ class RolloutSearch:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 world = dist.get_world_size(group)
-                key, sol = reduce_best(key, sol, group=group, device=env.device if dist.get_backend(group) == "nccl" else None)
+                if not reduced:
+                    key, sol = reduce_best(key, sol, group=group, device=env.device if dist.get_backend(group) == "nccl" else None)
                 ok, rid = decode_key(key)
         except ImportError:
             pass

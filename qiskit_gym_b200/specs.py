@@ -36,15 +36,15 @@ class SynthSpec:
             raise ValueError(f"Synth env class {cls_name} not supported, should be {list(_KINDS)}")
         self.cls_name = cls_name
         self.kind = _KINDS[cls_name]
-        self.config = dict(config)
-        self.config["gateset"] = [(g, tuple(int(q) for q in qs)) for g, qs in config["gateset"]]
+        self.config = dict(config)                       # kept exactly as given: to_json() round-trips the reference's JSON files
+        self.gateset = [(g, tuple(int(q) for q in qs)) for g, qs in config["gateset"]]
         kw = {k: self.config[k] for k in _ENGINE_KEYS if k in self.config}
         if self.kind != _abi.ENV_PAULI_NETWORK:
             kw = {k: v for k, v in kw.items() if k in ("metrics_weights", "add_inverts", "add_perms", "track_solution")}
         else:
             kw.pop("add_inverts", None)
             kw.setdefault("max_rotations", 5)
-        self._cfg = host.make_config(self.kind, self.config["num_qubits"], self.config["gateset"], self.config.get("difficulty", 1),
+        self._cfg = host.make_config(self.kind, self.config["num_qubits"], self.gateset, self.config.get("difficulty", 1),
                                      self.config.get("depth_slope", 2), self.config.get("max_depth", 128), **kw)
         host.validate(self._cfg)
         self._rotation_params = []
@@ -76,7 +76,7 @@ class SynthSpec:
         return host.obs_shape(self._cfg)
 
     def num_actions(self) -> int:
-        return len(self.config["gateset"])
+        return len(self.gateset)
 
     # ---- wire formats -----------------------------------------------------------------------------------------------------
     def _tableau(self, target) -> np.ndarray:
@@ -119,7 +119,7 @@ class SynthSpec:
     def build_circuit_from_solution(self, actions, target=None):
         """Env::solution -> gate list.  Clifford targets that carry a phase column get the trailing Pauli layer that fixes the signs
         (what envs/synthesis.py:162-177, 211-217 does with Qiskit objects); PauliNetwork solutions are decoded into gates and rotations."""
-        gs = self.config["gateset"]
+        gs = self.gateset
         if self.kind == _abi.ENV_PAULI_NETWORK:
             return wire.pauli_solution_to_gates(gs, actions, self._rotation_params or None)
         gates = wire.solution_to_gates(gs, actions)

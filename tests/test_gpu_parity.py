@@ -76,6 +76,18 @@ def test_step_parity(name):
     run_parity(name)
 
 
+@pytest.mark.parametrize("tile", [16, 32])
+@pytest.mark.parametrize("name", ["C1_perm_grid3", "C2_lf8_line", "C3_clifford8_full", "C4_pauli10_line", "C5_perm27_heavyhex", "pauli6_line",
+                                  "clifford20_line", "lf11_line", "perm5_mixed"])
+def test_parity_for_both_tile_sizes(name, tile):
+    """qg_config.tile_envs: 16- and 32-env warp tiles (what a launch picks from the batch size when it is 0) give the same bits, single
+    steps and replay, with and without the add_inverts inverse; B = 77 leaves a ragged last tile for both."""
+    kind = H.config_table()[name][0]
+    run_parity(name, B=77, T=20, seed=31, tile_envs=tile, add_inverts=(kind != H.PAULI), add_perms=(kind == H.PAULI),
+               invalid_rate=0.0 if kind == H.PAULI else 0.05)          # (the reference panics on an out-of-range action under add_perms, pauli.rs:594-599)
+    run_replay_parity(name, B=77, T=35, seed=32, tile_envs=tile, ring=3)
+
+
 @pytest.mark.parametrize("name", ["C1_perm_grid3", "C2_lf8_line", "C3_clifford8_full", "C5_perm27_heavyhex", "lf5_line_swap",
                                   "clifford5_allgates", "perm5_mixed"])
 def test_step_parity_with_inverts(name):
