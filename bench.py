@@ -533,7 +533,8 @@ def run_collector(args, dev, local, rank, world):
 
     def leg_packed():
         col = RolloutCollector(env, pol, use_twists=False, seed=rank)
-        col.collect_packed(4)
+        col.collect_packed(T)              # eager (lazy initialisation)
+        col.collect_packed(T)              # captured into a CUDA graph and replayed
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

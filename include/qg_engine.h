@@ -278,6 +278,13 @@ QG_API int qg_nccl_comm_destroy(qg_nccl_comm comm);
 QG_API int qg_collect_step(qg_engine* e, uint64_t seed, const float* weights_dev, int32_t deterministic,
                            float* obs_dev, uint8_t* mask_dev, int32_t* chosen_dev,
                            float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
+/* The two collector calls with the Philox seed of the decision read from DEVICE memory when the kernel runs (*seed_dev), so that a decision —
+ * or a whole rollout of decisions — captured in a CUDA graph can be replayed with fresh seeds: the host rewrites the seed words between
+ * replays.  Otherwise identical to qg_reset_select / qg_collect_step. */
+QG_API int qg_reset_select_dev(qg_engine* e, const uint64_t* seed_dev, int64_t first_env_id, const uint8_t* select_dev, qg_stream stream);
+QG_API int qg_collect_step_dev(qg_engine* e, const uint64_t* seed_dev, const float* weights_dev, int32_t deterministic,
+                               float* obs_dev, uint8_t* mask_dev, int32_t* chosen_dev,
+                               float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream);
 /* Generalised advantage estimation over a rollout laid out [num_steps][batch] (value_dev has num_steps + 1 rows, the
  * last one bootstraps the truncated episodes):  nd = !done[t];  delta = (reward[t] + (gamma*value[t+1])*nd) - value[t];
  * adv[t] = delta + ((gamma*lambda)*nd)*adv[t+1];  ret[t] = adv[t] + value[t]  — f32, every operation rounded on its
@@ -346,6 +353,9 @@ QG_API int qg_policy_tc_create(int32_t device, int32_t obs_size, int32_t num_lay
                                const float* value_weight_host, float value_bias, int64_t max_batch, qg_policy_tc** out);
 QG_API void qg_policy_tc_destroy(qg_policy_tc* p);
 QG_API int32_t qg_policy_tc_num_actions(const qg_policy_tc* p);
+/* A three-layer policy whose padded widths fit (embeddings a multiple of 128, common layer <= 256) runs as ONE kernel that keeps the hidden
+ * activations on chip; per_layer = 1 forces the one-kernel-per-layer path instead (same arithmetic).  Returns 1 if the fused kernel will run. */
+QG_API int32_t qg_policy_tc_set_mode(qg_policy_tc* p, int32_t per_layer);
 QG_API int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev, float* logits_dev,
                                      float* values_dev, qg_stream stream);
 

@@ -31,7 +31,8 @@ SYMBOLS = [
     "qg_step_slots", "qg_copy_records", "qg_mcts_begin", "qg_mcts_select", "qg_mcts_backup", "qg_mcts_root_weights", "qg_search_run",
     "qg_solutions", "qg_solutions_host", "qg_replay_host_packed", "qg_replay_packed", "qg_host_alloc", "qg_host_free", "qg_bind_thread_to_device",
     "qg_dlpack_obs", "qg_search_finish", "qg_nccl_unique_id", "qg_nccl_comm_create", "qg_nccl_comm_destroy",
-    "qg_policy_tc_create", "qg_policy_tc_destroy", "qg_policy_tc_num_actions", "qg_policy_tc_forward_bits",
+    "qg_policy_tc_create", "qg_policy_tc_destroy", "qg_policy_tc_num_actions", "qg_policy_tc_forward_bits", "qg_policy_tc_set_mode",
+    "qg_reset_select_dev", "qg_collect_step_dev",
 ]
 
 
@@ -149,6 +150,9 @@ def lib():
     L.qg_policy_tc_destroy.restype = None
     L.qg_policy_tc_num_actions.argtypes = [vp]
     L.qg_policy_tc_forward_bits.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    L.qg_policy_tc_set_mode.argtypes = [vp, i32]
+    L.qg_reset_select_dev.argtypes = [vp, vp, i64, vp, vp]
+    L.qg_collect_step_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

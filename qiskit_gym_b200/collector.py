@@ -122,6 +122,7 @@ class RolloutCollector:
         self._gen = torch.Generator(device=env.device)
         self._gen.manual_seed(self.seed & (2**63 - 1))
         self.hook = None                  # tests: called as hook(t, weights [B, A] in env action order) before each collect step
+        self._packed = {}                 # collect_packed: buffers / CUDA graph per (num_steps, deterministic)
 
     def _policy(self, obs):
         with torch.no_grad():
@@ -139,10 +140,13 @@ class RolloutCollector:
                 logits, value = self.policy(obs)
             return torch.softmax(logits.float(), dim=-1), value.float().reshape(-1)
 
-    def collect_packed(self, num_steps: int, deterministic: bool = False) -> Rollout:
+    def collect_packed(self, num_steps: int, deterministic: bool = False, use_cuda_graph: bool = True) -> Rollout:
         """The large-batch collection path: packed-bit observations (32x less observation traffic than dense f32) and the policy on the
         tensor cores (policy.TensorCorePolicy, tcgen05).  Per decision: reset_select -> observe_bits -> qg_policy_tc_forward_bits (softmax
-        weights + value) -> qg_collect_step; log-probabilities and GAE once at the end.  No twists on this path."""
+        weights + value) -> qg_collect_step; log-probabilities and GAE once at the end.  No twists on this path.
+        use_cuda_graph: the whole rollout (num_steps decisions, ~6 launches each) is captured once and replayed; the decisions' Philox seeds
+        are read from a device array the host refills before every replay (qg_reset_select_dev / qg_collect_step_dev).  The returned tensors
+        are the collector's own buffers: they are overwritten by the next call with the same num_steps."""
         from .policy import TensorCorePolicy, weights_version
         env, T, B = self.env, int(num_steps), self.env.batch
         dev, A = env.device, env.num_actions()
@@ -151,23 +155,45 @@ class RolloutCollector:
         tcp = getattr(self, "_tcp", None)
         if tcp is None or tcp.version != weights_version(self.policy) or tcp.max_batch < B:
             tcp = self._tcp = TensorCorePolicy(self.policy, max_batch=B, device=dev, with_value=True)
-        ow = env.obs_words()
-        bits = torch.empty((T + 1, B, ow), dtype=torch.int32, device=dev)
-        probs = torch.empty((T, B, A), dtype=torch.float32, device=dev)
-        actions = torch.full((T, B), -1, dtype=torch.int32, device=dev)
-        rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
-        dones = torch.zeros((T, B), dtype=torch.bool, device=dev)
-        succ = torch.zeros((T, B), dtype=torch.bool, device=dev)
-        values = torch.zeros((T + 1, B), dtype=torch.float32, device=dev)
-        for t in range(T):
-            s = decision_seed(self.seed, self.counter)
-            env.reset_select(s, self.first_env_id)
-            env.observe_bits(bits[t])
-            tcp.forward_bits(bits[t], probs=probs[t], values=values[t])
-            env.collect_step(probs[t], s, deterministic=deterministic, obs=False, chosen=actions[t], reward=rewards[t], done=dones[t], success=succ[t])
-            self.counter += 1
-        env.observe_bits(bits[T])
-        tcp.forward_bits(bits[T], values=values[T])
+            self._packed = {}
+        st = self._packed.get((T, deterministic))
+        if st is None:
+            ow = env.obs_words()
+            st = {"bits": torch.empty((T + 1, B, ow), dtype=torch.int32, device=dev), "probs": torch.empty((T, B, A), dtype=torch.float32, device=dev),
+                  "actions": torch.full((T, B), -1, dtype=torch.int32, device=dev), "rewards": torch.zeros((T, B), dtype=torch.float32, device=dev),
+                  "dones": torch.zeros((T, B), dtype=torch.bool, device=dev), "succ": torch.zeros((T, B), dtype=torch.bool, device=dev),
+                  "values": torch.zeros((T + 1, B), dtype=torch.float32, device=dev), "seeds": torch.zeros(T, dtype=torch.int64, device=dev),
+                  "seeds_host": torch.zeros(T, dtype=torch.int64).pin_memory(), "graph": None, "runs": 0}
+            self._packed[(T, deterministic)] = st
+        bits, probs, actions, rewards, dones, succ, values, seeds = (st[k] for k in ("bits", "probs", "actions", "rewards", "dones", "succ", "values", "seeds"))
+        for t in range(T):          # the seeds of this rollout's decisions (two's-complement view of the uint64 seeds)
+            s_ = decision_seed(self.seed, self.counter + t)
+            st["seeds_host"][t] = s_ - (1 << 64) if s_ >= (1 << 63) else s_
+        seeds.copy_(st["seeds_host"], non_blocking=True)
+        self.counter += T
+
+        def body():
+            for t in range(T):
+                env.reset_select_dev(seeds[t:t + 1], self.first_env_id)
+                env.observe_bits(bits[t])
+                tcp.forward_bits(bits[t], probs=probs[t], values=values[t])
+                env.collect_step_dev(probs[t], seeds[t:t + 1], deterministic=deterministic, chosen=actions[t], reward=rewards[t], done=dones[t], success=succ[t])
+            env.observe_bits(bits[T])
+            tcp.forward_bits(bits[T], values=values[T])
+
+        if not use_cuda_graph:
+            body()
+        elif st["graph"] is None and st["runs"] == 0:
+            body()                                  # the first rollout runs eagerly (lazy initialisation outside any capture) ...
+            st["runs"] = 1
+        else:
+            if st["graph"] is None:                 # ... the second one is captured, then replayed
+                torch.cuda.current_stream(dev).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    body()
+                st["graph"] = g
+            st["graph"].replay()
         valid = actions >= 0
         a = actions.long().clamp_(min=0)
         logp = torch.log(probs.gather(2, a[..., None]).squeeze(2).clamp_min(1e-38))

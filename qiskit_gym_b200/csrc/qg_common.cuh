@@ -58,6 +58,8 @@ struct DevCfg {
     const uint16_t* aperms;   // [nperms][A]
     const uint32_t* pgen;     // PauliNetwork reset generator tables (see k_reset_pauli)
     uint64_t seed; int64_t first_id;
+    const uint64_t* seed_dev; // if set, the Philox seed is read from device memory at launch time instead (CUDA-graph replays: the host
+                              // rewrites the word between replays; qg_reset_select_dev / qg_collect_step_dev)
     uint32_t magic_n;         // ceil(2^32 / n): exact division of obs offsets by n (Permutation expander)
     int32_t row_shift;        // LinearFunction / Clifford: log2(D) when D is a power of two <= 32 (a row then lies inside one word at bit offset
                               // (r << row_shift) & 31 and the row primitives are one load / shift / xor / store), else -1
@@ -80,6 +82,7 @@ __host__ __device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint64_t
 }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ uint64_t seed_of(const DevCfg& c) { return c.seed_dev ? *c.seed_dev : c.seed; }
 // ---- per-thread word array living in shared memory with stride EPC (bank == lane, conflict free
 //      for any per-thread dynamic index) ------------------------------------------------------------
 template <int EPC>

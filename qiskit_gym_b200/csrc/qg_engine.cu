@@ -95,6 +95,10 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
     const bool cat_in_O = e->L.kind == QG_ENV_PERMUTATION && !a.obs_bits && cat_w <= e->L.OW * stride;
     a.sm_cat = (cat_w && a.obs && mode != MODE_SEARCH && !a.skip_negative) ? (cat_in_O ? a.sm_obs : lay_words * stride) : -1;
     a.sm_warp_words = lay_words * stride + ((a.sm_cat >= 0 && !cat_in_O) ? cat_w : 0);
+    a.sm_wts = -1;
+    if (mode == MODE_SEARCH && a.weights && (int64_t)(e->L.A | 1) * epw * 4 <= 16 * 1024) {        // staged action weights (step_tile)
+        a.sm_wts = a.sm_warp_words; a.sm_warp_words += (e->L.A | 1) * epw;
+    }
     a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     { const uint32_t vpe = (uint32_t)e->L.obs_size / 4; a.exp_q = vpe ? 32u / vpe : 0u; a.exp_r = vpe ? 32u - a.exp_q * vpe : 0u; }
@@ -275,7 +279,8 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     // observations that are not whole words per environment are expanded from the tile's concatenated bit stream (expand_cat): obs words per
     // 32-env tile; a Permutation too wide for a bit stream (OW == 0) keeps the direct byte test
     e->cat_words = ((L.obs_size & 31) != 0 && !(L.kind == QG_ENV_PERMUTATION && L.OW == 0)) ? L.obs_size : 0;
-    e->smem_bytes = ((size_t)kLutWords + (size_t)(e->sm_warp_words + e->cat_words) * kWarpsPerCta) * 4;      // the largest layout a launch may ask for
+    const int wts_words = ((int64_t)(L.A | 1) * 32 * 4 <= 16 * 1024) ? (L.A | 1) * 32 : 0;
+    e->smem_bytes = ((size_t)kLutWords + (size_t)(e->sm_warp_words + std::max(e->cat_words, wts_words)) * kWarpsPerCta) * 4;   // the largest layout a launch may ask for
     if (e->smem_bytes > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
     e->magic_obs = magic40((uint32_t)L.obs_size); e->magic_A = magic40((uint32_t)L.A);
     auto magic32 = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
@@ -396,9 +401,10 @@ int qg_set_state(qg_engine* e, const int64_t* states_host, int64_t stride, int64
 }
 
 namespace {
-int launch_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, int which, const uint8_t* select_dev, cudaStream_t st) {
+int launch_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, int which, const uint8_t* select_dev, cudaStream_t st, const uint64_t* seed_dev = nullptr) {
     CUDA_OK(cudaSetDevice(e->device));
-    e->dc.seed = seed; e->dc.first_id = first_env_id;
+    if (!seed_dev) e->dc.seed = seed;
+    e->dc.first_id = first_env_id; e->dc.seed_dev = seed_dev;
     if (e->B == 0) return QG_OK;
     if (e->L.kind == QG_ENV_PAULI_NETWORK) {
         const int words = e->L.SW + e->L.XW + 3 * e->L.Rtot;
@@ -428,6 +434,13 @@ int qg_reset(qg_engine* e, uint64_t seed, int64_t first_env_id, qg_stream stream
 int qg_reset_select(qg_engine* e, uint64_t seed, int64_t first_env_id, const uint8_t* select_dev, qg_stream stream) {
     if (!e) { set_error("null engine"); return QG_ERR_INVALID; }
     return launch_reset(e, seed, first_env_id, select_dev ? RESET_SELECT : RESET_FINAL, select_dev, (cudaStream_t)stream);
+}
+
+int qg_reset_select_dev(qg_engine* e, const uint64_t* seed_dev, int64_t first_env_id, const uint8_t* select_dev, qg_stream stream) {
+    if (!e || !seed_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    const int rc = launch_reset(e, 0, first_env_id, select_dev ? RESET_SELECT : RESET_FINAL, select_dev, (cudaStream_t)stream, seed_dev);
+    e->dc.seed_dev = nullptr;
+    return rc;
 }
 
 int qg_snapshot(qg_engine* e, qg_stream stream) {
@@ -667,6 +680,17 @@ int qg_collect_step(qg_engine* e, uint64_t seed, const float* weights_dev, int32
     return launch_step(e, MODE_SEARCH, a, (cudaStream_t)stream);
 }
 
+int qg_collect_step_dev(qg_engine* e, const uint64_t* seed_dev, const float* weights_dev, int32_t deterministic, float* obs_dev, uint8_t* mask_dev,
+                        int32_t* chosen_dev, float* reward_dev, uint8_t* done_dev, uint8_t* success_dev, qg_stream stream) {
+    if (!e || !weights_dev || !seed_dev) { set_error("null argument"); return QG_ERR_INVALID; }
+    e->dc.seed_dev = seed_dev;
+    StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic; a.obs = obs_dev; a.mask = mask_dev; a.chosen = chosen_dev;
+    a.reward = reward_dev; a.done = done_dev; a.success = success_dev;
+    const int rc = launch_step(e, MODE_SEARCH, a, (cudaStream_t)stream);
+    e->dc.seed_dev = nullptr;
+    return rc;
+}
+
 int qg_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, const uint8_t* valid_dev, int32_t num_steps, int64_t batch,
            float gamma, float lambda, float* adv_dev, float* ret_dev, qg_stream stream) {
     if (!reward_dev || !value_dev || !done_dev || !adv_dev) { set_error("null argument"); return QG_ERR_INVALID; }
@@ -774,7 +798,7 @@ int qg_search_run(qg_engine* e, qg_policy* pol, int32_t deterministic, int32_t m
     CUDA_OK(cudaSetDevice(e->device));
     StepArgs a{}; a.weights = weights_dev; a.deterministic = deterministic;      // (no packed-observation output: the kernel keeps the bit stream on chip)
     a.nsteps = 1; a.ring = 1; a.pdl_mode = 0; a.num_sms = e->num_sms;
-    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.sm_cat = -1; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
+    a.sm_warp_words = e->sm_warp_words; a.sm_scr = e->sm_scr; a.sm_obs = e->sm_obs; a.sm_cat = -1; a.sm_wts = -1; a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4; a.symplectic = e->all_symplectic ? 1 : 0;
     a.magic_ow = magic40(((uint32_t)e->L.obs_size + 31u) / 32u);
     const size_t step_smem = (size_t)e->sm_warp_words * 4 + 16;

@@ -46,6 +46,7 @@ struct StepArgs {
     int64_t out_stride;          // elements between consecutive steps of reward / done / success
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
     int32_t sm_cat;                          // offset of the tile's concatenated observation bit stream (expand_cat), or -1: not used by this launch
+    int32_t sm_wts;                          // MODE_SEARCH: offset of the tile's staged action weights [env][A | 1], or -1: read them from global memory
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
     uint64_t magic_ow;                // ceil(2^40/ceil(obs_size/32))        (packed observation)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
@@ -315,6 +316,27 @@ __device__ void pn_build_obs(const DevCfg& c, const Wd& S, const PauliRegs& p, c
     const int n = c.n, D = 2 * n, RW = c.CW >> 5;
     const int m = min((int)(p.misc >> 24), c.max_rot);
     const uint8_t* perm = (c.nperms > 0) ? (c.qperms + (size_t)perm_idx * n) : nullptr;
+    if (!perm && c.obs_cols <= 32 && c.max_rot <= 8) {
+        // the usual shape (C4: 20 + 5 columns): one observation row fits a word.  The DAG-order gather of the rotation bits runs over
+        // eight shift amounts computed once per step (positions >= m read bit 31 of a < 2^16 value: zero) and a row is ONE append
+        // (2 500 -> ~900 instructions per env-step, ncu source counters in profiles/r2_*)
+        uint32_t sh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh[i] = (i < m) ? ((p.ord0 >> (4 * i)) & 15u) : 31u;
+        const uint32_t tmask = (1u << D) - 1u;                      // D <= 31 here
+        unsigned long long acc = 0; int fill = 0, ow = 0;
+        for (int r = 0; r < D; ++r) {
+            const uint32_t t = S[r * RW] & tmask, rb = rot_bits(c, S, r);
+            uint32_t rot = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rot |= ((rb >> sh[i]) & 1u) << i;
+            acc |= (unsigned long long)(t | (rot << D)) << fill; fill += c.obs_cols;
+            if (fill >= 32) { O[ow++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        if (fill > 0) O[ow++] = (uint32_t)acc;
+        for (; ow < c.OW; ++ow) O[ow] = 0;
+        return;
+    }
     unsigned long long acc = 0; int fill = 0, ow = 0;
     auto append = [&](uint32_t v, int len) {       // len in 1..32, v has no bits above len
         acc |= (unsigned long long)v << fill; fill += len;
@@ -701,6 +723,18 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         if (a.coins) next_coin = QG_LD_STREAM(a.coins + env);
     }
     uint32_t acc_done = 0, acc_succ = 0;             // lane l: the tile's is_final / success ballots of step (t & ~31) + l (a.done_bits)
+    // MODE_SEARCH: the tile's action weights [cnt][A] are contiguous in global memory: the warp copies them into shared memory with coalesced
+    // loads (row stride A | 1: odd, so the lanes' rows start in different banks) instead of every lane walking its own row with a 4*A-byte
+    // stride between lanes (a 65 536-env collector decision: 43 -> ~10 us for A = 72)
+    const float* staged_wts = nullptr;
+    if (MODE == MODE_SEARCH && !weights_tile && a.sm_wts >= 0) {
+        float* w = reinterpret_cast<float*>(wbase + a.sm_wts);
+        const uint32_t A = (uint32_t)c.A, rs = A | 1u, total = (uint32_t)cnt * A;
+        const float* src = a.weights + (size_t)e0 * A;
+        for (uint32_t i = lane; i < total; i += 32) { const uint32_t e = fastdiv40(i, a.magic_A); w[e * rs + (i - e * A)] = src[i]; }
+        __syncwarp();
+        staged_wts = w;
+    }
     for (int t = 0; t < a.nsteps; ++t) {
         bool success = (flags & FL_SUCCESS) != 0, enabled = live;
         const uint32_t coin_in = next_coin;
@@ -718,7 +752,8 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 // twisterl-style rollout decision: skip rollouts that are final (is_final, clifford.rs:353)
                 enabled = !(depth == 0 || success);
                 if (enabled) {
-                    const float* wt = weights_tile ? weights_tile + (size_t)lane * c.A : a.weights + (size_t)env * c.A;
+                    const float* wt = weights_tile ? weights_tile + (size_t)lane * c.A
+                                      : (staged_wts ? staged_wts + (size_t)lane * (c.A | 1) : a.weights + (size_t)env * c.A);
                     if (a.deterministic) {
                         float best = wt[0]; action = 0;
                         for (int k = 1; k < c.A; ++k) { const float v = wt[k]; if (v > best) { best = v; action = k; } }
@@ -726,7 +761,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                         float total = 0.0f;
 #pragma unroll 4
                         for (int k = 0; k < c.A; ++k) total = __fadd_rn(total, wt[k]);
-                        const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_SAMPLE);
+                        const uint32_t raw = philox_draw(seed_of(c), (uint64_t)(c.first_id + env), tick, STREAM_SAMPLE);
                         if (!(total > 0.0f)) action = (int)__umulhi(raw, (uint32_t)c.A);
                         else {
                             const float target = __fmul_rn((float)(raw >> 8) * (1.0f / 16777216.0f), total);
@@ -793,7 +828,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 if (KIND != QG_ENV_PAULI_NETWORK && c.add_inverts) {
                     bool coin;
                     if (a.coins) coin = (MODE == MODE_STEP) ? (coin_in != 0) : (a.coins[(size_t)t * a.in_stride + env] != 0);
-                    else coin = (philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
+                    else coin = (philox_draw(seed_of(c), (uint64_t)(c.first_id + env), tick, STREAM_COIN) >> 31) != 0;
                     if (coin) {
                         if (KIND == QG_ENV_PERMUTATION) { invert_perm(c, S, SCR); flags ^= FL_INVERTED; oh_full = true; }
                         else {
@@ -830,7 +865,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 // PauliNetwork picks its qubit permutation here (pauli.rs:653-665)
                 int perm_idx = c.nperms > 0 ? (int)(pr.misc & 0xFFFFu) : 0;
                 if (c.nperms > 0 && enabled && (a.obs || a.obs_bits || fused)) {
-                    const uint32_t raw = a.perm_raw ? a.perm_raw[(size_t)t * a.in_stride + env] : philox_draw(c.seed, (uint64_t)(c.first_id + env), tick, STREAM_PERM);
+                    const uint32_t raw = a.perm_raw ? a.perm_raw[(size_t)t * a.in_stride + env] : philox_draw(seed_of(c), (uint64_t)(c.first_id + env), tick, STREAM_PERM);
                     perm_idx = (int)__umulhi(raw, (uint32_t)c.nperms);
                     pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
                     dirty = true;
@@ -1022,8 +1057,9 @@ __global__ void __launch_bounds__(EPC) k_reset(const __grid_constant__ DevCfg c,
     const Wd S{smem + tid};
     if (KIND == QG_ENV_PERMUTATION) { for (int w = 0; w < c.SW; ++w) S[w] = 0; for (int q = 0; q < c.n; ++q) set8(S, q, (uint32_t)q); }
     else for (int w = 0; w < c.SW; ++w) S[w] = c.ident[w];
+    const uint64_t seed = seed_of(c);
     for (int k = 0; k < c.difficulty; ++k) {
-        const uint32_t raw = philox_draw(c.seed, (uint64_t)(c.first_id + env), (uint32_t)k, STREAM_RESET);
+        const uint32_t raw = philox_draw(seed, (uint64_t)(c.first_id + env), (uint32_t)k, STREAM_RESET);
         const int act = (int)__umulhi(raw, (uint32_t)c.A);      // Uniform::new(0, num_actions)
         const uint32_t g = __ldg(c.gates + act);
         apply_gate_state<KIND>(c, S, (int)(g & 0xFFu), (int)((g >> 8) & 0xFFu), (int)((g >> 16) & 0xFFu));
@@ -1060,7 +1096,8 @@ __global__ void __launch_bounds__(EPC) k_reset_pauli(const __grid_constant__ Dev
     const int ND = (int)tab[0], NCX = (int)tab[2];
     const uint32_t* dists = tab + 3; const uint32_t* poff = dists + ND; const uint32_t* pairs = poff + ND + 1; const uint32_t* cxp = pairs + tab[1];
     uint32_t ctr = 0;
-    auto draw = [&]() { return philox_draw(c.seed, (uint64_t)(c.first_id + env), ctr++, STREAM_RESET); };
+    const uint64_t seed = seed_of(c);
+    auto draw = [&]() { return philox_draw(seed, (uint64_t)(c.first_id + env), ctr++, STREAM_RESET); };
     auto below = [&](uint32_t k) { return __umulhi(draw(), k); };
     auto unit = [&]() { return (float)(draw() >> 8) * (1.0f / 16777216.0f); };
     auto count_le = [&](uint32_t lim) { int k = 0; while (k < ND && dists[k] <= lim) ++k; return k; };

@@ -94,28 +94,35 @@ struct LayerArgs {
     const float* bias;       // [n_tiles * NT]
     __half* Y;               // next layer's X images [m_tiles][out_Kb][2][8][128][8], or null (last layer)
     float* logits; float* probs; float* values;      // last layer outputs (each may be null)
-    int a_terms, Kb, NT, n_tiles, m_tiles, out_Kb, relu, num_actions, has_value;
+    int a_terms, Kb, NT, n_tiles, m_tiles, out_Kb, relu, num_actions, has_value, stages;
     long long batch;
 };
 
-struct SmemPlan { uint32_t a_off[kStages][2], b_off[kStages][2], bar_off, total; };
-__host__ __device__ inline SmemPlan plan_smem(int a_terms, int NT) {
+struct SmemPlan { uint32_t a_off[kStages][2], b_off[kStages][2], bar_off, stage_off, total; };
+// stages: pipeline depth of this layer (<= kStages); staging_floats: row-major [128][num_actions] output staging of the last layer (0 elsewhere)
+__host__ __device__ inline SmemPlan plan_smem(int a_terms, int NT, int stages, int staging_floats) {
     SmemPlan p{}; uint32_t o = 0;
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
         for (int t = 0; t < 2; ++t) { p.a_off[s][t] = o; if (t < a_terms) o += kImgA * 2; }
         for (int t = 0; t < 2; ++t) { p.b_off[s][t] = o; o += (uint32_t)NT * kKB * 2; }
     }
     p.bar_off = o; o += 128;
+    p.stage_off = o; o += (uint32_t)staging_floats * 4;
     p.total = o;
     return p;
 }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void epilogue_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }      // the 4 epilogue warps
 
 __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant__ LayerArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const SmemPlan sp = plan_smem(a.a_terms, a.NT);
+    const SmemPlan sp = plan_smem(a.a_terms, a.NT, a.stages, a.Y ? 0 : kM * a.num_actions);
+    const int kNumStages = a.stages;
     uint64_t* const full = reinterpret_cast<uint64_t*>(smem + sp.bar_off);      // [kStages]
     uint64_t* const empty = full + kStages;                                     // [kStages]
     uint64_t* const acc_full = empty + kStages;                                 // [2]
+    float* const staging = reinterpret_cast<float*>(smem + sp.stage_off);
     uint64_t* const acc_empty = acc_full + 2;                                   // [2]
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     const uint32_t acc_cols = 128;                                              // columns per accumulator buffer (NT <= 128)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kNumStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -135,6 +142,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above overlapped the previous kernel of the stream; its results are needed from here on
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ===== loader =====
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                         bulk_g2s(smem + sp.a_off[stage][term], a.X + (((size_t)mt * a.Kb + kb) * a.a_terms + term) * kImgA, kImgA * 2, full + stage);
                     for (int term = 0; term < 2; ++term)
                         bulk_g2s(smem + sp.b_off[stage][term], a.W + (((size_t)term * a.n_tiles + nt) * a.Kb + kb) * ((size_t)a.NT * kKB), (uint32_t)a.NT * kKB * 2, full + stage);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == (uint32_t)kNumStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                         if (a.a_terms == 2) umma_f16(d, smem_desc(sa1 + 2u * k * lbo_a, lbo_a, sbo), b_hi, idesc, 1u);
                     }
                     umma_commit(empty + stage);                     // the stage is free once these MMAs have read it
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == (uint32_t)kNumStages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(acc_full + as);                         // accumulator complete -> epilogue
                 if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -218,40 +228,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                     p_lo[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); p_lo[kM] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 }
             } else {
-                // last layer: columns 0 .. A-1 are the action logits, column A the value head; softmax over the logits (three passes over the
-                // accumulator: max, sum, write — tensor-memory reads are cheap, 80 live registers are not)
+                // last layer: columns 0 .. A-1 are the action logits, column A the value head.  The row's logits are read from tensor memory once
+                // into registers (fully unrolled: NT <= 128), soft-maxed there, and leave through a row-major staging tile in shared memory so
+                // that the tile's [128][A] block of the output — contiguous in the [B][A] tensor — is written with coalesced stores
                 const int A = a.num_actions;
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < a.NT; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + (uint32_t)c0, v);
+                float x[kMaxNT];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = c0 + i;
-                        const float x = __uint_as_float(v[i]) + __ldg(a.bias + n);
-                        if (n < A) { mx = fmaxf(mx, x); if (a.logits && grow < a.batch) a.logits[(size_t)grow * A + n] = x; }
-                        else if (n == A && a.has_value && a.values && grow < a.batch) a.values[grow] = x;
+                for (int c = 0; c < kMaxNT / 16; ++c) {
+                    if (c * 16 < a.NT) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + (uint32_t)(c * 16), v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) + __ldg(a.bias + c * 16 + i);
                     }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + as);         // the accumulator is in registers: the MMA warp may reuse the buffer now
+                if (a.has_value && a.values && grow < a.batch) {
+                    float val = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < kMaxNT; ++n) if (n == A) val = x[n];
+                    a.values[grow] = val;
+                }
+                const long long rows_left = a.batch - (long long)mt * kM;
+                const int nrows = rows_left < kM ? (int)rows_left : kM;
+                float* const srow = staging + (size_t)row * A;
+                auto flush = [&](float* out) {                       // staging [nrows][A] -> out rows mt*128 .., coalesced
+                    epilogue_sync();
+                    float* dst = out + (size_t)mt * kM * A;
+                    const int tid = row, total = nrows * A;
+                    for (int i = tid; i < total; i += 128) dst[i] = staging[i];
+                    epilogue_sync();
+                };
+                if (a.logits) {
+#pragma unroll
+                    for (int n = 0; n < kMaxNT; ++n) if (n < A) srow[n] = x[n];
+                    flush(a.logits);
                 }
                 if (a.probs) {
-                    float sum = 0.0f;
-                    for (int c0 = 0; c0 < a.NT; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(taddr + (uint32_t)c0, v);
+                    float mx = -INFINITY, sum = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { const int n = c0 + i; if (n < A) sum += expf(__uint_as_float(v[i]) + __ldg(a.bias + n) - mx); }
-                    }
+                    for (int n = 0; n < kMaxNT; ++n) if (n < A) mx = fmaxf(mx, x[n]);
+#pragma unroll
+                    for (int n = 0; n < kMaxNT; ++n) if (n < A) { x[n] = expf(x[n] - mx); sum += x[n]; }
                     const float inv = 1.0f / sum;
-                    for (int c0 = 0; c0 < a.NT; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int n = c0 + i;
-                            if (n < A && grow < a.batch) a.probs[(size_t)grow * A + n] = expf(__uint_as_float(v[i]) + __ldg(a.bias + n) - mx) * inv;
-                        }
-                    }
+                    for (int n = 0; n < kMaxNT; ++n) if (n < A) srow[n] = x[n] * inv;
+                    flush(a.probs);
                 }
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+                continue;
             }
             tc_fence_before();
             __syncwarp();
@@ -262,6 +289,312 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
+}
+
+// ---- the three layers of a BasicPolicy (embeddings -> one common layer -> action / value head) in ONE kernel ------------------------------
+// The per-layer kernels above push every hidden activation through global memory twice (h1: 2 x 134 MB at 65 536 rows).  Here a CTA keeps its
+// 128 rows on chip from the observation tile to the logits:
+//   layer 1 is computed in 128-column chunks (accumulators D1[0] / D1[1] in tensor memory, double buffered); the epilogue turns a finished
+//   chunk into f16 hi/lo halves in a 64 KB shared-memory buffer laid out as TWO K blocks of layer 2's A operand; layer 2 accumulates those two
+//   K blocks into D2 (256 columns) while layer 1's next chunk is already being multiplied; when the last chunk is in, D2 is turned — 128 columns
+//   at a time, through the same buffer — into layer 3's A operand, and the head's accumulator takes the place of a D1 buffer.
+// Tensor memory: D1[0] cols 0..127, D1[1] cols 128..255, D2 cols 256..511.  Shared memory: 2 ring stages of 64 KB (weight tiles, and layer
+// 1's observation tiles) + the 64 KB activation buffer (which doubles as the output staging tile of the head).
+//   warp 0 loader, warp 1 MMA issuer, warps 2..9 epilogue (two warps per tensor-memory lane quarter, each converting half of the columns).
+struct FusedArgs {
+    const __half* X0;        // observation tile images [m_tiles][Kb0][8][128][8]
+    const __half* W1;        // [2 terms][NC chunks][Kb0][8][128][8]
+    const __half* W2;        // [2 terms][Kb2 = E_pad / 64][8][C_pad][8]
+    const __half* W3;        // [2 terms][Kb3 = C_pad / 64][8][H][8]
+    const float* b1; const float* b2; const float* b3;
+    float* logits; float* probs; float* values;
+    int Kb0, NC, C_pad, Kb3, H, m_tiles, num_actions, has_value;
+    long long batch;
+};
+constexpr int kFusedThreads = 320;
+constexpr uint32_t kRingStage = 64 * 1024, kActBytes = 64 * 1024;
+constexpr uint32_t kFusedSmem = 2 * kRingStage + kActBytes + 256;
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void epilogue8_sync() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void epilogue4_sync() { asm volatile("bar.sync 3, 128;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_constant__ FusedArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* const ring = smem;                         // [2][64 KB]
+    uint8_t* const act = smem + 2 * kRingStage;         // hi: K blocks 0, 1 (16 KB each) | lo: K blocks 0, 1
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(act + kActBytes);
+    uint64_t* const full = bars;            // [2]
+    uint64_t* const empty = bars + 2;       // [2]
+    uint64_t* const d1_full = bars + 4;     // [2]
+    uint64_t* const d1_empty = bars + 6;    // [2]
+    uint64_t* const d2_full = bars + 8;
+    uint64_t* const d2_empty = bars + 9;
+    uint64_t* const act_full = bars + 10;
+    uint64_t* const act_empty = bars + 11;
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int halves = (a.C_pad + 127) / 128;           // D2 leaves in 128-column pieces
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(d1_full + s, 1); mbar_init(d1_empty + s, 8); }
+        mbar_init(d2_full, 1); mbar_init(d2_empty, 8); mbar_init(act_full, 8); mbar_init(act_empty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const uint32_t img128 = 128 * kKB;                  // halves per 128-row K-block image
+    if (warp == 0) {
+        // ===== loader: the stages in the order the MMA warp consumes them =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            auto next = [&]() { if (++stage == 2) { stage = 0; phase ^= 1u; } };
+            auto stage_l1 = [&](int mt, int c, int kb) {
+                mbar_wait(empty + stage, phase ^ 1u);
+                uint8_t* sp = ring + stage * kRingStage;
+                mbar_expect_tx(full + stage, 3u * img128 * 2);
+                bulk_g2s(sp, a.X0 + ((size_t)mt * a.Kb0 + kb) * img128, img128 * 2, full + stage);
+                bulk_g2s(sp + 16384, a.W1 + (((size_t)0 * a.NC + c) * a.Kb0 + kb) * img128, img128 * 2, full + stage);
+                bulk_g2s(sp + 32768, a.W1 + (((size_t)1 * a.NC + c) * a.Kb0 + kb) * img128, img128 * 2, full + stage);
+                next();
+            };
+            auto stage_w = [&](const __half* W, int kbs, int rows, int kb) {       // hi at +0, lo at +32 KB
+                mbar_wait(empty + stage, phase ^ 1u);
+                uint8_t* sp = ring + stage * kRingStage;
+                const uint32_t bytes = (uint32_t)rows * kKB * 2;
+                mbar_expect_tx(full + stage, 2u * bytes);
+                bulk_g2s(sp, W + ((size_t)0 * kbs + kb) * ((size_t)rows * kKB), bytes, full + stage);
+                bulk_g2s(sp + 32768, W + ((size_t)1 * kbs + kb) * ((size_t)rows * kKB), bytes, full + stage);
+                next();
+            };
+            for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+                for (int c = 0; c <= a.NC; ++c) {
+                    if (c < a.NC) for (int kb = 0; kb < a.Kb0; ++kb) stage_l1(mt, c, kb);
+                    if (c > 0) for (int j = 0; j < 2; ++j) stage_w(a.W2, 2 * a.NC, a.C_pad, 2 * (c - 1) + j);
+                }
+                for (int kb = 0; kb < a.Kb3; ++kb) stage_w(a.W3, a.Kb3, a.H, kb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t n_d1e[2] = {0, 0}, n_actf = 0, n_d2e = 0;          // waits done so far on d1_empty[b], act_full, d2_empty
+            const uint32_t lbo128 = 128 * 16, sbo = 128;
+            const uint32_t id1 = instr_desc(128), id2 = instr_desc(a.C_pad), id3 = instr_desc(a.H);
+            const uint32_t lbo2 = (uint32_t)a.C_pad * 16, lbo3 = (uint32_t)a.H * 16;
+            const uint32_t act_u = smem_u32(act);
+            auto next = [&]() { if (++stage == 2) { stage = 0; phase ^= 1u; } };
+            for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+                for (int c = 0; c <= a.NC; ++c) {
+                    if (c < a.NC) {
+                        // layer 1, chunk c -> D1[c & 1]
+                        const int b = c & 1;
+                        mbar_wait(d1_empty + b, (n_d1e[b] & 1u) ^ 1u); ++n_d1e[b];
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)b * 128;
+                        for (int kb = 0; kb < a.Kb0; ++kb) {
+                            mbar_wait(full + stage, phase);
+                            tc_fence_after();
+                            const uint32_t sp = smem_u32(ring + stage * kRingStage);
+#pragma unroll
+                            for (int k = 0; k < kKB / 16; ++k) {
+                                const uint64_t ad = smem_desc(sp + 2u * k * lbo128, lbo128, sbo);
+                                umma_f16(d, ad, smem_desc(sp + 16384 + 2u * k * lbo128, lbo128, sbo), id1, (kb | k) ? 1u : 0u);
+                                umma_f16(d, ad, smem_desc(sp + 32768 + 2u * k * lbo128, lbo128, sbo), id1, 1u);
+                            }
+                            umma_commit(empty + stage);
+                            next();
+                        }
+                        umma_commit(d1_full + b);
+                    }
+                    if (c > 0) {
+                        // layer 2 over the two K blocks of chunk c - 1 (the epilogue's halves in the activation buffer) -> D2
+                        if (c == 1) { mbar_wait(d2_empty, (n_d2e & 1u) ^ 1u); ++n_d2e; }
+                        mbar_wait(act_full, n_actf & 1u); ++n_actf;
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + 256;
+                        for (int j = 0; j < 2; ++j) {
+                            mbar_wait(full + stage, phase);
+                            tc_fence_after();
+                            const uint32_t sp = smem_u32(ring + stage * kRingStage);
+                            const uint32_t a_hi = act_u + (uint32_t)j * 16384, a_lo = act_u + 32768 + (uint32_t)j * 16384;
+#pragma unroll
+                            for (int k = 0; k < kKB / 16; ++k) {
+                                const uint64_t ah = smem_desc(a_hi + 2u * k * lbo128, lbo128, sbo), bh = smem_desc(sp + 2u * k * lbo2, lbo2, sbo);
+                                umma_f16(d, ah, bh, id2, (c > 1 || j || k) ? 1u : 0u);
+                                umma_f16(d, ah, smem_desc(sp + 32768 + 2u * k * lbo2, lbo2, sbo), id2, 1u);
+                                umma_f16(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id2, 1u);
+                            }
+                            umma_commit(empty + stage);
+                            next();
+                        }
+                        umma_commit(act_empty);                      // the buffer may be rewritten once these products have read it
+                    }
+                }
+                umma_commit(d2_full);
+                // the head: layer 3 over the halves of D2 as they come back through the activation buffer -> the D1 buffer whose turn it is
+                {
+                    const int b = a.NC & 1;
+                    mbar_wait(d1_empty + b, (n_d1e[b] & 1u) ^ 1u); ++n_d1e[b];
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)b * 128;
+                    for (int h = 0; h < halves; ++h) {
+                        mbar_wait(act_full, n_actf & 1u); ++n_actf;
+                        tc_fence_after();
+                        const int kbs = min(2, a.Kb3 - 2 * h);
+                        for (int j = 0; j < kbs; ++j) {
+                            mbar_wait(full + stage, phase);
+                            tc_fence_after();
+                            const uint32_t sp = smem_u32(ring + stage * kRingStage);
+                            const uint32_t a_hi = act_u + (uint32_t)j * 16384, a_lo = act_u + 32768 + (uint32_t)j * 16384;
+#pragma unroll
+                            for (int k = 0; k < kKB / 16; ++k) {
+                                const uint64_t ah = smem_desc(a_hi + 2u * k * lbo128, lbo128, sbo), bh = smem_desc(sp + 2u * k * lbo3, lbo3, sbo);
+                                umma_f16(d, ah, bh, id3, (h || j || k) ? 1u : 0u);
+                                umma_f16(d, ah, smem_desc(sp + 32768 + 2u * k * lbo3, lbo3, sbo), id3, 1u);
+                                umma_f16(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id3, 1u);
+                            }
+                            umma_commit(empty + stage);
+                            next();
+                        }
+                        umma_commit(act_empty);
+                    }
+                    umma_commit(d1_full + b);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..9.  Quarter q = warp % 4 owns tensor-memory lanes 32q..32q+31 (rows); of the two warps of a quarter the one
+        // with hsel = 0 converts columns 0..63 of a 128-column piece (K block 0 of the buffer), the other columns 64..127 (K block 1) =====
+        const int q = warp & 3, hsel = (warp - 2) >> 2, row = q * 32 + lane;
+        uint32_t n_d1f[2] = {0, 0}, n_acte = 0, n_d2f = 0;
+        const uint32_t lane_base = ((uint32_t)(q * 32) << 16);
+        // 64 accumulator columns starting at tensor-memory column `tcol` -> + bias, ReLU, hi / lo halves -> K block `hsel` of the buffer.
+        // (Tried: converting into 64 registers before waiting for act_empty, so that only the shared-memory stores sit between act_empty
+        // and act_full — 158 instead of 133 us per 65 536-row forward: the longer live ranges spill, profiles/r2_v12_tc_probe.json.)
+        auto convert64 = [&](uint32_t tcol, const float* bias) {
+            uint8_t* const kb_hi = act + (uint32_t)hsel * 16384;
+            uint8_t* const kb_lo = kb_hi + 32768;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_base + tcol + (uint32_t)c0, v);
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float x0 = fmaxf(__uint_as_float(v[i]) + __ldg(bias + c0 + i), 0.0f), x1 = fmaxf(__uint_as_float(v[i + 1]) + __ldg(bias + c0 + i + 1), 0.0f);
+                    const __half2 h2 = __floats2half2_rn(x0, x1);
+                    const float2 hf = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                    hi[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                const int ch = c0 >> 3;                               // 8-column chunk within the K block
+                uint4* p_hi = reinterpret_cast<uint4*>(kb_hi + ((size_t)ch * kM + row) * 16);
+                uint4* p_lo = reinterpret_cast<uint4*>(kb_lo + ((size_t)ch * kM + row) * 16);
+                p_hi[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); p_hi[kM] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                p_lo[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); p_lo[kM] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+        };
+        auto publish = [&]() {                                        // this warp's part of the buffer is written: hand it to the tensor core
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(act_full);
+        };
+        for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+            for (int c = 0; c < a.NC; ++c) {
+                const int b = c & 1;
+                mbar_wait(d1_full + b, n_d1f[b] & 1u); ++n_d1f[b];
+                mbar_wait(act_empty, (n_acte & 1u) ^ 1u); ++n_acte;   // the previous chunk's layer-2 products have read the buffer
+                tc_fence_after();
+                convert64((uint32_t)b * 128 + (uint32_t)hsel * 64, a.b1 + c * 128 + hsel * 64);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d1_empty + b);
+                publish();
+            }
+            mbar_wait(d2_full, n_d2f & 1u); ++n_d2f;
+            for (int h = 0; h < halves; ++h) {
+                mbar_wait(act_empty, (n_acte & 1u) ^ 1u); ++n_acte;
+                tc_fence_after();
+                if (h * 128 + hsel * 64 < a.C_pad) convert64(256u + (uint32_t)h * 128 + (uint32_t)hsel * 64, a.b2 + h * 128 + hsel * 64);
+                if (h == halves - 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(d2_empty); }
+                publish();
+            }
+            // the head's accumulator
+            {
+                const int b = a.NC & 1;
+                mbar_wait(d1_full + b, n_d1f[b] & 1u); ++n_d1f[b];
+                tc_fence_after();
+                const int A = a.num_actions;
+                const long long grow = (long long)mt * kM + row;
+                float x[kMaxNT];
+                if (hsel == 0) {
+#pragma unroll
+                    for (int c = 0; c < kMaxNT / 16; ++c) {
+                        if (c * 16 < a.H) {
+                            uint32_t v[16];
+                            tmem_ld16(tmem_base + lane_base + (uint32_t)b * 128 + (uint32_t)(c * 16), v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) + __ldg(a.b3 + c * 16 + i);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d1_empty + b);             // (all 8 warps arrive: the barrier's count is the same for every use)
+                if (hsel == 0) {
+                    // the activation buffer is idle until the next tile's first chunk (these same warps write it): it is the staging tile
+                    if (a.has_value && a.values && grow < a.batch) {
+                        float val = 0.0f;
+#pragma unroll
+                        for (int n = 0; n < kMaxNT; ++n) if (n == A) val = x[n];
+                        a.values[grow] = val;
+                    }
+                    float* const staging = reinterpret_cast<float*>(act);
+                    const long long rows_left = a.batch - (long long)mt * kM;
+                    const int nrows = rows_left < kM ? (int)rows_left : kM;
+                    float* const srow = staging + (size_t)row * A;
+                    auto flush = [&](float* out) {
+                        epilogue4_sync();
+                        float* dst = out + (size_t)mt * kM * A;
+                        const int total = nrows * A;
+                        for (int i = row; i < total; i += 128) dst[i] = staging[i];
+                        epilogue4_sync();
+                    };
+                    if (a.logits) {
+#pragma unroll
+                        for (int n = 0; n < kMaxNT; ++n) if (n < A) srow[n] = x[n];
+                        flush(a.logits);
+                    }
+                    if (a.probs) {
+                        float mx = -INFINITY, sum = 0.0f;
+#pragma unroll
+                        for (int n = 0; n < kMaxNT; ++n) if (n < A) mx = fmaxf(mx, x[n]);
+#pragma unroll
+                        for (int n = 0; n < kMaxNT; ++n) if (n < A) { x[n] = expf(x[n] - mx); sum += x[n]; }
+                        const float inv = 1.0f / sum;
+#pragma unroll
+                        for (int n = 0; n < kMaxNT; ++n) if (n < A) srow[n] = x[n] * inv;
+                        flush(a.probs);
+                    }
+                }
+                epilogue8_sync();      // the other four warps must not start the next tile's first chunk in the buffer while it is the staging tile
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 // packed observation bits -> the first layer's X tile images (one half per entry: 0 / 1 are exact): thread = (row, 8-column chunk)
@@ -295,10 +628,13 @@ __global__ void k_tc_expand_bits(const uint32_t* __restrict__ bits, int obs_word
 using namespace qg;
 
 struct TcLayer {
-    int K = 0, N = 0, Kb = 0, NT = 0, n_tiles = 0, Npad = 0, a_terms = 2, relu = 1;
+    int K = 0, N = 0, Kb = 0, NT = 0, n_tiles = 0, Npad = 0, a_terms = 2, relu = 1, stages = qg::tc::kStages, staging = 0;
     __half* W = nullptr; float* bias = nullptr;
 };
 struct qg_policy_tc {
+    bool fused = false;            // three layers that fit k_tc_fused3
+    bool force_layers = false;     // qg_policy_tc_set_mode(p, 1): one kernel per layer even where the fused kernel applies (A/B runs, tests)
+    __half* W2_fused = nullptr;    // layer 2's weight images with all C_pad rows in one tile
     int device = 0, obs_size = 0, obs_words = 0, num_actions = 0, has_value = 0, num_sms = 148;
     long long max_batch = 0; int m_tiles = 0;
     std::vector<TcLayer> layers;
@@ -323,6 +659,7 @@ void qg_policy_tc_destroy(qg_policy_tc* p) {
     if (!p) return;
     for (auto& l : p->layers) { if (l.W) cudaFree(l.W); if (l.bias) cudaFree(l.bias); }
     for (auto* a : p->acts) if (a) cudaFree(a);
+    if (p->W2_fused) cudaFree(p->W2_fused);
     delete p;
 }
 
@@ -398,14 +735,46 @@ int qg_policy_tc_create(int32_t device, int32_t obs_size, int32_t num_layers, co
     }
     // (layer l writes round_up(N_l, 64) columns = all K blocks of layer l+1: padded columns come out as relu(0 + 0) = 0)
     size_t max_smem = 0;
-    for (auto& L : p->layers) max_smem = std::max<size_t>(max_smem, tc::plan_smem(L.a_terms, L.NT).total);
+    for (size_t l = 0; l < p->layers.size(); ++l) {
+        TcLayer& L = p->layers[l];
+        L.staging = (l + 1 == p->layers.size()) ? tc::kM * p->num_actions : 0;
+        L.stages = tc::kStages;
+        while (L.stages > 1 && tc::plan_smem(L.a_terms, L.NT, L.stages, L.staging).total > 220 * 1024) --L.stages;
+        max_smem = std::max<size_t>(max_smem, tc::plan_smem(L.a_terms, L.NT, L.stages, L.staging).total);
+    }
     cudaError_t ce = cudaFuncSetAttribute(tc::k_tc_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
     if (ce != cudaSuccess) { set_error(std::string("qg_policy_tc_create: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
+    // the one-kernel path: embeddings (a multiple of 128 wide after padding) -> one common layer (<= 256) -> head
+    if (num_layers == 3 && p->layers[0].Npad % 128 == 0 && p->layers[0].NT == 128 && p->layers[1].Npad <= 256) {
+        const TcLayer& L1 = p->layers[1];
+        const int C_pad = L1.Npad, Kb2 = L1.Kb, K = L1.K;
+        const size_t img = (size_t)C_pad * tc::kKB, count = (size_t)2 * Kb2 * img;
+        std::vector<__half> wimg(count, __float2half(0.0f));
+        const float* W = weights_host[1];
+        for (int n = 0; n < out_features[1]; ++n)
+            for (int k = 0; k < K; ++k) {
+                const float w = W[(size_t)n * K + k];
+                const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+                const int kb = k / tc::kKB, kl = k % tc::kKB;
+                const size_t at = (size_t)kb * img + ((size_t)(kl >> 3) * C_pad + n) * 8 + (kl & 7);
+                wimg[at] = hi; wimg[(size_t)Kb2 * img + at] = lo;
+            }
+        ce = cudaMalloc(&p->W2_fused, count * sizeof(__half));
+        if (ce == cudaSuccess) ce = cudaMemcpy(p->W2_fused, wimg.data(), count * sizeof(__half), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tc::k_tc_fused3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kFusedSmem);
+        if (ce != cudaSuccess) { set_error(std::string("qg_policy_tc_create: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
+        p->fused = true;
+    }
     *out = p;
     return QG_OK;
 }
 
 int32_t qg_policy_tc_num_actions(const qg_policy_tc* p) { return p ? p->num_actions : 0; }
+int32_t qg_policy_tc_set_mode(qg_policy_tc* p, int32_t per_layer) {
+    if (!p) return 0;
+    p->force_layers = per_layer != 0;
+    return (p->fused && !p->force_layers) ? 1 : 0;
+}
 
 int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int64_t batch, float* probs_dev, float* logits_dev, float* values_dev,
                               qg_stream stream) {
@@ -422,6 +791,22 @@ int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int
         tc::k_tc_expand_bits<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs_bits_dev, p->obs_words, p->obs_size, batch, L0.Kb, p->acts[0], total);
         TC_CUDA_OK(cudaGetLastError());
     }
+    if (p->fused && !p->force_layers) {
+        const TcLayer &L0 = p->layers[0], &L1 = p->layers[1], &L2 = p->layers[2];
+        tc::FusedArgs a{};
+        a.X0 = p->acts[0]; a.W1 = L0.W; a.W2 = p->W2_fused; a.W3 = L2.W; a.b1 = L0.bias; a.b2 = L1.bias; a.b3 = L2.bias;
+        a.logits = logits_dev; a.probs = probs_dev; a.values = values_dev;
+        a.Kb0 = L0.Kb; a.NC = L0.Npad / 128; a.C_pad = L1.Npad; a.Kb3 = L2.Kb; a.H = L2.Npad; a.m_tiles = m_tiles;
+        a.num_actions = p->num_actions; a.has_value = p->has_value; a.batch = batch;
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)std::min(m_tiles, p->num_sms)); lc.blockDim = dim3(tc::kFusedThreads);
+        lc.dynamicSmemBytes = tc::kFusedSmem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        TC_CUDA_OK(cudaLaunchKernelEx(&lc, tc::k_tc_fused3, a));
+        return QG_OK;
+    }
     for (size_t l = 0; l < p->layers.size(); ++l) {
         const TcLayer& L = p->layers[l];
         const bool last = l + 1 == p->layers.size();
@@ -430,10 +815,17 @@ int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int
         a.logits = last ? logits_dev : nullptr; a.probs = last ? probs_dev : nullptr; a.values = last ? values_dev : nullptr;
         a.a_terms = L.a_terms; a.Kb = L.Kb; a.NT = L.NT; a.n_tiles = L.n_tiles; a.m_tiles = m_tiles;
         a.out_Kb = last ? 0 : p->layers[l + 1].Kb; a.relu = L.relu; a.num_actions = p->num_actions; a.has_value = p->has_value; a.batch = batch;
+        a.stages = L.stages;
         const int tiles = m_tiles * L.n_tiles;
-        const size_t smem = tc::plan_smem(L.a_terms, L.NT).total;
-        tc::k_tc_layer<<<(unsigned)std::min(tiles, p->num_sms), tc::kThreads, smem, st>>>(a);
-        TC_CUDA_OK(cudaGetLastError());
+        // programmatic dependent launch: the kernel's prologue (barrier init, tensor-memory allocation) overlaps the previous kernel's tail;
+        // it waits (griddepcontrol.wait) before it touches global memory
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)std::min(tiles, p->num_sms)); lc.blockDim = dim3(tc::kThreads);
+        lc.dynamicSmemBytes = tc::plan_smem(L.a_terms, L.NT, L.stages, L.staging).total; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        TC_CUDA_OK(cudaLaunchKernelEx(&lc, tc::k_tc_layer, a));
     }
     return QG_OK;
 }

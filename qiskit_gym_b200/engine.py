@@ -126,6 +126,19 @@ class BatchedEnv:
     def reset(self, seed: int = 0, first_env_id: int = 0):
         check(lib().qg_reset(self._h, C.c_uint64(seed & (2**64 - 1)), first_env_id, self._stream()))
 
+    def reset_select_dev(self, seed_dev: torch.Tensor, first_env_id: int = 0, select: torch.Tensor | None = None):
+        """reset_select with the seed read from device memory at run time (int64 tensor, 1 element): CUDA-graph replays."""
+        assert seed_dev.is_cuda and seed_dev.element_size() == 8
+        check(lib().qg_reset_select_dev(self._h, _dptr(seed_dev), first_env_id, _dptr(select), self._stream()))
+
+    def collect_step_dev(self, weights: torch.Tensor, seed_dev: torch.Tensor, deterministic: bool = False, chosen: torch.Tensor | None = None,
+                         reward: torch.Tensor | None = None, done: torch.Tensor | None = None, success: torch.Tensor | None = None):
+        """collect_step with the seed read from device memory at run time; no observation / mask output."""
+        assert weights.dtype == torch.float32 and weights.is_cuda and weights.is_contiguous() and seed_dev.is_cuda and seed_dev.element_size() == 8
+        check(lib().qg_collect_step_dev(self._h, _dptr(seed_dev), _dptr(weights), 1 if deterministic else 0, None, None, _dptr(chosen),
+                                        _dptr(self.reward if reward is None else reward), _dptr(self.done if done is None else done),
+                                        _dptr(self.success if success is None else success), self._stream()))
+
     def reset_select(self, seed: int = 0, first_env_id: int = 0, select: torch.Tensor | None = None):
         """Env::reset for the envs flagged in `select` (bool/uint8 [B]) or, with select=None, for every env that is final."""
         assert select is None or (select.is_cuda and select.numel() == self.batch and select.element_size() == 1)

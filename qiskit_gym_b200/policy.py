@@ -146,6 +146,11 @@ class TensorCorePolicy:
                 pass
             self._h = None
 
+    def set_per_layer(self, per_layer: bool) -> bool:
+        """Forces the one-kernel-per-layer path (True) or lets the fused three-layer kernel run where it applies (False); returns whether
+        the fused kernel will run."""
+        return bool(lib().qg_policy_tc_set_mode(self._h, 1 if per_layer else 0))
+
     def forward_bits(self, obs_bits: torch.Tensor, probs: torch.Tensor | None = None, logits: torch.Tensor | None = None,
                      values: torch.Tensor | None = None):
         assert obs_bits.is_cuda and obs_bits.element_size() == 4 and obs_bits.is_contiguous() and obs_bits.shape[-1] == self.obs_words

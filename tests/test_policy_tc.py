@@ -41,6 +41,16 @@ def test_tensor_core_policy_matches_float64(obs_shape, A, emb, common, density):
         assert torch.allclose(values.double(), ref_v.reshape(-1), rtol=1e-4, atol=2e-5), (B, float((values.double() - ref_v.reshape(-1)).abs().max()))
         assert torch.allclose(probs.double(), ref_probs, rtol=1e-4, atol=1e-6)
         assert torch.allclose(probs.sum(dim=1), torch.ones(B, device=dev), atol=1e-5)
+    # the fused three-layer kernel (where the shape allows it) and the one-kernel-per-layer path do the same products in the same order
+    fused_runs = tcp.set_per_layer(False)
+    assert fused_runs == (len(common) == 1 and ((emb + 63) // 64 * 64) % 128 == 0 and (common[0] + 63) // 64 * 64 <= 256)
+    if fused_runs:
+        tcp.set_per_layer(True)
+        l2 = torch.empty_like(logits); p2 = torch.empty_like(probs); v2 = torch.empty_like(values)
+        tcp.forward_bits(bits, probs=p2, logits=l2, values=v2)
+        assert torch.allclose(l2, logits, rtol=0, atol=1e-6) and torch.allclose(p2, probs, rtol=0, atol=1e-7) and torch.allclose(v2, values, rtol=0, atol=1e-6)
+        assert torch.allclose(l2.double(), ref_logits, rtol=1e-4, atol=2e-5)
+        tcp.set_per_layer(False)
     # a second call on the same handle (buffers are reused) and a handle without the value head
     tcp.forward_bits(bits, logits=logits)
     assert torch.allclose(logits.double(), ref_logits, rtol=1e-4, atol=2e-5)

@@ -1,8 +1,9 @@
 #!/bin/bash
 # Multi-GPU evidence in one gpurun --gpus N call: the differential test at 1 GPU (reference) and at every N in the list, then bench.py at the
 # largest N.   usage: gpurun --gpus 8 --timeout 1500 -- 'bash tools/multi_gpu_check.sh TAG 2 4 8'
-TAG=${1:-r2_vX}; shift
-NS=${@:-2}
+TAG=${1:-r2_vX}
+NS=${2:-2}            # GPU counts of the differential test, e.g. "2 4 8"
+BN=${3:-$NS}          # GPU counts of the bench runs, e.g. "8"
 O=gpurun_out
 mkdir -p $O
 nvidia-smi topo -m > $O/${TAG}_topo.txt 2>&1
@@ -13,7 +14,7 @@ for n in $NS; do
   echo "parity N=$n rc=$?"; tail -1 $O/${TAG}_parity_n$n.log | head -c 600; echo
   LAST=$n
 done
-for n in $NS; do
+for n in $BN; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 20 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_n$n.json 2> $O/${TAG}_bench_n$n.err
 echo "bench N=$n rc=$?"
 python - <<PY

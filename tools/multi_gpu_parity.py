@@ -135,7 +135,7 @@ def main():
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         digest = {k: hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() for k, v in arrays.items()}
         report = {"world": world, "global_envs": Bg, "steps": T, "rollouts": R, "arrays": len(arrays), "searches": searches}
-        ref_npz, ref_json = args.out + "_n1.npz", args.out + "_n1.json"
+        ref_npz, ref_json = args.out + "_ref.npz", args.out + "_ref.json"
         if world == 1:
             np.savez_compressed(ref_npz, **{k.replace("/", "__"): v for k, v in arrays.items()})
             json.dump({"digest": digest, "searches": searches}, open(ref_json, "w"))

@@ -11,8 +11,8 @@ EXTRA=smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_lsu.sum,smsp__in
 for c in $CONFIGS; do
   timeout 420 ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:k_step -s 0 -c 3 -f -o $O/${TAG}_${c} \
     python bench.py --config $c --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-packed --no-collector --no-synth > $O/${TAG}_${c}_ncu.log 2>&1
-  ncu -i $O/${TAG}_${c}.ncu-rep --page raw --csv > $O/${TAG}_${c}_raw.csv 2>/dev/null
-  ncu -i $O/${TAG}_${c}.ncu-rep --page details --csv > $O/${TAG}_${c}_details.csv 2>/dev/null
-  tail -2 $O/${TAG}_${c}_ncu.log
+  python tools/ncu_summarize_box.py $O/${TAG}_${c}.ncu-rep $O/${TAG}_${c}_ncu.txt 2> $O/${TAG}_${c}_sum.err
+  rm -f $O/${TAG}_${c}.ncu-rep          # (tens of MB each: gpurun_out is capped at 64 MiB; the summary holds what profiles/ keeps)
+  tail -1 $O/${TAG}_${c}_ncu.log | head -c 300; echo
 done
-ls -la $O | grep ${TAG}
+ls -la $O | grep ${TAG} | head -30

@@ -47,6 +47,10 @@ def timed(fn, reps=20):
 
 
 out["tc_us"] = timed(lambda: tcp.forward_bits(bits, probs=probs, values=values))
+out["tc_fused_kernel"] = tcp.set_per_layer(True) is False and tcp.set_per_layer(False)
+tcp.set_per_layer(True)
+out["tc_per_layer_us"] = timed(lambda: tcp.forward_bits(bits, probs=probs, values=values))
+tcp.set_per_layer(False)
 
 
 def torch_fwd(prec):
