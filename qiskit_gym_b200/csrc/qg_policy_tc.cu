@@ -300,9 +300,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
 //   at a time, through the same buffer — into layer 3's A operand, and the head's accumulator takes the place of a D1 buffer.
 // Tensor memory: D1[0] cols 0..127, D1[1] cols 128..255, D2 cols 256..511.  Shared memory: 2 ring stages of 64 KB (weight tiles, and layer
 // 1's observation tiles) + the 64 KB activation buffer (which doubles as the output staging tile of the head).
-//   warp 0 loader, warp 1 MMA issuer, warps 2..9 epilogue (two warps per tensor-memory lane quarter, each converting half of the columns).
+//   warp 0 loader, warp 1 MMA issuer, warps 2..9 epilogue (two warps per tensor-memory lane quarter, each converting half of the columns),
+//   warps 10..11 expand the packed observation bits of the CTA's 128 rows into layer 1's A tile of every layer-1 stage (0 / 1 as f16: one
+//   16-byte store per 8 entries) — no expansion pre-pass, no A tiles in global memory, a fifth less traffic into shared memory.
 struct FusedArgs {
-    const __half* X0;        // observation tile images [m_tiles][Kb0][8][128][8]
+    const uint32_t* bits;    // packed observations [batch][obs_words]: layer 1's A tiles are expanded from them inside the kernel
+    int obs_words, obs_size;
+    const __half* X0;        // (unused by the fused kernel: observation tile images of the per-layer path)
     const __half* W1;        // [2 terms][NC chunks][Kb0][8][128][8]
     const __half* W2;        // [2 terms][Kb2 = E_pad / 64][8][C_pad][8]
     const __half* W3;        // [2 terms][Kb3 = C_pad / 64][8][H][8]
@@ -311,9 +315,10 @@ struct FusedArgs {
     int Kb0, NC, C_pad, Kb3, H, m_tiles, num_actions, has_value;
     long long batch;
 };
-constexpr int kFusedThreads = 320;
+constexpr int kFusedThreads = 384;        // loader, MMA, 8 epilogue warps, 2 observation-tile producer warps
 constexpr uint32_t kRingStage = 64 * 1024, kActBytes = 64 * 1024;
-constexpr uint32_t kFusedSmem = 2 * kRingStage + kActBytes + 256;
+constexpr uint32_t kFusedBias = (512 + 256 + 128) * 4;        // the three bias vectors, staged once per CTA (NC <= 4, C_pad <= 256, H <= 128)
+constexpr uint32_t kFusedSmem = 2 * kRingStage + kActBytes + 256 + kFusedBias;
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void epilogue8_sync() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void epilogue4_sync() { asm volatile("bar.sync 3, 128;\n" ::: "memory"); }
@@ -329,15 +334,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
     uint64_t* const d1_empty = bars + 6;    // [2]
     uint64_t* const d2_full = bars + 8;
     uint64_t* const d2_empty = bars + 9;
-    uint64_t* const act_full = bars + 10;
-    uint64_t* const act_empty = bars + 11;
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* const act_full = bars + 10;   // [2]: one pair of barriers per K block of the activation buffer (columns 0..63 / 64..127 of a
+    uint64_t* const act_empty = bars + 12;  // [2]  128-column piece): the epilogue refills K block 0 while the products of K block 1 still run
+    uint64_t* const a0_full = bars + 14;    // [2]: the producers' part of a layer-1 stage (the observation tile) is written
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* const sb1 = reinterpret_cast<float*>(act + kActBytes + 256);       // biases in shared memory: the epilogue reads them with broadcast
+    float* const sb2 = sb1 + 512;                                              // 16-byte loads instead of one global load per column (those
+    float* const sb3 = sb2 + 256;                                              // were the epilogue's top stall: long_scoreboard, ncu r2_v11)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halves = (a.C_pad + 127) / 128;           // D2 leaves in 128-column pieces
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(d1_full + s, 1); mbar_init(d1_empty + s, 8); }
-        mbar_init(d2_full, 1); mbar_init(d2_empty, 8); mbar_init(act_full, 8); mbar_init(act_empty, 1);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, 8);
+        for (int j = 0; j < 2; ++j) { mbar_init(act_full + j, 4); mbar_init(act_empty + j, 1); mbar_init(a0_full + j, 2); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -350,6 +360,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
     pdl_wait();
+    for (int i = threadIdx.x; i < a.NC * 128; i += kFusedThreads) sb1[i] = a.b1[i];
+    for (int i = threadIdx.x; i < a.C_pad; i += kFusedThreads) sb2[i] = a.b2[i];
+    for (int i = threadIdx.x; i < a.H; i += kFusedThreads) sb3[i] = a.b3[i];
+    __syncthreads();
 
     const uint32_t img128 = 128 * kKB;                  // halves per 128-row K-block image
     if (warp == 0) {
@@ -360,8 +374,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
             auto stage_l1 = [&](int mt, int c, int kb) {
                 mbar_wait(empty + stage, phase ^ 1u);
                 uint8_t* sp = ring + stage * kRingStage;
-                mbar_expect_tx(full + stage, 3u * img128 * 2);
-                bulk_g2s(sp, a.X0 + ((size_t)mt * a.Kb0 + kb) * img128, img128 * 2, full + stage);
+                mbar_expect_tx(full + stage, 2u * img128 * 2);           // (the first 16 KB of the stage is the producers' observation tile)
                 bulk_g2s(sp + 16384, a.W1 + (((size_t)0 * a.NC + c) * a.Kb0 + kb) * img128, img128 * 2, full + stage);
                 bulk_g2s(sp + 32768, a.W1 + (((size_t)1 * a.NC + c) * a.Kb0 + kb) * img128, img128 * 2, full + stage);
                 next();
@@ -387,7 +400,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            uint32_t n_d1e[2] = {0, 0}, n_actf = 0, n_d2e = 0;          // waits done so far on d1_empty[b], act_full, d2_empty
+            uint32_t n_d1e[2] = {0, 0}, n_actf[2] = {0, 0}, n_d2e = 0, n_a0[2] = {0, 0};  // waits done so far on d1_empty[b], act_full[j], d2_empty, a0_full[s]
             const uint32_t lbo128 = 128 * 16, sbo = 128;
             const uint32_t id1 = instr_desc(128), id2 = instr_desc(a.C_pad), id3 = instr_desc(a.H);
             const uint32_t lbo2 = (uint32_t)a.C_pad * 16, lbo3 = (uint32_t)a.H * 16;
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                         const uint32_t d = tmem_base + (uint32_t)b * 128;
                         for (int kb = 0; kb < a.Kb0; ++kb) {
                             mbar_wait(full + stage, phase);
+                            mbar_wait(a0_full + stage, n_a0[stage] & 1u); ++n_a0[stage];
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
 #pragma unroll
@@ -419,10 +433,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                     if (c > 0) {
                         // layer 2 over the two K blocks of chunk c - 1 (the epilogue's halves in the activation buffer) -> D2
                         if (c == 1) { mbar_wait(d2_empty, (n_d2e & 1u) ^ 1u); ++n_d2e; }
-                        mbar_wait(act_full, n_actf & 1u); ++n_actf;
-                        tc_fence_after();
                         const uint32_t d = tmem_base + 256;
                         for (int j = 0; j < 2; ++j) {
+                            mbar_wait(act_full + j, n_actf[j] & 1u); ++n_actf[j];
                             mbar_wait(full + stage, phase);
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
@@ -435,9 +448,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                                 umma_f16(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id2, 1u);
                             }
                             umma_commit(empty + stage);
+                            umma_commit(act_empty + j);              // this K block may be rewritten once these products have read it
                             next();
                         }
-                        umma_commit(act_empty);                      // the buffer may be rewritten once these products have read it
                     }
                 }
                 umma_commit(d2_full);
@@ -448,10 +461,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)b * 128;
                     for (int h = 0; h < halves; ++h) {
-                        mbar_wait(act_full, n_actf & 1u); ++n_actf;
-                        tc_fence_after();
                         const int kbs = min(2, a.Kb3 - 2 * h);
                         for (int j = 0; j < kbs; ++j) {
+                            mbar_wait(act_full + j, n_actf[j] & 1u); ++n_actf[j];
                             mbar_wait(full + stage, phase);
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
@@ -464,13 +476,60 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                                 umma_f16(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id3, 1u);
                             }
                             umma_commit(empty + stage);
+                            umma_commit(act_empty + j);
                             next();
                         }
-                        umma_commit(act_empty);
                     }
                     umma_commit(d1_full + b);
                 }
             }
+        }
+    } else if (warp >= 10) {
+        // ===== observation-tile producers: follow the loader's stage sequence; for every layer-1 stage write rows' 64 entries of K block kb =====
+        const int t = threadIdx.x - 320;                 // 0..63: rows t and t + 64
+        uint32_t stage = 0, phase = 0;
+        auto next = [&]() { if (++stage == 2) { stage = 0; phase ^= 1u; } };
+        for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+            for (int c = 0; c <= a.NC; ++c) {
+                if (c < a.NC) {
+                    for (int kb = 0; kb < a.Kb0; ++kb) {
+                        mbar_wait(empty + stage, phase ^ 1u);            // the products that read this stage's previous contents are done
+                        uint8_t* const tile = ring + stage * kRingStage;
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            const int row = t + rr * 64;
+                            const long long grow = (long long)mt * kM + row;
+                            uint32_t w0 = 0, w1 = 0;
+                            if (grow < a.batch) {
+                                const uint32_t* src = a.bits + (size_t)grow * a.obs_words;
+                                if (2 * kb < a.obs_words) w0 = src[2 * kb];
+                                if (2 * kb + 1 < a.obs_words) w1 = src[2 * kb + 1];
+                                const int left = a.obs_size - kb * 64;           // entries of this K block that exist
+                                if (left < 32) w0 &= left > 0 ? ((1u << left) - 1u) : 0u;
+                                if (left < 64) w1 &= left > 32 ? ((1u << (left - 32)) - 1u) : 0u;
+                            }
+#pragma unroll
+                            for (int ch = 0; ch < 8; ++ch) {
+                                const uint32_t b = ((ch < 4 ? w0 : w1) >> ((ch & 3) * 8)) & 0xFFu;
+                                uint4 o;
+                                o.x = ((b & 1u) ? 0x3C00u : 0u) | ((b & 2u) ? 0x3C000000u : 0u);
+                                o.y = ((b & 4u) ? 0x3C00u : 0u) | ((b & 8u) ? 0x3C000000u : 0u);
+                                o.z = ((b & 16u) ? 0x3C00u : 0u) | ((b & 32u) ? 0x3C000000u : 0u);
+                                o.w = ((b & 64u) ? 0x3C00u : 0u) | ((b & 128u) ? 0x3C000000u : 0u);
+                                *reinterpret_cast<uint4*>(tile + ((size_t)ch * kM + row) * 16) = o;
+                            }
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a0_full + stage);
+                        next();
+                    }
+                }
+                // layer 2's two weight stages are not the producers' business, but every use of a stage has to be waited for: a parity
+                // wait can only tell the phase it expects from the one before it, so a waiter must never fall two phases behind
+                if (c > 0) for (int j = 0; j < 2; ++j) { mbar_wait(empty + stage, phase ^ 1u); next(); }
+            }
+            for (int kb = 0; kb < a.Kb3; ++kb) { mbar_wait(empty + stage, phase ^ 1u); next(); }      // the head's weight stages
         }
     } else {
         // ===== epilogue: warps 2..9.  Quarter q = warp % 4 owns tensor-memory lanes 32q..32q+31 (rows); of the two warps of a quarter the one
@@ -489,9 +548,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                 uint32_t v[16];
                 tmem_ld16(tmem_base + lane_base + tcol + (uint32_t)c0, v);
                 uint32_t hi[8], lo[8];
+                float bb[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(bb + i) = *reinterpret_cast<const float4*>(bias + c0 + i);
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float x0 = fmaxf(__uint_as_float(v[i]) + __ldg(bias + c0 + i), 0.0f), x1 = fmaxf(__uint_as_float(v[i + 1]) + __ldg(bias + c0 + i + 1), 0.0f);
+                    const float x0 = fmaxf(__uint_as_float(v[i]) + bb[i], 0.0f), x1 = fmaxf(__uint_as_float(v[i + 1]) + bb[i + 1], 0.0f);
                     const __half2 h2 = __floats2half2_rn(x0, x1);
                     const float2 hf = __half22float2(h2);
                     const __half2 l2 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
@@ -508,15 +570,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         auto publish = [&]() {                                        // this warp's part of the buffer is written: hand it to the tensor core
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(act_full);
+            if (lane == 0) mbar_arrive(act_full + hsel);
         };
         for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
             for (int c = 0; c < a.NC; ++c) {
                 const int b = c & 1;
                 mbar_wait(d1_full + b, n_d1f[b] & 1u); ++n_d1f[b];
-                mbar_wait(act_empty, (n_acte & 1u) ^ 1u); ++n_acte;   // the previous chunk's layer-2 products have read the buffer
+                mbar_wait(act_empty + hsel, (n_acte & 1u) ^ 1u); ++n_acte;   // the previous chunk's layer-2 products have read this K block
                 tc_fence_after();
-                convert64((uint32_t)b * 128 + (uint32_t)hsel * 64, a.b1 + c * 128 + hsel * 64);
+                convert64((uint32_t)b * 128 + (uint32_t)hsel * 64, sb1 + c * 128 + hsel * 64);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d1_empty + b);
@@ -524,11 +586,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
             }
             mbar_wait(d2_full, n_d2f & 1u); ++n_d2f;
             for (int h = 0; h < halves; ++h) {
-                mbar_wait(act_empty, (n_acte & 1u) ^ 1u); ++n_acte;
+                const bool mine = h * 128 + hsel * 64 < a.C_pad;       // (a K block past C_pad does not exist: the MMA warp does not wait for it)
+                if (mine) { mbar_wait(act_empty + hsel, (n_acte & 1u) ^ 1u); ++n_acte; }
                 tc_fence_after();
-                if (h * 128 + hsel * 64 < a.C_pad) convert64(256u + (uint32_t)h * 128 + (uint32_t)hsel * 64, a.b2 + h * 128 + hsel * 64);
+                if (mine) convert64(256u + (uint32_t)h * 128 + (uint32_t)hsel * 64, sb2 + h * 128 + hsel * 64);
                 if (h == halves - 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(d2_empty); }
-                publish();
+                if (mine) publish();
             }
             // the head's accumulator
             {
@@ -545,7 +608,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                             uint32_t v[16];
                             tmem_ld16(tmem_base + lane_base + (uint32_t)b * 128 + (uint32_t)(c * 16), v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) + __ldg(a.b3 + c * 16 + i);
+                            for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) + sb3[c * 16 + i];
                         }
                     }
                 }
@@ -745,7 +808,7 @@ int qg_policy_tc_create(int32_t device, int32_t obs_size, int32_t num_layers, co
     cudaError_t ce = cudaFuncSetAttribute(tc::k_tc_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
     if (ce != cudaSuccess) { set_error(std::string("qg_policy_tc_create: ") + cudaGetErrorString(ce)); return fail(QG_ERR_CUDA); }
     // the one-kernel path: embeddings (a multiple of 128 wide after padding) -> one common layer (<= 256) -> head
-    if (num_layers == 3 && p->layers[0].Npad % 128 == 0 && p->layers[0].NT == 128 && p->layers[1].Npad <= 256) {
+    if (num_layers == 3 && p->layers[0].Npad % 128 == 0 && p->layers[0].Npad <= 512 && p->layers[0].NT == 128 && p->layers[1].Npad <= 256) {
         const TcLayer& L1 = p->layers[1];
         const int C_pad = L1.Npad, Kb2 = L1.Kb, K = L1.K;
         const size_t img = (size_t)C_pad * tc::kKB, count = (size_t)2 * Kb2 * img;
@@ -785,7 +848,7 @@ int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int
     TC_CUDA_OK(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int m_tiles = (int)((batch + tc::kM - 1) / tc::kM);
-    {
+    if (!(p->fused && !p->force_layers)) {          // (the fused kernel expands the bits itself)
         const TcLayer& L0 = p->layers[0];
         const long long total = (long long)m_tiles * L0.Kb * 8 * tc::kM;
         tc::k_tc_expand_bits<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs_bits_dev, p->obs_words, p->obs_size, batch, L0.Kb, p->acts[0], total);
@@ -794,6 +857,7 @@ int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int
     if (p->fused && !p->force_layers) {
         const TcLayer &L0 = p->layers[0], &L1 = p->layers[1], &L2 = p->layers[2];
         tc::FusedArgs a{};
+        a.bits = obs_bits_dev; a.obs_words = p->obs_words; a.obs_size = p->obs_size;
         a.X0 = p->acts[0]; a.W1 = L0.W; a.W2 = p->W2_fused; a.W3 = L2.W; a.b1 = L0.bias; a.b2 = L1.bias; a.b3 = L2.bias;
         a.logits = logits_dev; a.probs = probs_dev; a.values = values_dev;
         a.Kb0 = L0.Kb; a.NC = L0.Npad / 128; a.C_pad = L1.Npad; a.Kb3 = L2.Kb; a.H = L2.Npad; a.m_tiles = m_tiles;

@@ -43,7 +43,7 @@ def test_tensor_core_policy_matches_float64(obs_shape, A, emb, common, density):
         assert torch.allclose(probs.sum(dim=1), torch.ones(B, device=dev), atol=1e-5)
     # the fused three-layer kernel (where the shape allows it) and the one-kernel-per-layer path do the same products in the same order
     fused_runs = tcp.set_per_layer(False)
-    assert fused_runs == (len(common) == 1 and ((emb + 63) // 64 * 64) % 128 == 0 and (common[0] + 63) // 64 * 64 <= 256)
+    assert fused_runs == (len(common) == 1 and ((emb + 63) // 64 * 64) % 128 == 0 and emb <= 512 and (common[0] + 63) // 64 * 64 <= 256)
     if fused_runs:
         tcp.set_per_layer(True)
         l2 = torch.empty_like(logits); p2 = torch.empty_like(probs); v2 = torch.empty_like(values)
