@@ -99,6 +99,24 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
     if (mode == MODE_SEARCH && a.weights && (int64_t)(e->L.A | 1) * epw * 4 <= 16 * 1024) {        // staged action weights (step_tile)
         a.sm_wts = a.sm_warp_words; a.sm_warp_words += (e->L.A | 1) * epw;
     }
+    // replay launches that write dense observations: a warp PAIR per tile (step warp + store warp, step_tile roles 1 / 2) when the tile's
+    // observation bits can be handed over as one buffer: LinearFunction / Clifford (the state words), or the concatenated-stream kinds
+    // Measured at 65 536 envs (profiles/r2_v20_pair_sweep.txt): pairs gain where the stores dominate a step (C3 0.89 -> 1.06 of the copy
+    // bandwidth, C5 0.92 -> 1.02) and lose where the step logic does (C1 0.79 -> 0.52, C2 0.75 -> 0.56, C4 PauliNetwork 0.89 -> 0.72): used for
+    // observations of at least 160 entries of every kind but PauliNetwork.
+    a.pair = 0; a.sm_pair = 0; a.pair_words = 0;
+    const bool pair_pays = e->L.kind != QG_ENV_PAULI_NETWORK && e->L.obs_size >= 160;
+    if (mode == MODE_STEP && a.nsteps > 1 && a.obs && !a.obs_bits && !a.skip_negative && epw == 32 && (e->pair_forced ? e->pair_forced > 0 : pair_pays)) {
+        const int k = e->L.kind;
+        int pw = 0;
+        if (k == QG_ENV_LINEAR_FUNCTION || k == QG_ENV_CLIFFORD) pw = e->L.SW * stride;
+        else if (a.sm_cat >= 0) pw = (k == QG_ENV_PERMUTATION) ? cat_w : e->L.OW * stride;
+        if (pw > 0 && (k != QG_ENV_LINEAR_FUNCTION && k != QG_ENV_CLIFFORD ? true : (cat_w == 0 || a.sm_cat >= 0))) {
+            a.pair = 1; a.pair_words = pw; a.sm_pair = a.sm_warp_words;
+            a.sm_pair_bar = (a.sm_pair + 2 * pw + 2 + 1) & ~1;          // after the two ballot words, 8-byte aligned (the region starts 16-byte aligned)
+            a.sm_warp_words = a.sm_pair_bar + 8;
+        }
+    }
     a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     { const uint32_t vpe = (uint32_t)e->L.obs_size / 4; a.exp_q = vpe ? 32u / vpe : 0u; a.exp_r = vpe ? 32u - a.exp_q * vpe : 0u; }
@@ -111,6 +129,7 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
     DevCfg dc = e->dc;
     dc.B = LB;
     LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), ((size_t)kLutWords + (size_t)a.sm_warp_words * kWarpsPerCta) * 4, a.pdl_mode ? 1 : 0, epw};
+    if (a.pair) { g.grid = (unsigned)tiles; g.smem_bytes = ((size_t)kLutWords + (size_t)a.sm_warp_words) * 4; }
     if (e->l2_persist_bytes > 0 && mode == MODE_STEP && a.nsteps > 1 && a.actions) {
         // replay: keep the resident action stream in L2 (persisting window) so that the launch's DRAM traffic is writes only
         g.l2_base = a.actions; g.l2_bytes = std::min<size_t>((size_t)a.nsteps * (size_t)a.in_stride * 4, e->l2_persist_bytes);
@@ -257,6 +276,7 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     if (const char* v = std::getenv("QG_INV_SYMPLECTIC")) e->all_symplectic = std::atoi(v) != 0;   // 0: never use the transpose shortcut
     if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
     if (const char* v = std::getenv("QG_EPW")) e->epw_forced = std::atoi(v);
+    if (const char* v = std::getenv("QG_PAIR")) e->pair_forced = std::atoi(v) > 0 ? 1 : -1;      // 1: on for every kind, 0: off
 #endif
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
     // replay stagger (warp k of an SM starting k slab-times late so that the warps do not alternate between the step logic and the
@@ -280,7 +300,11 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     // 32-env tile; a Permutation too wide for a bit stream (OW == 0) keeps the direct byte test
     e->cat_words = ((L.obs_size & 31) != 0 && !(L.kind == QG_ENV_PERMUTATION && L.OW == 0)) ? L.obs_size : 0;
     const int wts_words = ((int64_t)(L.A | 1) * 32 * 4 <= 16 * 1024) ? (L.A | 1) * 32 : 0;
-    e->smem_bytes = ((size_t)kLutWords + (size_t)(e->sm_warp_words + std::max(e->cat_words, wts_words)) * kWarpsPerCta) * 4;   // the largest layout a launch may ask for
+    {
+        const int region = e->sm_warp_words + std::max(e->cat_words, wts_words);
+        const int pair_w = 2 * std::max({L.SW * kStride, L.OW * kStride, e->cat_words}) + 12;
+        e->smem_bytes = ((size_t)kLutWords + (size_t)std::max(region * kWarpsPerCta, region + pair_w)) * 4;   // the largest layout a launch may ask for
+    }
     if (e->smem_bytes > 200 * 1024) { set_error("configuration needs more shared memory than one SM has"); return fail(QG_ERR_UNSUPPORTED); }
     e->magic_obs = magic40((uint32_t)L.obs_size); e->magic_A = magic40((uint32_t)L.A);
     auto magic32 = [](uint32_t d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };

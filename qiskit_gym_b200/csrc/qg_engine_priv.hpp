@@ -30,6 +30,7 @@ struct qg_engine {
     size_t smem_bytes = 0; int sm_warp_words = 0, sm_scr = 0, sm_obs = 0;      // 32-env tile layout without the concatenated stream (the one-launch search's)
     int cat_words = 0;               // words of a 32-env tile's concatenated observation stream (0: this config does not use expand_cat)
     int epw_forced = 0;              // (tools builds only: 16 / 32 forces the tile size)
+    int pair_forced = 0;             // (tools builds only, QG_PAIR: +1 / -1 forces warp pairs on / off in replay launches; 0 = by observation size)
     uint64_t magic_obs = 0, magic_A = 0; uint32_t magic_vpe = 0, magic_a4 = 0;
     int nperms = 0;
     int pdl_mode = 2;                // programmatic dependent launch variant (see StepArgs); 2 = dependents launch once this grid owns the records

@@ -47,6 +47,9 @@ struct StepArgs {
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
     int32_t sm_cat;                          // offset of the tile's concatenated observation bit stream (expand_cat), or -1: not used by this launch
     int32_t sm_wts;                          // MODE_SEARCH: offset of the tile's staged action weights [env][A | 1], or -1: read them from global memory
+    int32_t pair;                            // replay with a warp PAIR per tile: warp 0 plays the steps, warp 1 expands / stores the observations (step_tile)
+    int32_t sm_pair, pair_words;             // offset of the pair's two hand-over buffers ([2][pair_words] words, then 2 header words) in the tile's region
+    int32_t sm_pair_bar;                     // offset (words, 8-byte aligned) of the pair's four mbarriers
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
     uint64_t magic_ow;                // ceil(2^40/ceil(obs_size/32))        (packed observation)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
@@ -667,6 +670,23 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
     }
 }
 
+// hand-over barriers of a warp pair: four mbarriers in the tile's shared memory (full[0..1], empty[0..1], one arrival each: lane 0 of the
+// warp that is done); the waiting warp spins on try_wait.  (Named barriers — bar.arrive / bar.sync — were measured first: the step warp of the
+// small-observation configs lost 35 % to them.)
+__device__ __forceinline__ void pair_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void pair_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "PAIR_WAIT_LOOP:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra PAIR_WAIT_DONE;\n"
+        " bra PAIR_WAIT_LOOP;\n"
+        "PAIR_WAIT_DONE:\n}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
 // The work of ONE warp on its tile of `cnt` (<= 32) consecutive environments starting at e0: record load, `a.nsteps` steps
 // (phase 1 + phase 2 each), record write-back.  wbase: the warp's private shared-memory region (a.sm_warp_words words), lut: the
 // CTA's nibble -> float4 table (only read when a.obs is set).  Returns the ballot of the environments that were stepped in the
@@ -682,10 +702,16 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
 // EPW: environments per warp tile (32, or 16: twice the warps for the same batch, lanes 16..31 idle in phase 1 and at work in phase 2 —
 // at 65 536 environments that is 28 instead of 14 warps per SM to overlap one warp's latency-bound step logic with the others' stores).
 // The tile's shared-memory words are laid out [word][EPW + 1].
-template <int KIND, int MODE, int INV, int EPW = 32>
+template <int KIND, int MODE, int INV, int EPW = 32, int ROLE = 0>
 __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a, uint32_t* const wbase, const uint32_t* const lut, const int lane,
                                               const int64_t e0, const int cnt, const bool resident = false, const float* const weights_tile = nullptr,
                                               const bool fused = false, float* const ret_local = nullptr) {
+    constexpr int role = ROLE;             // compile-time: the solo kernels carry none of the pair code (their single-step launches are
+                                           // latency-bound and lost 10-40 % to the larger code when the role was a run-time argument)
+    // role (replay launches with a.pair): 0 = the warp does everything; 1 = step warp: plays the steps and hands every step's observation
+    // bits + mask ballot to its partner through two buffers; 2 = store warp: expands them into the float / mask slabs.  The latency-bound
+    // step logic of step t+1 then overlaps the stores of step t on the SAME tile without more environments per SM (full[b] / empty[b] named
+    // barriers per buffer b = t & 1).
     constexpr int kStride = EPW + 1;       // (shadows the namespace constant: everything below indexes the tile with this launch's stride)
     typedef SmWords<kStride> Wd;
     const int64_t env = e0 + lane;
@@ -699,6 +725,35 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
     // slot launches, whose tiles may skip environments, keep the per-element path
     const bool use_cat = MODE != MODE_SEARCH && a.obs && a.sm_cat >= 0 && !a.skip_negative && !fused;
     uint32_t* const cat = wbase + (a.sm_cat >= 0 ? a.sm_cat : 0);
+    uint32_t* const pair_base = wbase + (role ? a.sm_pair : 0);
+    uint32_t* const pair_hdr = pair_base + 2 * a.pair_words;                     // [2] mask ballots, then (8-byte aligned) the four mbarriers
+    uint64_t* const pair_bar = reinterpret_cast<uint64_t*>(wbase + (role ? a.sm_pair_bar : 0));      // full[0], full[1], empty[0], empty[1]
+    if constexpr (role == 2) {
+        // ===== store warp of a pair =====
+        const uint32_t en_all = cnt >= 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+        int slot2 = a.slot0;
+        for (int t = 0; t < a.nsteps; ++t) {
+            const int b = t & 1;
+            pair_wait(pair_bar + b, (uint32_t)(t >> 1) & 1u);            // the step warp has filled buffer b
+            const uint32_t* src = pair_base + b * a.pair_words;
+            const uint32_t mask_bits2 = pair_hdr[b];
+            float* out = a.obs + ((size_t)slot2 * c.B + (size_t)e0) * c.obs_size;
+            if (use_cat) {
+                if (KIND != QG_ENV_PERMUTATION) { cat_gather<kStride>(src, cat, (uint32_t)cnt, (uint32_t)c.obs_size, a.magic_obs, lane); src = cat; }
+                expand_cat<true>(src, lut, out, (uint32_t)cnt * (uint32_t)c.obs_size, lane);
+            } else {
+                expand_obs<MODE, kStride>(src, lut, out, (uint32_t)cnt, (uint32_t)c.obs_size, en_all, lane, a.magic_vpe, a.magic_obs, a.exp_q, a.exp_r, true);
+            }
+            if (a.mask) {
+                uint8_t* mout = a.mask + ((size_t)slot2 * c.B + (size_t)e0) * c.A;
+                if ((c.A & 3) == 0) expand_mask<MODE, 4>(mout, (uint32_t)cnt, (uint32_t)c.A, mask_bits2, en_all, lane, a.magic_A);
+                else expand_mask<MODE, 1>(mout, (uint32_t)cnt, (uint32_t)c.A, mask_bits2, en_all, lane, a.magic_A);
+            }
+            if (++slot2 == a.ring) slot2 = 0;
+            pair_arrive(pair_bar + 2 + b, lane);                         // buffer b may be refilled
+        }
+        return en_all;
+    }
     uint32_t last_en_bits = 0;
     if (live && !resident) {
         const uint32_t* src = c.rec + (a.src_slot ? (int64_t)a.src_slot[env] : env);
@@ -736,6 +791,9 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         staged_wts = w;
     }
     for (int t = 0; t < a.nsteps; ++t) {
+        uint32_t* const hand = pair_base + (t & 1) * a.pair_words;       // (role 1) this step's hand-over buffer
+        if (role == 1 && t >= 2) pair_wait(pair_bar + 2 + (t & 1), (uint32_t)((t >> 1) - 1) & 1u);   // ... free again: the store warp is done with step t - 2
+        const Wd Ob = (role == 1) ? Wd{hand + lane} : O;                 // where this step's per-env observation stream is built
         bool success = (flags & FL_SUCCESS) != 0, enabled = live;
         const uint32_t coin_in = next_coin;
         if (live) {
@@ -870,7 +928,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                     pr.misc = (pr.misc & 0xFFFF0000u) | (uint32_t)perm_idx;
                     dirty = true;
                 }
-                if (a.obs || a.obs_bits || fused) pn_build_obs(c, S, pr, O, perm_idx);
+                if (a.obs || a.obs_bits || fused) pn_build_obs(c, S, pr, Ob, perm_idx);
             }
             if (KIND == QG_ENV_PERMUTATION && c.OW > 0 && (enabled || (fused && !resident)) && ((a.obs && !use_cat) || a.obs_bits || fused)) {
                 // one-hot rows: bit i*n + state[i] (permutation.rs:241-243)
@@ -911,6 +969,15 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
             }
         }
 
+        if constexpr (role == 1) {
+            // step warp of a pair: hand the observation bits and the mask ballot over, then go on with the next step
+            if (KIND == QG_ENV_PERMUTATION) cat_onehot(c, S, hand, (uint32_t)cnt, live, lane);          // (pairs need the concatenated stream for Permutation)
+            else if (KIND != QG_ENV_PAULI_NETWORK) { if (live) for (int w = 0; w < c.SW; ++w) hand[w * kStride + lane] = S[w]; }
+            if (lane == 0) pair_hdr[t & 1] = mask_bits;
+            pair_arrive(pair_bar + (t & 1), lane);
+            last_en_bits = en_bits;
+            continue;
+        }
         // ---------------- phase 2: the warp expands its 32 environments: bits -> float observation slab, mask slab --------
         if (a.obs) {
             float* out = a.obs + ((size_t)slot * c.B + (size_t)e0) * c.obs_size;
@@ -978,15 +1045,16 @@ __device__ __forceinline__ void tile_writeback(const DevCfg& c, const uint32_t* 
 
 // INV: register bucket of the add_inverts inverse (qg_gf2.cuh): 0 = generic shared-memory Gauss-Jordan (or no inverts),
 // 8 / 16 / 32 = matrix dimension bound of the register-resident versions.
-template <int KIND, int MODE, int INV, int EPW>
+template <int KIND, int MODE, int INV, int EPW, int PAIR = 0>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(const __grid_constant__ DevCfg c, const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.pdl_mode == 1) pdl_launch_dependents();
-    const int64_t e0 = ((int64_t)blockIdx.x * kWarpsPerCta + warp) * EPW;
+    constexpr bool pair = PAIR != 0;                 // one tile per CTA, warp 0 steps, warp 1 stores (step_tile roles 1 / 2)
+    const int64_t e0 = pair ? (int64_t)blockIdx.x * EPW : ((int64_t)blockIdx.x * kWarpsPerCta + warp) * EPW;
     if (e0 >= c.B) return;                           // whole warp leaves; no block barrier below
     const int cnt = (int)min((int64_t)EPW, c.B - e0);
-    uint32_t* const wbase = smem + kLutWords + (size_t)warp * a.sm_warp_words;
+    uint32_t* const wbase = smem + kLutWords + (pair ? 0 : (size_t)warp * a.sm_warp_words);
     const uint32_t* const lut = smem;                // nibble -> float4 table, first kLutWords words of the CTA's shared memory
     if (a.obs) lut_fill(smem, lane);
     if (a.pdl_mode) pdl_wait();                      // the previous grid of the stream wrote the records
@@ -1002,7 +1070,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
             __nanosleep(200);
         }
     }
-    step_tile<KIND, MODE, INV, EPW>(c, a, wbase, lut, lane, e0, cnt);
+    if constexpr (pair) {
+        if (threadIdx.x == 0) {
+            uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + a.sm_pair_bar);
+            for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bars + i)) : "memory");
+        }
+        __syncthreads();                             // (both warps of a pair CTA are alive here: they share e0)
+        // (which warp of the CTA steps alternates with the CTA index, so that the issue-heavy step warps do not all sit on the same
+        // scheduler if warps are assigned to the SM's sub-partitions by their index within the CTA)
+        if (warp == (int)(blockIdx.x & 1u)) step_tile<KIND, MODE, INV, EPW, 1>(c, a, wbase, lut, lane, e0, cnt);
+        else step_tile<KIND, MODE, INV, EPW, 2>(c, a, wbase, lut, lane, e0, cnt);
+    } else {
+        step_tile<KIND, MODE, INV, EPW, 0>(c, a, wbase, lut, lane, e0, cnt);
+    }
 }
 
 // ---- load (set_state / constructor) --------------------------------------------------------------

@@ -26,7 +26,8 @@ cudaError_t launch_epw(const DevCfg& c, const StepArgs& a, const LaunchGeom& g, 
         ++na;
     }
     lc.attrs = at; lc.numAttrs = na;
-    return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV, EPW>, c, a);
+    if constexpr (MODE == MODE_STEP && EPW == 32) { if (a.pair) return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV, EPW, 1>, c, a); }
+    return cudaLaunchKernelEx(&lc, k_step<KIND, MODE, INV, EPW, 0>, c, a);
 }
 
 template <int KIND, int MODE, int INV>
@@ -70,6 +71,10 @@ cudaError_t prepare_one(size_t smem_bytes) {
 #endif
     cudaError_t e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if constexpr (MODE == MODE_STEP) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
     if constexpr (MODE != MODE_OBSERVE) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess && smem_bytes > 48 * 1024) e = cudaFuncSetAttribute(k_step<KIND, MODE, INV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
