@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-collector", action="store_true", help="skip the policy-in-the-loop collector leg (collector.RolloutCollector)")
     ap.add_argument("--synth-rollouts", type=int, default=1000, help="num_searches per GPU of the synth leg")
     ap.add_argument("--synth-searches", type=int, default=5, help="timed searches of the synth leg")
+    ap.add_argument("--obs-buffers", type=int, default=0, help="slabs of the observation / mask ring a launch rotates over: 0 = automatic (> 2x L2 in total)")
     ap.add_argument("--tile-envs", type=int, default=0, help="qg_config.tile_envs of the env-step legs: 0 = automatic, 16 or 32 (A/B runs)")
     ap.add_argument("--synth-all-backends", action="store_true", help="also time the two-kernel and PyTorch-policy searches")
     return ap.parse_args()
@@ -86,7 +87,9 @@ def config_json(args, n_gpus):
                     f"(set_state targets: identity scrambled by 256 random gates; uniform random actions; add_inverts={bool(args.add_inverts)}, "
                     "add_perms=False, track_solution=True, default MetricsWeights)",
         "envs_per_gpu": args.envs, "env_steps_per_step": args.episode_steps, "n_gpus": n_gpus,
-        "l2_policy": "observation tensor rotates over buffers totalling > 2x L2 (126 MB); every launch writes a slab larger than it can keep resident",
+        "l2_policy": "one observation / mask slab per env-step of a launch (every step's observation is kept: nothing a launch writes is overwritten "
+                     "while it could still sit in the 126 MB L2, so all of it reaches DRAM); the ring is shorter only where it would exceed 64 GB, "
+                     "and never shorter than 3x L2",
     }
     return c
 
@@ -237,10 +240,13 @@ def run_ours(args):
     coins = None
     if args.add_inverts and kind != W.PAULI:
         coins = torch.from_numpy(rng.integers(0, 2, size=(T, B)).astype(np.uint8)).to(dev)
-    # rotating observation / mask ring: > 2x L2 in total, so every launch writes slabs that cannot stay resident
+    # observation / mask ring: one slab per env-step of an episode, so that a launch never rewrites a line that may still be in L2 (with a short
+    # ring and few tiles in flight the L2 absorbs part of the rewrites and the launch "beats" the DRAM bandwidth: profiles/r2_v26_pair_ab.txt)
     obs_bytes = B * obs_size * 4
-    nbuf = max(2, int(np.ceil(2 * 126e6 / max(obs_bytes, 1))) + 1)
-    nbuf = min(nbuf, 64)
+    nbuf = min(T, max(int(np.ceil(3 * 126e6 / max(obs_bytes, 1))) + 1, int(64e9 // max(obs_bytes + B * A, 1))))
+    nbuf = max(2, nbuf)
+    if args.obs_buffers > 0:
+        nbuf = args.obs_buffers
     obs_ring = torch.empty((nbuf, B, obs_size), dtype=torch.float32, device=dev)
     mask_ring = torch.empty((nbuf, B, A), dtype=torch.bool, device=dev)
     rew_tb = torch.empty((T, B), dtype=torch.float32, device=dev)
@@ -386,9 +392,49 @@ def run_ours(args):
                 env.replay_host_packed(h_a8, h_db, h_sb, reward_dev=rew_dev_tb, coins=h_c8, obs=obs_ring, mask=mask_ring)
                 return float(h_db[0, T - 1] & 1)
 
-            pms = host_timed(episode_host_packed, Ke)
+            # the same call, two episodes in flight (qg_replay_host_packed_async): episode i + 1 is queued (its own reward / flag buffers) before
+            # the host waits for episode i and reads its results, so the device does not idle across the host's turn-around
+            h_rw2 = [h_rw, env.host_buffer((T, B), np.float32)]
+            h_db2 = [h_db, env.host_buffer((tiles, T), np.uint32)]; h_sb2 = [h_sb, env.host_buffer((tiles, T), np.uint32)]
+
+            def submit(i):
+                env.restore()
+                env.replay_host_packed(h_a8, h_db2[i & 1], h_sb2[i & 1], reward=h_rw2[i & 1], coins=h_c8, obs=obs_ring, mask=mask_ring, sync=False)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                return ev
+
+            def collect(i):
+                return float(h_rw2[i & 1][T - 1, 0]) + float(h_db2[i & 1][0, T - 1] & 1)
+
+            def pipelined(reps):
+                with torch.cuda.stream(stream):
+                    submit(0).synchronize(); collect(0)
+                    stream.synchronize()
+                    if world > 1:
+                        dist.barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    pending = None
+                    for i in range(reps):
+                        ev = submit(i)
+                        if pending is not None:
+                            pending[0].synchronize(); collect(pending[1])
+                        pending = (ev, i)
+                    pending[0].synchronize(); collect(pending[1])
+                    e1.record(stream)
+                    stream.synchronize()
+                    t_ms = e0.elapsed_time(e1)
+                if world > 1:
+                    t2 = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+                    t_ms = float(t2.item())
+                return t_ms
+
+            sms = host_timed(episode_host_packed, Ke)          # one episode at a time: the call synchronises
             fms = host_timed(episode_host_flags_only, Ke)
-            e2e_packed = {"value": world * B * T * Ke / (pms * 1e-3), "ms": pms,
+            pms = pipelined(Ke)
+            e2e_packed = {"value": world * B * T * Ke / (pms * 1e-3), "ms": pms, "sync_value": world * B * T * Ke / (sms * 1e-3),
                           "h2d": T * B * (1 + (1 if h_c8 is not None else 0)), "d2h": T * B * 4 + 2 * tiles * T * 4,
                           "flags_only": world * B * T * Ke / (fms * 1e-3), "numa_node": getattr(env, "numa_node", -1)}
 
@@ -421,10 +467,13 @@ def run_ours(args):
         e2e = {"value": e2e_packed["value"] if e2e_packed else wide, "unit": UNIT,
                "h2d_bytes_per_step": e2e_packed["h2d"] if e2e_packed else T * B * (4 + (1 if c_np is not None else 0)),
                "d2h_bytes_per_step": e2e_packed["d2h"] if e2e_packed else T * B * 6,
-               "note": ("qg_replay_host_packed, pinned NUMA-local host buffers: uint8 actions [T][B] read by the kernel over PCIe one step ahead; f32 reward [T][B] and the "
-                        "is_final / success bit planes uint32[B/32][T] written by the kernel to host memory; one launch per episode, obs + mask stay on the device; "
-                        "the call returns when the stream is synchronised") if e2e_packed else "qg_replay_host (int32 actions; f32 reward, u8 done, u8 success)",
+               "note": ("qg_replay_host_packed_async, pinned NUMA-local host buffers, two episodes in flight (episode i + 1 is queued, with its own output buffers, "
+                        "before the host waits for episode i and reads its rewards / flags): every episode's uint8 actions [T][B] are copied from pinned host memory "
+                        "by the copy engine in flagged chunks while the kernel plays; f32 reward [T][B] and the is_final / success bit planes uint32[B/32][T] are "
+                        "written by the kernel to host memory and read by the host; one launch per episode, obs + mask stay on the device.  sync_value: "
+                        "qg_replay_host_packed, one episode at a time (the call returns when the stream is synchronised)") if e2e_packed else "qg_replay_host (int32 actions; f32 reward, u8 done, u8 success)",
                "steps": Ke,
+               "sync_value": e2e_packed["sync_value"] if e2e_packed else wide,             # one episode at a time, synchronous call
                "flags_only_value": e2e_packed["flags_only"] if e2e_packed else None,        # rewards kept on the device
                "int32_u8_format_value": wide,                                              # round-1 wire format: 10 B per env-step
                "per_step_sync_value": world * B * T * Ks / (ems_ps * 1e-3),                # qg_step_host: one synchronous call per env-step

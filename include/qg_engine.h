@@ -214,11 +214,18 @@ QG_API int qg_solutions_host(qg_engine* e, int64_t first, int64_t count, uint32_
  *  reward_dev     float[num_steps][B] or NULL
  *  done_bits_host, success_bits_host  uint32[ceil(B/32)][num_steps] (success may be NULL): bit (env % 32) of word [env / 32][t] = is_final /
  *                 success of env after step t: 2 bits per env-step, each tile's 32 consecutive steps written as one 128-byte line
- * Buffers must be pinned (qg_host_alloc, cudaHostAlloc, cudaHostRegister): the kernel reads / writes them over PCIe itself, one launch per
- * episode; QG_ERR_INVALID for pageable memory.  Observations / masks go to the device ring as in qg_replay. */
+ * Buffers must be pinned (qg_host_alloc, cudaHostAlloc, cudaHostRegister): the kernel writes the outputs over PCIe itself and reads the inputs
+ * either the same way (small episodes) or from a device staging buffer that the copy engine fills in chunks while the kernel runs (>= 1 MB of
+ * actions); one launch per episode; QG_ERR_INVALID for pageable memory.  Observations / masks go to the device ring as in qg_replay. */
 QG_API int qg_replay_host_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host,
                                  float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_host, float* reward_dev,
                                  uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream);
+/* The same call without the final synchronisation: returns once everything is queued on `stream`; the host buffers are the call's until the
+ * stream (or an event recorded on it after the call) has been waited for.  A collector keeps two episodes in flight — queue episode k + 1 (its
+ * own output buffers), then wait for episode k and read its rewards / flags — so the device never idles across the host's turn-around. */
+QG_API int qg_replay_host_packed_async(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host,
+                                       float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_host, float* reward_dev,
+                                       uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream);
 /* The device-resident form of the same formats (actions8_dev uint8[num_steps][B], bit planes on the device). */
 QG_API int qg_replay_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_dev, const uint8_t* coins_dev,
                             float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_dev,

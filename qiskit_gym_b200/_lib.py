@@ -29,7 +29,7 @@ SYMBOLS = [
     "qg_policy_create", "qg_policy_create_value", "qg_policy_destroy", "qg_policy_num_actions", "qg_policy_has_value", "qg_policy_forward_bits",
     "qg_policy_forward_bits_value",
     "qg_step_slots", "qg_copy_records", "qg_mcts_begin", "qg_mcts_select", "qg_mcts_backup", "qg_mcts_root_weights", "qg_search_run",
-    "qg_solutions", "qg_solutions_host", "qg_replay_host_packed", "qg_replay_packed", "qg_host_alloc", "qg_host_free", "qg_bind_thread_to_device",
+    "qg_solutions", "qg_solutions_host", "qg_replay_host_packed", "qg_replay_host_packed_async", "qg_replay_packed", "qg_host_alloc", "qg_host_free", "qg_bind_thread_to_device",
     "qg_dlpack_obs", "qg_search_finish", "qg_nccl_unique_id", "qg_nccl_comm_create", "qg_nccl_comm_destroy",
     "qg_policy_tc_create", "qg_policy_tc_destroy", "qg_policy_tc_num_actions", "qg_policy_tc_forward_bits", "qg_policy_tc_set_mode",
     "qg_reset_select_dev", "qg_collect_step_dev",
@@ -136,6 +136,7 @@ def lib():
     L.qg_solutions.argtypes = [vp, i64, i64, vp, i32, vp, vp]
     L.qg_solutions_host.argtypes = [vp, i64, i64, vp, i32, vp, vp]
     L.qg_replay_host_packed.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.qg_replay_host_packed_async.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.qg_replay_packed.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     L.qg_host_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), C.POINTER(i32)]
     L.qg_host_free.argtypes = [vp]

@@ -46,12 +46,17 @@ int pauli_perms(const qg_config* cfg, Twists& tw) {
     return compute_twists(cfg, true, tw);
 }
 
+// shared memory of an SM that CTAs can share (228 KB, 1 KB of it reserved per CTA) and the largest request the replay cap makes (2 CTAs per SM)
+constexpr size_t kSmSharedBytes = 228 * 1024, kReplaySmemCapMax = kSmSharedBytes / 2 - 1024;
+
 int prepare_kernels(qg_engine* e) {   // kernel attributes (shared-memory carve-out, > 48 KB opt-in) once, outside any stream capture
+    // (replay launches may ask for more shared memory than their layout needs, to bound the CTAs an SM holds: launch_step)
+    const size_t attr_bytes = std::max(e->smem_bytes, (size_t)kReplaySmemCapMax);
     switch (e->L.kind) {
-        case QG_ENV_PERMUTATION: CUDA_OK(prepare_step_kind<QG_ENV_PERMUTATION>(e->smem_bytes)); break;
-        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(prepare_step_kind<QG_ENV_LINEAR_FUNCTION>(e->smem_bytes)); break;
-        case QG_ENV_CLIFFORD: CUDA_OK(prepare_step_kind<QG_ENV_CLIFFORD>(e->smem_bytes)); break;
-        default: CUDA_OK(prepare_step_kind<QG_ENV_PAULI_NETWORK>(e->smem_bytes)); break;
+        case QG_ENV_PERMUTATION: CUDA_OK(prepare_step_kind<QG_ENV_PERMUTATION>(attr_bytes)); break;
+        case QG_ENV_LINEAR_FUNCTION: CUDA_OK(prepare_step_kind<QG_ENV_LINEAR_FUNCTION>(attr_bytes)); break;
+        case QG_ENV_CLIFFORD: CUDA_OK(prepare_step_kind<QG_ENV_CLIFFORD>(attr_bytes)); break;
+        default: CUDA_OK(prepare_step_kind<QG_ENV_PAULI_NETWORK>(attr_bytes)); break;
     }
     return QG_OK;
 }
@@ -100,13 +105,16 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
         a.sm_wts = a.sm_warp_words; a.sm_warp_words += (e->L.A | 1) * epw;
     }
     // replay launches that write dense observations: a warp PAIR per tile (step warp + store warp, step_tile roles 1 / 2) when the tile's
-    // observation bits can be handed over as one buffer: LinearFunction / Clifford (the state words), or the concatenated-stream kinds
-    // Measured at 65 536 envs (profiles/r2_v20_pair_sweep.txt): pairs gain where the stores dominate a step (C3 0.89 -> 1.06 of the copy
-    // bandwidth, C5 0.92 -> 1.02) and lose where the step logic does (C1 0.79 -> 0.52, C2 0.75 -> 0.56, C4 PauliNetwork 0.89 -> 0.72): used for
-    // observations of at least 160 entries of every kind but PauliNetwork.
+    // observation bits can be handed over as one buffer — LinearFunction / Clifford (the state words), or the concatenated-stream kinds — and a
+    // bound on the CTAs (= tiles) an SM holds at a time.  Measured at 65 536 envs with one observation slab per step
+    // (profiles/r2_v27_resident_sweep.txt, fractions of the copy bandwidth): what decides is how many tiles write at once — with all 2 048
+    // tiles resident a launch reaches 0.89 (C3) whether tiles are pairs or not; with 3-5 pair CTAs per SM 0.98-0.99 (C3), 1.00-1.01 (C5); the
+    // kinds whose step logic dominates need more tiles in flight to cover it: 8 per SM gives C2 0.80 (all resident: 0.74), C4 0.945 (0.89),
+    // C1 0.80 (0.79), while 4 per SM loses a third.  Pairs because a bounded SM needs the step logic of step t+1 overlapped with the stores of
+    // step t on the SAME tile (single-warp tiles at the best bound: C3 0.94, and 0.75 one notch off it).
     a.pair = 0; a.sm_pair = 0; a.pair_words = 0;
-    const bool pair_pays = e->L.kind != QG_ENV_PAULI_NETWORK && e->L.obs_size >= 160;
-    if (mode == MODE_STEP && a.nsteps > 1 && a.obs && !a.obs_bits && !a.skip_negative && epw == 32 && (e->pair_forced ? e->pair_forced > 0 : pair_pays)) {
+    int resident = 0;                // CTAs per SM of this launch (0 = whatever fits)
+    if (mode == MODE_STEP && a.nsteps >= 8 && a.obs && !a.obs_bits && !a.skip_negative && epw == 32 && e->pair_forced >= 0) {
         const int k = e->L.kind;
         int pw = 0;
         if (k == QG_ENV_LINEAR_FUNCTION || k == QG_ENV_CLIFFORD) pw = e->L.SW * stride;
@@ -115,8 +123,25 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
             a.pair = 1; a.pair_words = pw; a.sm_pair = a.sm_warp_words;
             a.sm_pair_bar = (a.sm_pair + 2 * pw + 2 + 1) & ~1;          // after the two ballot words, 8-byte aligned (the region starts 16-byte aligned)
             a.sm_warp_words = a.sm_pair_bar + 8;
+            // CTAs per SM (profiles/r2_v27_resident_sweep.txt, r2_v28_resident_sweep2.txt; 2 048 tiles on 148 SMs).  Where the stores dominate a
+            // step (LinearFunction / Clifford / Permutation with >= 160 entries) 3-5 are equally good (C3 0.98-0.99, C5 1.00-1.01) and the tail
+            // of a partly filled last wave costs nothing (its tiles get the bandwidth of the missing ones).  Where the step logic dominates,
+            // a tile runs at its own pace however few are left: the last wave has to be full — 7 per SM is 1.98 waves (C1 0.82, C2 0.84), 6 is
+            // 2.31 (0.64, 0.67), 8 is 1.73 (0.80, 0.79): the bound with the best-filled last wave among 7..10.  PauliNetwork, both at once: 8.
+            const int64_t t32 = (LB + 31) / 32;
+            if (k != QG_ENV_PAULI_NETWORK && e->L.obs_size >= 160) resident = 5;
+            else if (k == QG_ENV_PAULI_NETWORK) resident = 8;
+            else {
+                double best = -1.0;
+                for (int r = 7; r <= 10; ++r) {
+                    const int64_t slots = (int64_t)e->num_sms * r, waves = (t32 + slots - 1) / slots;
+                    const double fill = (double)t32 / (double)(waves * slots);
+                    if (fill > best + 1e-9) { best = fill; resident = r; }
+                }
+            }
         }
     }
+    if (e->replay_ctas) resident = e->replay_ctas > 0 ? e->replay_ctas : 0;
     a.magic_obs = e->magic_obs; a.magic_A = e->magic_A;
     a.magic_vpe = e->magic_vpe; a.magic_a4 = e->magic_a4;
     { const uint32_t vpe = (uint32_t)e->L.obs_size / 4; a.exp_q = vpe ? 32u / vpe : 0u; a.exp_r = vpe ? 32u - a.exp_q * vpe : 0u; }
@@ -130,6 +155,11 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
     dc.B = LB;
     LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), ((size_t)kLutWords + (size_t)a.sm_warp_words * kWarpsPerCta) * 4, a.pdl_mode ? 1 : 0, epw};
     if (a.pair) { g.grid = (unsigned)tiles; g.smem_bytes = ((size_t)kLutWords + (size_t)a.sm_warp_words) * 4; }
+    // the bound: the request is padded to 1 / resident of the SM's shared memory
+    if (mode == MODE_STEP && a.nsteps >= 8 && a.obs && resident >= 2) {
+        const size_t cap = (kSmSharedBytes / (size_t)resident - 1024) & ~(size_t)127;
+        if (cap > g.smem_bytes) g.smem_bytes = cap;
+    }
     if (e->l2_persist_bytes > 0 && mode == MODE_STEP && a.nsteps > 1 && a.actions) {
         // replay: keep the resident action stream in L2 (persisting window) so that the launch's DRAM traffic is writes only
         g.l2_base = a.actions; g.l2_bytes = std::min<size_t>((size_t)a.nsteps * (size_t)a.in_stride * 4, e->l2_persist_bytes);
@@ -276,7 +306,8 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     if (const char* v = std::getenv("QG_INV_SYMPLECTIC")) e->all_symplectic = std::atoi(v) != 0;   // 0: never use the transpose shortcut
     if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
     if (const char* v = std::getenv("QG_EPW")) e->epw_forced = std::atoi(v);
-    if (const char* v = std::getenv("QG_PAIR")) e->pair_forced = std::atoi(v) > 0 ? 1 : -1;      // 1: on for every kind, 0: off
+    if (const char* v = std::getenv("QG_REPLAY_CTAS")) e->replay_ctas = std::atoi(v);
+    if (const char* v = std::getenv("QG_PAIR")) e->pair_forced = std::atoi(v) > 0 ? 1 : -1;      // 0: single-warp tiles in replay launches too
 #endif
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }
     // replay stagger (warp k of an SM starting k slab-times late so that the warps do not alternate between the step logic and the

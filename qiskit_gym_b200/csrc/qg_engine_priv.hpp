@@ -30,7 +30,8 @@ struct qg_engine {
     size_t smem_bytes = 0; int sm_warp_words = 0, sm_scr = 0, sm_obs = 0;      // 32-env tile layout without the concatenated stream (the one-launch search's)
     int cat_words = 0;               // words of a 32-env tile's concatenated observation stream (0: this config does not use expand_cat)
     int epw_forced = 0;              // (tools builds only: 16 / 32 forces the tile size)
-    int pair_forced = 0;             // (tools builds only, QG_PAIR: +1 / -1 forces warp pairs on / off in replay launches; 0 = by observation size)
+    int replay_ctas = 0;             // (tools builds only, QG_REPLAY_CTAS: CTAs an SM may hold in replay launches, -1 = whatever fits; 0 = launch_step's rule)
+    int pair_forced = 0;             // (tools builds only, QG_PAIR=0 -> -1: no warp pairs in replay launches)
     uint64_t magic_obs = 0, magic_A = 0; uint32_t magic_vpe = 0, magic_a4 = 0;
     int nperms = 0;
     int pdl_mode = 2;                // programmatic dependent launch variant (see StepArgs); 2 = dependents launch once this grid owns the records
@@ -44,6 +45,13 @@ struct qg_engine {
     float* rp_reward[2] = {nullptr, nullptr}; uint8_t* rp_done[2] = {nullptr, nullptr}; uint8_t* rp_success[2] = {nullptr, nullptr};
     cudaStream_t rp_in = nullptr, rp_out = nullptr;
     cudaEvent_t rp_ev_in[2] = {nullptr, nullptr}, rp_ev_run[2] = {nullptr, nullptr}, rp_ev_out[2] = {nullptr, nullptr}, rp_ev_start = nullptr;
+    // qg_replay_host_packed: device staging of the host action / coin streams, filled by the copy engine while the kernel runs (qg_extras.cu)
+    uint8_t* hp_act[2] = {nullptr, nullptr}; uint8_t* hp_coin[2] = {nullptr, nullptr}; size_t hp_cap = 0;      // two slots, used in turn
+    uint32_t* hp_flags = nullptr;                    // device: [2 slots][4] chunk-arrived flags
+    uint32_t* hp_ones = nullptr;                     // pinned host: four ones (the value a flag is raised to), four zeros (what clears a slot's flags)
+    cudaStream_t hp_stream = nullptr;
+    cudaEvent_t hp_ev_done[2] = {nullptr, nullptr}, hp_ev_zero[2] = {nullptr, nullptr};      // a slot's last launch is over / its flags are cleared
+    bool hp_used[2] = {false, false}; int hp_next = 0;
     // qg_extras.cu (allocated on first use, freed by qg_destroy through qg_extras_release)
     uint32_t* fin_send = nullptr; uint32_t* fin_recv = nullptr; int fin_cap = 0, fin_world = 0;   // qg_search_finish exchange buffers
     uint32_t* h_fin = nullptr;                                                                     // pinned copy of the winning row

@@ -160,6 +160,17 @@ void qg::extras_release(qg_engine* e) {
     if (e->bulk_sol) cudaFree(e->bulk_sol);
     if (e->bulk_len) cudaFree(e->bulk_len);
     if (e->dl_obs) cudaFree(e->dl_obs);
+    for (int s2 = 0; s2 < 2; ++s2) {
+        if (e->hp_act[s2]) cudaFree(e->hp_act[s2]);
+        if (e->hp_coin[s2]) cudaFree(e->hp_coin[s2]);
+        if (e->hp_ev_done[s2]) cudaEventDestroy(e->hp_ev_done[s2]);
+        if (e->hp_ev_zero[s2]) cudaEventDestroy(e->hp_ev_zero[s2]);
+        e->hp_act[s2] = e->hp_coin[s2] = nullptr; e->hp_ev_done[s2] = e->hp_ev_zero[s2] = nullptr;
+    }
+    if (e->hp_flags) cudaFree(e->hp_flags);
+    if (e->hp_ones) cudaFreeHost(e->hp_ones);
+    if (e->hp_stream) cudaStreamDestroy(e->hp_stream);
+    e->hp_flags = e->hp_ones = nullptr; e->hp_stream = nullptr; e->hp_cap = 0;
     e->fin_send = e->fin_recv = e->h_fin = e->bulk_sol = nullptr; e->bulk_len = nullptr; e->dl_obs = nullptr;
 }
 
@@ -225,8 +236,9 @@ int qg_replay_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_de
     return launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
 }
 
-int qg_replay_host_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
-                          int32_t ring, float* reward_host, float* reward_dev, uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream) {
+static int replay_host_packed_impl(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
+                                   int32_t ring, float* reward_host, float* reward_dev, uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream,
+                                   bool synchronise) {
     if (!e || !actions8_host) { set_error("null argument"); return QG_ERR_INVALID; }
     if (num_steps < 0 || ring < 1) { set_error("qg_replay_host_packed: num_steps must be >= 0 and ring >= 1"); return QG_ERR_INVALID; }
     if (e->L.A > 256) { set_error("the packed wire format needs num_actions <= 256"); return QG_ERR_UNSUPPORTED; }
@@ -241,13 +253,77 @@ int qg_replay_host_packed(qg_engine* e, int32_t num_steps, const uint8_t* action
         return QG_ERR_INVALID;
     }
     StepArgs a{}; a.actions8 = (const uint8_t*)m_act; a.coins = (const uint8_t*)m_coin; a.obs = obs_dev; a.mask = mask_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    // Inputs: read by the kernel straight from host memory, a launch makes one 32-byte PCIe read per tile and step (262 144 of them for
+    // 65 536 envs x 128 steps) and is throttled by their rate (profiles/r2_v25_e2e_probe.json).  Instead the copy engine streams the rows into
+    // a device staging buffer in three chunks of growing size (4, 28 steps, the rest) on a second stream, each followed by a 4-byte copy that
+    // raises the chunk's flag; the kernel starts with the first chunk and polls a flag only when it crosses a chunk border
+    // (wait_input_chunk) — by then the engine, which moves a step's row in ~1 us against ~10 us per step of the kernel, is far ahead.
+    // Two staging slots alternate, so the inputs of an episode queued behind a running one (qg_replay_host_packed_async) arrive while
+    // that one still plays.  Everything is queued BEFORE the launch: a tool that serialises launches (ncu, compute-sanitizer) cannot
+    // dead-lock it; flags are cleared by a copy too (a memset kernel would wait for an SM slot).
+    const size_t row = (size_t)e->B, total = row * (size_t)num_steps;
+    int slot = -1;
+    if (num_steps >= 16 && total >= (size_t)1 << 20) {
+        if (!e->hp_stream) {
+            CUDA_OK(cudaStreamCreateWithFlags(&e->hp_stream, cudaStreamNonBlocking));
+            for (int s2 = 0; s2 < 2; ++s2) {
+                CUDA_OK(cudaEventCreateWithFlags(&e->hp_ev_done[s2], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&e->hp_ev_zero[s2], cudaEventDisableTiming));
+            }
+            CUDA_OK(cudaMalloc(&e->hp_flags, 2 * 4 * sizeof(uint32_t)));
+            CUDA_OK(cudaMemset(e->hp_flags, 0, 2 * 4 * sizeof(uint32_t)));
+            CUDA_OK(cudaHostAlloc(&e->hp_ones, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+            for (int i = 0; i < 4; ++i) { e->hp_ones[i] = 1u; e->hp_ones[4 + i] = 0u; }
+        }
+        if (total > e->hp_cap) {
+            CUDA_OK(cudaStreamSynchronize(st));
+            CUDA_OK(cudaStreamSynchronize(e->hp_stream));
+            for (int s2 = 0; s2 < 2; ++s2) {
+                if (e->hp_act[s2]) cudaFree(e->hp_act[s2]);
+                if (e->hp_coin[s2]) cudaFree(e->hp_coin[s2]);
+                e->hp_act[s2] = nullptr; e->hp_coin[s2] = nullptr;
+            }
+            e->hp_cap = 0;
+            for (int s2 = 0; s2 < 2; ++s2) { CUDA_OK(cudaMalloc(&e->hp_act[s2], total)); CUDA_OK(cudaMalloc(&e->hp_coin[s2], total)); }
+            e->hp_cap = total; e->hp_used[0] = e->hp_used[1] = false;
+        }
+        slot = e->hp_next; e->hp_next ^= 1;
+        uint32_t* const flags = e->hp_flags + 4 * slot;
+        if (e->hp_used[slot]) CUDA_OK(cudaStreamWaitEvent(e->hp_stream, e->hp_ev_done[slot], 0));     // the launch that last read this slot is over
+        CUDA_OK(cudaMemcpyAsync(flags, e->hp_ones + 4, 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, e->hp_stream));
+        CUDA_OK(cudaEventRecord(e->hp_ev_zero[slot], e->hp_stream));
+        const int begin[4] = {0, 4, 32, num_steps};
+        for (int k = 0; k < 4; ++k) a.in_chunk[k] = -1;
+        for (int k = 0; k < 3; ++k) {
+            if (begin[k] >= num_steps) continue;
+            const size_t o = (size_t)begin[k] * row, n = (size_t)(std::min(begin[k + 1], (int)num_steps) - begin[k]) * row;
+            CUDA_OK(cudaMemcpyAsync(e->hp_act[slot] + o, actions8_host + o, n, cudaMemcpyHostToDevice, e->hp_stream));
+            if (coins_host) CUDA_OK(cudaMemcpyAsync(e->hp_coin[slot] + o, coins_host + o, n, cudaMemcpyHostToDevice, e->hp_stream));
+            CUDA_OK(cudaMemcpyAsync(flags + k, e->hp_ones + k, sizeof(uint32_t), cudaMemcpyHostToDevice, e->hp_stream));
+            a.in_chunk[k] = begin[k];
+        }
+        CUDA_OK(cudaStreamWaitEvent(st, e->hp_ev_zero[slot], 0));                                        // the launch must not see the previous episode's flags
+        a.actions8 = e->hp_act[slot]; a.coins = coins_host ? e->hp_coin[slot] : nullptr; a.in_flags = flags;
+    }
     a.reward = reward_host ? (float*)m_rew : reward_dev;
     a.done_bits = (uint32_t*)m_done; a.success_bits = (uint32_t*)m_suc; a.bits_stride = num_steps; a.bits_t0 = 0;
     a.nsteps = num_steps; a.ring = ring; a.in_stride = e->B; a.out_stride = e->B;
-    const int rc = launch_step(e, MODE_STEP, a, (cudaStream_t)stream);
-    if (rc != QG_OK) return rc;
-    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    const int rc = launch_step(e, MODE_STEP, a, st);
+    if (rc != QG_OK) { if (slot >= 0) cudaStreamSynchronize(e->hp_stream); return rc; }
+    if (slot >= 0) { CUDA_OK(cudaEventRecord(e->hp_ev_done[slot], st)); e->hp_used[slot] = true; }
+    if (synchronise) CUDA_OK(cudaStreamSynchronize(st));
     return QG_OK;
+}
+
+int qg_replay_host_packed(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
+                          int32_t ring, float* reward_host, float* reward_dev, uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream) {
+    return replay_host_packed_impl(e, num_steps, actions8_host, coins_host, obs_dev, mask_dev, ring, reward_host, reward_dev, done_bits_host, success_bits_host, stream, true);
+}
+
+int qg_replay_host_packed_async(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host, float* obs_dev, uint8_t* mask_dev,
+                                int32_t ring, float* reward_host, float* reward_dev, uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream) {
+    return replay_host_packed_impl(e, num_steps, actions8_host, coins_host, obs_dev, mask_dev, ring, reward_host, reward_dev, done_bits_host, success_bits_host, stream, false);
 }
 
 int qg_bind_thread_to_device(int32_t device) {

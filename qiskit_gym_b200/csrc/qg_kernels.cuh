@@ -47,9 +47,11 @@ struct StepArgs {
     int32_t sm_warp_words, sm_scr, sm_obs;   // per-warp shared-memory region size and sub-region offsets (words)
     int32_t sm_cat;                          // offset of the tile's concatenated observation bit stream (expand_cat), or -1: not used by this launch
     int32_t sm_wts;                          // MODE_SEARCH: offset of the tile's staged action weights [env][A | 1], or -1: read them from global memory
+    const uint32_t* in_flags;                // replay from a staging buffer the copy engine is still filling (qg_replay_host_packed): in_flags[k] != 0 once the
+    int32_t in_chunk[4];                     // action / coin rows from step in_chunk[k] on have arrived (-1: no such chunk); null: all resident
     int32_t pair;                            // replay with a warp PAIR per tile: warp 0 plays the steps, warp 1 expands / stores the observations (step_tile)
     int32_t sm_pair, pair_words;             // offset of the pair's two hand-over buffers ([2][pair_words] words, then 2 header words) in the tile's region
-    int32_t sm_pair_bar;                     // offset (words, 8-byte aligned) of the pair's four mbarriers
+    int32_t sm_pair_bar;                     // offset (words, 8-byte aligned) of four mbarriers (QG_PAIR_MBARRIER tools builds only; the product uses named barriers)
     uint64_t magic_obs, magic_A;      // ceil(2^40/obs_size), ceil(2^40/A)   (general paths)
     uint64_t magic_ow;                // ceil(2^40/ceil(obs_size/32))        (packed observation)
     uint32_t magic_vpe, magic_a4;     // ceil(2^32/(obs_size/4)), ceil(2^32/(A/4))   (fast paths)
@@ -670,21 +672,73 @@ __device__ __forceinline__ void expand_mask(uint8_t* out, uint32_t cnt, uint32_t
     }
 }
 
-// hand-over barriers of a warp pair: four mbarriers in the tile's shared memory (full[0..1], empty[0..1], one arrival each: lane 0 of the
-// warp that is done); the waiting warp spins on try_wait.  (Named barriers — bar.arrive / bar.sync — were measured first: the step warp of the
-// small-observation configs lost 35 % to them.)
-__device__ __forceinline__ void pair_arrive(uint64_t* bar, int lane) {
+// hand-over barriers of a warp pair: hardware named barriers 0..3 of the CTA (full[0..1] = 0, 1; empty[0..1] = 2, 3; 64 threads each: the 32
+// lanes of the warp that is done arrive, the 32 of the waiting warp sync and sleep in hardware until then).  Shared-memory mbarriers with a
+// try_wait / nanosleep loop measure the same within 0.5 % (profiles/r2_v26_pair_ab.txt) and are kept as a tools build.
+#ifdef QG_PAIR_MBARRIER      // (tools A/B build)
+__device__ __forceinline__ void pair_arrive(uint64_t* bars, int idx, int lane) {
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+    // idx >= 2: the store warp frees a buffer it has only READ (its loads have returned: their values fed the stores) — a relaxed arrive
+    if (lane == 0) {
+        if (idx >= 2) asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bars + idx)) : "memory");
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bars + idx)) : "memory");
+    }
 }
-__device__ __forceinline__ void pair_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        "PAIR_WAIT_LOOP:\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @p bra PAIR_WAIT_DONE;\n"
-        " bra PAIR_WAIT_LOOP;\n"
-        "PAIR_WAIT_DONE:\n}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+__device__ __forceinline__ void pair_wait(uint64_t* bars, int idx, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bars + idx);
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(128);
+    }
+}
+#else
+// (immediate barrier numbers 0..3: with the number in a register ptxas reserves all 16 barriers for the CTA and the SM holds 4 CTAs instead of 16)
+#ifdef QG_PAIR_DYNBAR        // (tools A/B build)
+__device__ __forceinline__ void pair_arrive(uint64_t*, int idx, int) { asm volatile("bar.arrive %0, 64;\n" ::"r"(idx + 1) : "memory"); }
+__device__ __forceinline__ void pair_wait(uint64_t*, int idx, uint32_t) { asm volatile("bar.sync %0, 64;\n" ::"r"(idx + 1) : "memory"); }
+#else
+__device__ __forceinline__ void pair_arrive(uint64_t*, int idx, int) {
+    switch (idx) {
+        case 0: asm volatile("bar.arrive 0, 64;\n" ::: "memory"); break;
+        case 1: asm volatile("bar.arrive 1, 64;\n" ::: "memory"); break;
+        case 2: asm volatile("bar.arrive 2, 64;\n" ::: "memory"); break;
+        default: asm volatile("bar.arrive 3, 64;\n" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void pair_wait(uint64_t*, int idx, uint32_t) {
+    switch (idx) {
+        case 0: asm volatile("bar.sync 0, 64;\n" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 1, 64;\n" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 2, 64;\n" ::: "memory"); break;
+        default: asm volatile("bar.sync 3, 64;\n" ::: "memory"); break;
+    }
+}
+#endif
+#endif
+
+// Rows of the action / coin streams that the copy engine is still bringing from the host (qg_replay_host_packed): the warp that is about to read
+// row `step` waits until the chunk that starts there has landed (the flag is a 4-byte copy queued behind the chunk's copies on the same stream).
+__device__ __forceinline__ void wait_input_chunk(const StepArgs& a, int step, int lane) {
+    int k = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (step == a.in_chunk[i]) k = i;
+    if (k < 0) return;
+    if (lane == 0) {
+        long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.in_flags + k) : "memory");
+            if (v) break;
+            __nanosleep(256);
+            long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 10000000000ll) break;          // 10 s: a copy that never comes must not hang the device
+        }
+    }
+    __syncwarp();
 }
 
 // The work of ONE warp on its tile of `cnt` (<= 32) consecutive environments starting at e0: record load, `a.nsteps` steps
@@ -734,7 +788,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         int slot2 = a.slot0;
         for (int t = 0; t < a.nsteps; ++t) {
             const int b = t & 1;
-            pair_wait(pair_bar + b, (uint32_t)(t >> 1) & 1u);            // the step warp has filled buffer b
+            pair_wait(pair_bar, b, (uint32_t)(t >> 1) & 1u);            // the step warp has filled buffer b
             const uint32_t* src = pair_base + b * a.pair_words;
             const uint32_t mask_bits2 = pair_hdr[b];
             float* out = a.obs + ((size_t)slot2 * c.B + (size_t)e0) * c.obs_size;
@@ -750,7 +804,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 else expand_mask<MODE, 1>(mout, (uint32_t)cnt, (uint32_t)c.A, mask_bits2, en_all, lane, a.magic_A);
             }
             if (++slot2 == a.ring) slot2 = 0;
-            pair_arrive(pair_bar + 2 + b, lane);                         // buffer b may be refilled
+            pair_arrive(pair_bar, 2 + b, lane);                         // buffer b may be refilled
         }
         return en_all;
     }
@@ -772,10 +826,16 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
 
     // replay: the next step's action (and coin) is requested before this step's expansion, so its DRAM latency is hidden
     int next_action = -1; uint32_t next_coin = 0;
-    auto load_action = [&](size_t idx) { return a.actions8 ? (int)QG_LD_STREAM(a.actions8 + idx) : (int)QG_LD_STREAM(a.actions + idx); };
+    // (rows still in flight from the host: L2-only loads — a line of L1 could hold the neighbouring row from before this one arrived)
+    auto load_action = [&](size_t idx) {
+        if (a.in_flags) return a.actions8 ? (int)__ldcg(a.actions8 + idx) : (int)__ldcg(a.actions + idx);
+        return a.actions8 ? (int)QG_LD_STREAM(a.actions8 + idx) : (int)QG_LD_STREAM(a.actions + idx);
+    };
+    auto load_coin = [&](size_t idx) { return a.in_flags ? (uint32_t)__ldcg(a.coins + idx) : (uint32_t)QG_LD_STREAM(a.coins + idx); };
+    if (MODE == MODE_STEP && a.in_flags) wait_input_chunk(a, 0, lane);
     if (MODE == MODE_STEP && live) {
         next_action = load_action((size_t)env);
-        if (a.coins) next_coin = QG_LD_STREAM(a.coins + env);
+        if (a.coins) next_coin = load_coin((size_t)env);
     }
     uint32_t acc_done = 0, acc_succ = 0;             // lane l: the tile's is_final / success ballots of step (t & ~31) + l (a.done_bits)
     // MODE_SEARCH: the tile's action weights [cnt][A] are contiguous in global memory: the warp copies them into shared memory with coalesced
@@ -792,10 +852,11 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
     }
     for (int t = 0; t < a.nsteps; ++t) {
         uint32_t* const hand = pair_base + (t & 1) * a.pair_words;       // (role 1) this step's hand-over buffer
-        if (role == 1 && t >= 2) pair_wait(pair_bar + 2 + (t & 1), (uint32_t)((t >> 1) - 1) & 1u);   // ... free again: the store warp is done with step t - 2
+        if (role == 1 && t >= 2) pair_wait(pair_bar, 2 + (t & 1), (uint32_t)((t >> 1) - 1) & 1u);   // ... free again: the store warp is done with step t - 2
         const Wd Ob = (role == 1) ? Wd{hand + lane} : O;                 // where this step's per-env observation stream is built
         bool success = (flags & FL_SUCCESS) != 0, enabled = live;
         const uint32_t coin_in = next_coin;
+        if (MODE == MODE_STEP && a.in_flags && t + 1 < a.nsteps) wait_input_chunk(a, t + 1, lane);       // (whole warp) row t + 1 is requested below
         if (live) {
             int action = -1;
             if (MODE == MODE_STEP) {
@@ -803,7 +864,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
                 if (a.skip_negative && action < 0) enabled = false;
                 if (t + 1 < a.nsteps) {
                     next_action = load_action((size_t)(t + 1) * a.in_stride + env);
-                    if (a.coins) next_coin = QG_LD_STREAM(a.coins + (size_t)(t + 1) * a.in_stride + env);
+                    if (a.coins) next_coin = load_coin((size_t)(t + 1) * a.in_stride + env);
                 }
             }
             if (MODE == MODE_SEARCH) {
@@ -974,7 +1035,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
             if (KIND == QG_ENV_PERMUTATION) cat_onehot(c, S, hand, (uint32_t)cnt, live, lane);          // (pairs need the concatenated stream for Permutation)
             else if (KIND != QG_ENV_PAULI_NETWORK) { if (live) for (int w = 0; w < c.SW; ++w) hand[w * kStride + lane] = S[w]; }
             if (lane == 0) pair_hdr[t & 1] = mask_bits;
-            pair_arrive(pair_bar + (t & 1), lane);
+            pair_arrive(pair_bar, t & 1, lane);
             last_en_bits = en_bits;
             continue;
         }
@@ -1071,14 +1132,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
         }
     }
     if constexpr (pair) {
+#ifdef QG_PAIR_MBARRIER
         if (threadIdx.x == 0) {
             uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + a.sm_pair_bar);
             for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bars + i)) : "memory");
         }
         __syncthreads();                             // (both warps of a pair CTA are alive here: they share e0)
+#endif
         // (which warp of the CTA steps alternates with the CTA index, so that the issue-heavy step warps do not all sit on the same
         // scheduler if warps are assigned to the SM's sub-partitions by their index within the CTA)
-        if (warp == (int)(blockIdx.x & 1u)) step_tile<KIND, MODE, INV, EPW, 1>(c, a, wbase, lut, lane, e0, cnt);
+#ifdef QG_PAIR_NOALT
+        const bool steps = warp == 0;
+#else
+        const bool steps = warp == (int)(blockIdx.x & 1u);
+#endif
+        if (steps) step_tile<KIND, MODE, INV, EPW, 1>(c, a, wbase, lut, lane, e0, cnt);
         else step_tile<KIND, MODE, INV, EPW, 2>(c, a, wbase, lut, lane, e0, cnt);
     } else {
         step_tile<KIND, MODE, INV, EPW, 0>(c, a, wbase, lut, lane, e0, cnt);

@@ -284,9 +284,10 @@ class BatchedEnv:
 
     def replay_host_packed(self, actions8: np.ndarray, done_bits: np.ndarray, success_bits: np.ndarray | None = None, reward: np.ndarray | None = None,
                            reward_dev: torch.Tensor | None = None, coins: np.ndarray | None = None, obs: torch.Tensor | None = None,
-                           mask: torch.Tensor | None = None):
+                           mask: torch.Tensor | None = None, sync: bool = True):
         """qg_replay_host_packed: uint8 actions [T, B] in; f32 reward [T, B] (host, or kept on the device in reward_dev) and the
-        is_final / success bit planes uint32[ceil(B/32), T] out; pinned buffers (host_buffer) only."""
+        is_final / success bit planes uint32[ceil(B/32), T] out; pinned buffers (host_buffer) only.  sync=False (qg_replay_host_packed_async):
+        returns once the episode is queued on the current stream; the buffers belong to the call until that stream has been waited for."""
         assert actions8.dtype == np.uint8 and actions8.flags.c_contiguous and actions8.shape[-1] == self.batch
         T = int(actions8.shape[0])
         ring = 1
@@ -301,8 +302,8 @@ class BatchedEnv:
         assert reward is None or (reward.dtype == np.float32 and reward.flags.c_contiguous and reward.size == T * self.batch)
         assert reward_dev is None or (reward_dev.dtype == torch.float32 and reward_dev.is_contiguous() and reward_dev.numel() == T * self.batch)
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-        check(lib().qg_replay_host_packed(self._h, T, p(actions8), p(coins), _dptr(obs), _dptr(mask), ring, p(reward), _dptr(reward_dev),
-                                          p(done_bits), p(success_bits), self._stream()))
+        fn = lib().qg_replay_host_packed if sync else lib().qg_replay_host_packed_async
+        check(fn(self._h, T, p(actions8), p(coins), _dptr(obs), _dptr(mask), ring, p(reward), _dptr(reward_dev), p(done_bits), p(success_bits), self._stream()))
 
     def replay_packed(self, actions8: torch.Tensor, done_bits: torch.Tensor | None = None, success_bits: torch.Tensor | None = None,
                       reward: torch.Tensor | None = None, coins: torch.Tensor | None = None, obs: torch.Tensor | None = None, mask: torch.Tensor | None = None):

@@ -47,7 +47,9 @@ def test_bulk_solutions_equal_oracle_and_single_reads(name, inv):
 
 @pytest.mark.parametrize("tile", [16, 32])
 @pytest.mark.parametrize("name,inv,B,T", [("C3_clifford8_full", False, 333, 70), ("C2_lf8_line", True, 64, 33), ("C4_pauli10_line", False, 97, 40),
-                                          ("C5_perm27_heavyhex", False, 1, 5)])
+                                          ("C5_perm27_heavyhex", False, 1, 5),
+                                          # >= 1 MB of actions: the host form stages them through the copy engine in flagged chunks (ragged rows)
+                                          ("C3_clifford8_full", False, 16391, 70), ("C2_lf8_line", True, 32773, 40)])
 def test_packed_wire_format_equals_plain_replay(name, inv, B, T, tile):
     """uint8 actions / transposed flag bit planes carry exactly what int32 actions / uint8 flags carry (device and pinned-host forms)."""
     from qiskit_gym_b200 import BatchedEnv
@@ -90,6 +92,14 @@ def test_packed_wire_format_equals_plain_replay(name, inv, B, T, tile):
     rew3 = torch.zeros_like(rew); h_d[:] = 0
     env.replay_host_packed(h_a, h_d, None, reward_dev=rew3, coins=h_c)
     assert torch.equal(rew3.view(torch.int32), rew.view(torch.int32)) and np.array_equal(env.unpack_flag_bits(h_d, B), d)
+    # two episodes in flight (qg_replay_host_packed_async), each with its own output buffers
+    h_r2 = env.host_buffer((T, B), np.float32); h_d2 = env.host_buffer((tiles, T), np.uint32)
+    h_r[:] = 0; h_d[:] = 0; h_r2[:] = 0; h_d2[:] = 0
+    env.restore(); env.replay_host_packed(h_a, h_d, None, reward=h_r, coins=h_c, sync=False)
+    env.restore(); env.replay_host_packed(h_a, h_d2, None, reward=h_r2, coins=h_c, sync=False)
+    torch.cuda.synchronize()
+    for hr, hd in ((h_r, h_d), (h_r2, h_d2)):
+        assert np.array_equal(hr.view(np.uint32), rew.cpu().numpy().view(np.uint32)) and np.array_equal(env.unpack_flag_bits(hd, B), d)
     # pageable memory is refused, loudly
     with pytest.raises(ValueError):
         env.replay_host_packed(np.zeros((T, B), np.uint8), np.zeros((tiles, T), np.uint32))
