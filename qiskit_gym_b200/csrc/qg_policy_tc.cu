@@ -56,6 +56,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         " bra TC_WAIT_LOOP;\n"
         "TC_WAIT_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#ifdef QG_TC_PROBE           // tools build: cycles the fused kernel's MMA-issuing thread and its epilogue warp 2 spend per class of work (qg_policy_tc_debug_read*)
+__device__ long long g_tc_wait[160 * 8];     // waits on d1_empty, full (layer 1), a0_full, d2_empty, act_full (layer 2), full (layers 2 / 3), act_full (layer 3); total
+__device__ long long g_tc_epi[160 * 8];      // waits d1_full, act_empty; convert (layer 1); wait d2_full; layer-2 pieces; head wait; head (with its wait); total
+#define TC_MMA_WAIT(cls, bar, par) do { const long long _t0 = clock64(); mbar_wait(bar, par); tcw[cls] += clock64() - _t0; } while (0)
+#define TC_EPI(cls, stmt) do { const long long _t0 = clock64(); stmt; tce[cls] += clock64() - _t0; } while (0)
+#else
+#define TC_MMA_WAIT(cls, bar, par) mbar_wait(bar, par)
+#define TC_EPI(cls, stmt) do { stmt; } while (0)
+#endif
 __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes),
                  "r"(smem_u32(bar)) : "memory");
@@ -318,7 +327,8 @@ struct FusedArgs {
 constexpr int kFusedThreads = 384;        // loader, MMA, 8 epilogue warps, 2 observation-tile producer warps
 constexpr uint32_t kRingStage = 64 * 1024, kActBytes = 64 * 1024;
 constexpr uint32_t kFusedBias = (512 + 256 + 128) * 4;        // the three bias vectors, staged once per CTA (NC <= 4, C_pad <= 256, H <= 128)
-constexpr uint32_t kFusedSmem = 2 * kRingStage + kActBytes + 256 + kFusedBias;
+constexpr uint32_t kFusedRed = 4 * 128 * 4;                   // the head's partial row maxima / sums of the two warps of a lane quarter
+constexpr uint32_t kFusedSmem = 2 * kRingStage + kActBytes + 256 + kFusedBias + kFusedRed;
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void epilogue8_sync() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void epilogue4_sync() { asm volatile("bar.sync 3, 128;\n" ::: "memory"); }
@@ -341,6 +351,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
     float* const sb1 = reinterpret_cast<float*>(act + kActBytes + 256);       // biases in shared memory: the epilogue reads them with broadcast
     float* const sb2 = sb1 + 512;                                              // 16-byte loads instead of one global load per column (those
     float* const sb3 = sb2 + 256;                                              // were the epilogue's top stall: long_scoreboard, ncu r2_v11)
+    float* const red_max = sb3 + 128;                                          // [2][128]
+    float* const red_sum = red_max + 2 * kM;                                   // [2][128]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int halves = (a.C_pad + 127) / 128;           // D2 leaves in 128-column pieces
 
@@ -400,6 +412,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+#ifdef QG_TC_PROBE
+            long long tcw[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tc_t0 = clock64();
+#endif
             uint32_t n_d1e[2] = {0, 0}, n_actf[2] = {0, 0}, n_d2e = 0, n_a0[2] = {0, 0};  // waits done so far on d1_empty[b], act_full[j], d2_empty, a0_full[s]
             const uint32_t lbo128 = 128 * 16, sbo = 128;
             const uint32_t id1 = instr_desc(128), id2 = instr_desc(a.C_pad), id3 = instr_desc(a.H);
@@ -411,12 +426,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                     if (c < a.NC) {
                         // layer 1, chunk c -> D1[c & 1]
                         const int b = c & 1;
-                        mbar_wait(d1_empty + b, (n_d1e[b] & 1u) ^ 1u); ++n_d1e[b];
+                        TC_MMA_WAIT(0, d1_empty + b, (n_d1e[b] & 1u) ^ 1u); ++n_d1e[b];
                         tc_fence_after();
                         const uint32_t d = tmem_base + (uint32_t)b * 128;
                         for (int kb = 0; kb < a.Kb0; ++kb) {
-                            mbar_wait(full + stage, phase);
-                            mbar_wait(a0_full + stage, n_a0[stage] & 1u); ++n_a0[stage];
+                            TC_MMA_WAIT(1, full + stage, phase);
+                            TC_MMA_WAIT(2, a0_full + stage, n_a0[stage] & 1u); ++n_a0[stage];
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
 #pragma unroll
@@ -432,11 +447,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                     }
                     if (c > 0) {
                         // layer 2 over the two K blocks of chunk c - 1 (the epilogue's halves in the activation buffer) -> D2
-                        if (c == 1) { mbar_wait(d2_empty, (n_d2e & 1u) ^ 1u); ++n_d2e; }
+                        if (c == 1) { TC_MMA_WAIT(3, d2_empty, (n_d2e & 1u) ^ 1u); ++n_d2e; }
                         const uint32_t d = tmem_base + 256;
                         for (int j = 0; j < 2; ++j) {
-                            mbar_wait(act_full + j, n_actf[j] & 1u); ++n_actf[j];
-                            mbar_wait(full + stage, phase);
+                            TC_MMA_WAIT(4, act_full + j, n_actf[j] & 1u); ++n_actf[j];
+                            TC_MMA_WAIT(5, full + stage, phase);
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
                             const uint32_t a_hi = act_u + (uint32_t)j * 16384, a_lo = act_u + 32768 + (uint32_t)j * 16384;
@@ -457,14 +472,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                 // the head: layer 3 over the halves of D2 as they come back through the activation buffer -> the D1 buffer whose turn it is
                 {
                     const int b = a.NC & 1;
-                    mbar_wait(d1_empty + b, (n_d1e[b] & 1u) ^ 1u); ++n_d1e[b];
+                    TC_MMA_WAIT(0, d1_empty + b, (n_d1e[b] & 1u) ^ 1u); ++n_d1e[b];
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)b * 128;
                     for (int h = 0; h < halves; ++h) {
                         const int kbs = min(2, a.Kb3 - 2 * h);
                         for (int j = 0; j < kbs; ++j) {
-                            mbar_wait(act_full + j, n_actf[j] & 1u); ++n_actf[j];
-                            mbar_wait(full + stage, phase);
+                            TC_MMA_WAIT(6, act_full + j, n_actf[j] & 1u); ++n_actf[j];
+                            TC_MMA_WAIT(5, full + stage, phase);
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
                             const uint32_t a_hi = act_u + (uint32_t)j * 16384, a_lo = act_u + 32768 + (uint32_t)j * 16384;
@@ -483,6 +498,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                     umma_commit(d1_full + b);
                 }
             }
+#ifdef QG_TC_PROBE
+            tcw[7] = clock64() - tc_t0;
+            if (blockIdx.x < 160) for (int i = 0; i < 8; ++i) g_tc_wait[blockIdx.x * 8 + i] = tcw[i];
+#endif
         }
     } else if (warp >= 10) {
         // ===== observation-tile producers: follow the loader's stage sequence; for every layer-1 stage write rows' 64 entries of K block kb =====
@@ -536,6 +555,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         // with hsel = 0 converts columns 0..63 of a 128-column piece (K block 0 of the buffer), the other columns 64..127 (K block 1) =====
         const int q = warp & 3, hsel = (warp - 2) >> 2, row = q * 32 + lane;
         uint32_t n_d1f[2] = {0, 0}, n_acte = 0, n_d2f = 0;
+#ifdef QG_TC_PROBE
+        long long tce[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tce_t0 = clock64();
+#endif
         const uint32_t lane_base = ((uint32_t)(q * 32) << 16);
         // 64 accumulator columns starting at tensor-memory column `tcol` -> + bias, ReLU, hi / lo halves -> K block `hsel` of the buffer.
         // (Tried: converting into 64 registers before waiting for act_empty, so that only the shared-memory stores sit between act_empty
@@ -575,16 +597,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
             for (int c = 0; c < a.NC; ++c) {
                 const int b = c & 1;
-                mbar_wait(d1_full + b, n_d1f[b] & 1u); ++n_d1f[b];
-                mbar_wait(act_empty + hsel, (n_acte & 1u) ^ 1u); ++n_acte;   // the previous chunk's layer-2 products have read this K block
+                TC_EPI(0, mbar_wait(d1_full + b, n_d1f[b] & 1u)); ++n_d1f[b];
+                TC_EPI(1, mbar_wait(act_empty + hsel, (n_acte & 1u) ^ 1u)); ++n_acte;   // the previous chunk's layer-2 products have read this K block
                 tc_fence_after();
-                convert64((uint32_t)b * 128 + (uint32_t)hsel * 64, sb1 + c * 128 + hsel * 64);
+                TC_EPI(2, convert64((uint32_t)b * 128 + (uint32_t)hsel * 64, sb1 + c * 128 + hsel * 64);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d1_empty + b);
-                publish();
+                publish());
             }
-            mbar_wait(d2_full, n_d2f & 1u); ++n_d2f;
+            TC_EPI(3, mbar_wait(d2_full, n_d2f & 1u)); ++n_d2f;
+#ifdef QG_TC_PROBE
+            const long long tce_t4 = clock64();
+#endif
             for (int h = 0; h < halves; ++h) {
                 const bool mine = h * 128 + hsel * 64 < a.C_pad;       // (a K block past C_pad does not exist: the MMA warp does not wait for it)
                 if (mine) { mbar_wait(act_empty + hsel, (n_acte & 1u) ^ 1u); ++n_acte; }
@@ -593,67 +618,108 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                 if (h == halves - 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(d2_empty); }
                 if (mine) publish();
             }
-            // the head's accumulator
+#ifdef QG_TC_PROBE
+            tce[4] += clock64() - tce_t4;
+            const long long tce_t6 = clock64();
+#endif
+            // the head's accumulator.  All 8 epilogue warps share it: of the two warps of a tensor-memory lane quarter the one with hsel = 0 takes
+            // the head's columns below `split`, the other the rest (measured with four warps holding whole rows — 128 live registers per thread,
+            // a 128-entry predicated soft-max loop, 8-way bank conflicts on a row stride of A floats: 17 us of a tile's 30, the MMA thread idle
+            // behind it; profiles/r2_v34_tc_probe.json).  The pair's partial maxima / sums meet in shared memory; the staging tile has an odd
+            // row stride and leaves row by row, coalesced.
             {
                 const int b = a.NC & 1;
-                mbar_wait(d1_full + b, n_d1f[b] & 1u); ++n_d1f[b];
+                TC_EPI(5, mbar_wait(d1_full + b, n_d1f[b] & 1u)); ++n_d1f[b];
                 tc_fence_after();
                 const int A = a.num_actions;
                 const long long grow = (long long)mt * kM + row;
-                float x[kMaxNT];
-                if (hsel == 0) {
+                const int split = ((a.H + 31) / 32) * 16;             // a multiple of 16 (tcgen05.ld width), <= 64
+                const int col0 = hsel ? split : 0, ncols = hsel ? a.H - split : split;
+                float x[64];
 #pragma unroll
-                    for (int c = 0; c < kMaxNT / 16; ++c) {
-                        if (c * 16 < a.H) {
-                            uint32_t v[16];
-                            tmem_ld16(tmem_base + lane_base + (uint32_t)b * 128 + (uint32_t)(c * 16), v);
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 16 < ncols) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + lane_base + (uint32_t)b * 128 + (uint32_t)(col0 + c * 16), v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) + sb3[c * 16 + i];
-                        }
+                        for (int i = 0; i < 16; ++i) x[c * 16 + i] = __uint_as_float(v[i]) + sb3[col0 + c * 16 + i];
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d1_empty + b);             // (all 8 warps arrive: the barrier's count is the same for every use)
-                if (hsel == 0) {
-                    // the activation buffer is idle until the next tile's first chunk (these same warps write it): it is the staging tile
-                    if (a.has_value && a.values && grow < a.batch) {
-                        float val = 0.0f;
+                const int na = min(max(A - col0, 0), ncols);          // this warp's action columns: x[0 .. na)
+                if (a.has_value && a.values && grow < a.batch && A >= col0 && A < col0 + ncols) {
+                    float val = 0.0f;
 #pragma unroll
-                        for (int n = 0; n < kMaxNT; ++n) if (n == A) val = x[n];
-                        a.values[grow] = val;
-                    }
-                    float* const staging = reinterpret_cast<float*>(act);
-                    const long long rows_left = a.batch - (long long)mt * kM;
-                    const int nrows = rows_left < kM ? (int)rows_left : kM;
-                    float* const srow = staging + (size_t)row * A;
-                    auto flush = [&](float* out) {
-                        epilogue4_sync();
-                        float* dst = out + (size_t)mt * kM * A;
-                        const int total = nrows * A;
-                        for (int i = row; i < total; i += 128) dst[i] = staging[i];
-                        epilogue4_sync();
-                    };
-                    if (a.logits) {
-#pragma unroll
-                        for (int n = 0; n < kMaxNT; ++n) if (n < A) srow[n] = x[n];
-                        flush(a.logits);
-                    }
-                    if (a.probs) {
-                        float mx = -INFINITY, sum = 0.0f;
-#pragma unroll
-                        for (int n = 0; n < kMaxNT; ++n) if (n < A) mx = fmaxf(mx, x[n]);
-#pragma unroll
-                        for (int n = 0; n < kMaxNT; ++n) if (n < A) { x[n] = expf(x[n] - mx); sum += x[n]; }
-                        const float inv = 1.0f / sum;
-#pragma unroll
-                        for (int n = 0; n < kMaxNT; ++n) if (n < A) srow[n] = x[n] * inv;
-                        flush(a.probs);
-                    }
+                    for (int n = 0; n < 64; ++n) if (n == A - col0) val = x[n];
+                    a.values[grow] = val;
                 }
-                epilogue8_sync();      // the other four warps must not start the next tile's first chunk in the buffer while it is the staging tile
+                // the activation buffer is idle until the next tile's first chunk (these same warps write it): it is the staging tile
+                float* const staging = reinterpret_cast<float*>(act);
+                // row stride of the staging tile: A % 4 == 0 -> 4 (mod 8) floats, so that the 16-byte stores of the 8 lanes of a quarter-warp
+                // (8 rows) cover all 32 banks, and rows leave as float4; otherwise odd, scalar stores
+                const bool vec = (A & 3) == 0;
+                const int SA = vec ? A + ((12 - (A & 7)) & 7) : (A | 1);
+                const long long rows_left = a.batch - (long long)mt * kM;
+                const int nrows = rows_left < kM ? (int)rows_left : kM;
+                float* const srow = staging + (size_t)row * SA + col0;
+                const int et = threadIdx.x - 64;                      // 0..255 over the 8 epilogue warps
+                auto stage_row = [&](float scale) {
+                    if (vec) {
+#pragma unroll
+                        for (int n = 0; n < 64; n += 4) if (n < na) *reinterpret_cast<float4*>(srow + n) = make_float4(x[n] * scale, x[n + 1] * scale, x[n + 2] * scale, x[n + 3] * scale);
+                    } else {
+#pragma unroll
+                        for (int n = 0; n < 64; ++n) if (n < na) srow[n] = x[n] * scale;
+                    }
+                };
+                auto flush = [&](float* out) {                        // staging [nrows][SA] -> out rows mt * 128 .. (contiguous: row stride A), coalesced
+                    epilogue8_sync();
+                    float* dst = out + (size_t)mt * kM * A;
+                    if (vec) {
+                        const int a4 = A >> 2, total = nrows * a4;
+                        for (int i = et; i < total; i += 256) {
+                            const int r = i / a4, c4 = i - r * a4;
+                            reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(staging + (size_t)r * SA + 4 * c4);
+                        }
+                    } else {
+                        for (int r = et >> 5; r < nrows; r += 8) for (int cc = lane; cc < A; cc += 32) dst[(size_t)r * A + cc] = staging[(size_t)r * SA + cc];
+                    }
+                    epilogue8_sync();
+                };
+                if (a.logits) {
+                    stage_row(1.0f);
+                    flush(a.logits);
+                }
+                if (a.probs) {
+                    float mx = -INFINITY, sum = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < 64; ++n) if (n < na) mx = fmaxf(mx, x[n]);
+                    red_max[hsel * kM + row] = mx;
+                    epilogue8_sync();
+                    mx = fmaxf(red_max[row], red_max[kM + row]);
+#pragma unroll
+#ifdef QG_TC_FASTEXP         // (tools A/B build: ex2.approx instead of the full-precision expf)
+                    for (int n = 0; n < 64; ++n) if (n < na) { x[n] = __expf(x[n] - mx); sum += x[n]; }
+#else
+                    for (int n = 0; n < 64; ++n) if (n < na) { x[n] = expf(x[n] - mx); sum += x[n]; }
+#endif
+                    red_sum[hsel * kM + row] = sum;
+                    epilogue8_sync();
+                    stage_row(1.0f / (red_sum[row] + red_sum[kM + row]));
+                    flush(a.probs);
+                }
+                epilogue8_sync();      // (no warp starts the next tile's first chunk in the buffer while it is the staging tile)
             }
+#ifdef QG_TC_PROBE
+            tce[6] += clock64() - tce_t6;
+#endif
         }
+#ifdef QG_TC_PROBE
+        tce[7] = clock64() - tce_t0;
+        if (warp == 2 && lane == 0 && blockIdx.x < 160) for (int i = 0; i < 8; ++i) g_tc_epi[blockIdx.x * 8 + i] = tce[i];
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -895,3 +961,13 @@ int qg_policy_tc_forward_bits(qg_policy_tc* p, const uint32_t* obs_bits_dev, int
 }
 
 }  // extern "C"
+
+#ifdef QG_TC_PROBE
+// tools build: [160 CTAs][8] cycle counters of the last fused launch (see g_tc_wait / g_tc_epi)
+extern "C" __attribute__((visibility("default"))) int qg_policy_tc_debug_read(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, qg::tc::g_tc_wait, sizeof(long long) * 160 * 8) == cudaSuccess ? 0 : -1;
+}
+extern "C" __attribute__((visibility("default"))) int qg_policy_tc_debug_read_epilogue(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, qg::tc::g_tc_epi, sizeof(long long) * 160 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif

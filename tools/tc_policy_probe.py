@@ -72,3 +72,25 @@ torch.backends.cuda.matmul.allow_tf32 = False
 flops = 2 * B * (256 * 512 * 2 + 512 * 256 * 3 + 256 * 80 * 3)
 out["tc_tflops_f16_products"] = flops / (out["tc_us"] * 1e-6) / 1e12
 print(json.dumps(out))
+
+# tools build with -DQG_TC_PROBE: where the MMA-issuing threads wait
+try:
+    import ctypes as C
+    from qiskit_gym_b200._lib import lib
+    L = lib()
+    if hasattr(L, "qg_policy_tc_debug_read"):
+        tcp.forward_bits(bits, probs=probs, values=values); torch.cuda.synchronize()
+        buf = (C.c_longlong * (160 * 8))()
+        L.qg_policy_tc_debug_read(buf)
+        w = np.array(list(buf), dtype=np.float64).reshape(160, 8)[:148]
+        names = ["d1_empty", "full_l1", "a0_full", "d2_empty", "act_full_l2", "full_l23", "act_full_l3", "total"]
+        print(json.dumps({"mma_thread_wait_cycles_mean": {n: float(w[:, i].mean()) for i, n in enumerate(names)},
+                          "share_of_total": {n: float(w[:, i].mean() / w[:, 7].mean()) for i, n in enumerate(names)}}))
+        if hasattr(L, "qg_policy_tc_debug_read_epilogue"):
+            L.qg_policy_tc_debug_read_epilogue(buf)
+            w = np.array(list(buf), dtype=np.float64).reshape(160, 8)[:148]
+            names = ["wait_d1_full", "wait_act_empty", "convert_l1", "wait_d2_full", "l2_pieces", "head_wait", "head", "total"]
+            print(json.dumps({"epilogue_warp2_cycles_mean": {n: float(w[:, i].mean()) for i, n in enumerate(names)},
+                              "share_of_total": {n: float(w[:, i].mean() / w[:, 7].mean()) for i, n in enumerate(names)}}))
+except Exception as ex:  # noqa: BLE001
+    print("probe read failed:", ex, file=sys.stderr)
