@@ -82,6 +82,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// The same two for a whole converged warp: every lane runs the issue loop with warp-uniform operands and one elected lane (always the same
+// one for the full mask) issues.  Under `if (lane == 0)` the compiler cannot tell that one lane is active and wraps every tcgen05.mma in a loop
+// that broadcasts its operands into uniform registers (ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY): ~20 instructions and ~115 cycles per MMA in
+// the fused kernel, more than a 64-cycle layer-1 product takes on the tensor pipe (cuobjdump -sass, profiles/r2_v36_tc_probe.json).
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p, q;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " elect.sync _|q, 0xffffffff;\n"
+        " @q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n .reg .pred q;\n"
+        " elect.sync _|q, 0xffffffff;\n"
+        " @q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
@@ -410,7 +427,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        {   // (the whole warp: see umma_f16_w)
             uint32_t stage = 0, phase = 0;
 #ifdef QG_TC_PROBE
             long long tcw[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tc_t0 = clock64();
@@ -437,13 +454,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
 #pragma unroll
                             for (int k = 0; k < kKB / 16; ++k) {
                                 const uint64_t ad = smem_desc(sp + 2u * k * lbo128, lbo128, sbo);
-                                umma_f16(d, ad, smem_desc(sp + 16384 + 2u * k * lbo128, lbo128, sbo), id1, (kb | k) ? 1u : 0u);
-                                umma_f16(d, ad, smem_desc(sp + 32768 + 2u * k * lbo128, lbo128, sbo), id1, 1u);
+                                umma_f16_w(d, ad, smem_desc(sp + 16384 + 2u * k * lbo128, lbo128, sbo), id1, (kb | k) ? 1u : 0u);
+                                umma_f16_w(d, ad, smem_desc(sp + 32768 + 2u * k * lbo128, lbo128, sbo), id1, 1u);
                             }
-                            umma_commit(empty + stage);
+                            umma_commit_w(empty + stage);
                             next();
                         }
-                        umma_commit(d1_full + b);
+                        umma_commit_w(d1_full + b);
                     }
                     if (c > 0) {
                         // layer 2 over the two K blocks of chunk c - 1 (the epilogue's halves in the activation buffer) -> D2
@@ -458,17 +475,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
 #pragma unroll
                             for (int k = 0; k < kKB / 16; ++k) {
                                 const uint64_t ah = smem_desc(a_hi + 2u * k * lbo128, lbo128, sbo), bh = smem_desc(sp + 2u * k * lbo2, lbo2, sbo);
-                                umma_f16(d, ah, bh, id2, (c > 1 || j || k) ? 1u : 0u);
-                                umma_f16(d, ah, smem_desc(sp + 32768 + 2u * k * lbo2, lbo2, sbo), id2, 1u);
-                                umma_f16(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id2, 1u);
+                                umma_f16_w(d, ah, bh, id2, (c > 1 || j || k) ? 1u : 0u);
+                                umma_f16_w(d, ah, smem_desc(sp + 32768 + 2u * k * lbo2, lbo2, sbo), id2, 1u);
+                                umma_f16_w(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id2, 1u);
                             }
-                            umma_commit(empty + stage);
-                            umma_commit(act_empty + j);              // this K block may be rewritten once these products have read it
+                            umma_commit_w(empty + stage);
+                            umma_commit_w(act_empty + j);              // this K block may be rewritten once these products have read it
                             next();
                         }
                     }
                 }
-                umma_commit(d2_full);
+                umma_commit_w(d2_full);
                 // the head: layer 3 over the halves of D2 as they come back through the activation buffer -> the D1 buffer whose turn it is
                 {
                     const int b = a.NC & 1;
@@ -486,21 +503,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
 #pragma unroll
                             for (int k = 0; k < kKB / 16; ++k) {
                                 const uint64_t ah = smem_desc(a_hi + 2u * k * lbo128, lbo128, sbo), bh = smem_desc(sp + 2u * k * lbo3, lbo3, sbo);
-                                umma_f16(d, ah, bh, id3, (h || j || k) ? 1u : 0u);
-                                umma_f16(d, ah, smem_desc(sp + 32768 + 2u * k * lbo3, lbo3, sbo), id3, 1u);
-                                umma_f16(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id3, 1u);
+                                umma_f16_w(d, ah, bh, id3, (h || j || k) ? 1u : 0u);
+                                umma_f16_w(d, ah, smem_desc(sp + 32768 + 2u * k * lbo3, lbo3, sbo), id3, 1u);
+                                umma_f16_w(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id3, 1u);
                             }
-                            umma_commit(empty + stage);
-                            umma_commit(act_empty + j);
+                            umma_commit_w(empty + stage);
+                            umma_commit_w(act_empty + j);
                             next();
                         }
                     }
-                    umma_commit(d1_full + b);
+                    umma_commit_w(d1_full + b);
                 }
             }
 #ifdef QG_TC_PROBE
             tcw[7] = clock64() - tc_t0;
-            if (blockIdx.x < 160) for (int i = 0; i < 8; ++i) g_tc_wait[blockIdx.x * 8 + i] = tcw[i];
+            if (lane == 0 && blockIdx.x < 160) for (int i = 0; i < 8; ++i) g_tc_wait[blockIdx.x * 8 + i] = tcw[i];
 #endif
         }
     } else if (warp >= 10) {
