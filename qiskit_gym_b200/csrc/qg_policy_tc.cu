@@ -93,6 +93,19 @@ __device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t adesc, uint
         " elect.sync _|q, 0xffffffff;\n"
         " @q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ... with the descriptors as their low words only (start address and leading byte offset; the high word — stride byte offset 128, version
+// 1 — is the same for every operand of the fused kernel): stepping to the next K = 16 slice is one 32-bit add per operand
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p, q;\n .reg .b32 hi;\n .reg .b64 ad, bd;\n"
+        " setp.ne.b32 p, %4, 0;\n"
+        " mov.u32 hi, 0x4008;\n"
+        " mov.b64 ad, {%1, hi};\n"
+        " mov.b64 bd, {%2, hi};\n"
+        " elect.sync _|q, 0xffffffff;\n"
+        " @q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %3, p;\n}\n" ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
     asm volatile(
         "{\n .reg .pred q;\n"
@@ -326,9 +339,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
 //   at a time, through the same buffer — into layer 3's A operand, and the head's accumulator takes the place of a D1 buffer.
 // Tensor memory: D1[0] cols 0..127, D1[1] cols 128..255, D2 cols 256..511.  Shared memory: 2 ring stages of 64 KB (weight tiles, and layer
 // 1's observation tiles) + the 64 KB activation buffer (which doubles as the output staging tile of the head).
-//   warp 0 loader, warp 1 MMA issuer, warps 2..9 epilogue (two warps per tensor-memory lane quarter, each converting half of the columns),
-//   warps 10..11 expand the packed observation bits of the CTA's 128 rows into layer 1's A tile of every layer-1 stage (0 / 1 as f16: one
-//   16-byte store per 8 entries) — no expansion pre-pass, no A tiles in global memory, a fifth less traffic into shared memory.
+//   warp 0 loader, warp 1 MMA issuer (the whole warp runs the issue loop, an elected lane issues: umma_f16_lo), warps 2..9 epilogue (two warps
+//   per tensor-memory lane quarter, each converting half of the columns; all eight share the head's soft-max), warps 10..13 expand the packed
+//   observation bits of the CTA's 128 rows (one row per thread, words requested one stage ahead) into layer 1's A tile of every layer-1 stage
+//   (0 / 1 as f16: one 16-byte store per 8 entries) — no expansion pre-pass, no A tiles in global memory, a fifth less traffic into shared memory.
+// Where the time goes (tools build -DQG_TC_PROBE, profiles/r2_v42_tc_probe.json; 65 536 rows = 512 tiles on 148 CTAs): the MMA-issuing thread
+// waits 9 % for layer 2's activation halves, 6 % each for layer 1's weights and observation tiles, 6 % for the head's input, 3 % for a free
+// accumulator; a CTA with 4 tiles sets the kernel's time while the mean is 3.46 (wave quantisation: 13 %).  Tried and measured slower: four
+// 32 KB half-K-block ring stages (126 vs 122 us), two activation buffers + three stages (138 us), a shared-memory byte table for the producers
+// (114 vs 100 us: its loads compete with the operand reads), converting a chunk into registers before its buffer is free (spills).
 struct FusedArgs {
     const uint32_t* bits;    // packed observations [batch][obs_words]: layer 1's A tiles are expanded from them inside the kernel
     int obs_words, obs_size;
@@ -341,7 +360,8 @@ struct FusedArgs {
     int Kb0, NC, C_pad, Kb3, H, m_tiles, num_actions, has_value;
     long long batch;
 };
-constexpr int kFusedThreads = 384;        // loader, MMA, 8 epilogue warps, 2 observation-tile producer warps
+constexpr int kProducerWarps = 4;         // observation-tile producers: one row per thread
+constexpr int kFusedThreads = 320 + 32 * kProducerWarps;        // loader, MMA, 8 epilogue warps, the producers
 constexpr uint32_t kRingStage = 64 * 1024, kActBytes = 64 * 1024;
 constexpr uint32_t kFusedBias = (512 + 256 + 128) * 4;        // the three bias vectors, staged once per CTA (NC <= 4, C_pad <= 256, H <= 128)
 constexpr uint32_t kFusedRed = 4 * 128 * 4;                   // the head's partial row maxima / sums of the two warps of a lane quarter
@@ -376,7 +396,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(d1_full + s, 1); mbar_init(d1_empty + s, 8); }
         mbar_init(d2_full, 1); mbar_init(d2_empty, 8);
-        for (int j = 0; j < 2; ++j) { mbar_init(act_full + j, 4); mbar_init(act_empty + j, 1); mbar_init(a0_full + j, 2); }
+        for (int j = 0; j < 2; ++j) { mbar_init(act_full + j, 4); mbar_init(act_empty + j, 1); mbar_init(a0_full + j, kProducerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -433,9 +453,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
             long long tcw[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long tc_t0 = clock64();
 #endif
             uint32_t n_d1e[2] = {0, 0}, n_actf[2] = {0, 0}, n_d2e = 0, n_a0[2] = {0, 0};  // waits done so far on d1_empty[b], act_full[j], d2_empty, a0_full[s]
-            const uint32_t lbo128 = 128 * 16, sbo = 128;
+            const uint32_t lbo128 = 128 * 16;
             const uint32_t id1 = instr_desc(128), id2 = instr_desc(a.C_pad), id3 = instr_desc(a.H);
             const uint32_t lbo2 = (uint32_t)a.C_pad * 16, lbo3 = (uint32_t)a.H * 16;
+            const uint32_t ks128 = 2u * lbo128 >> 4, ks2 = 2u * lbo2 >> 4, ks3 = 2u * lbo3 >> 4;    // descriptor step per K = 16 slice (two 8-wide k groups)
             const uint32_t act_u = smem_u32(act);
             auto next = [&]() { if (++stage == 2) { stage = 0; phase ^= 1u; } };
             for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
@@ -451,11 +472,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                             TC_MMA_WAIT(2, a0_full + stage, n_a0[stage] & 1u); ++n_a0[stage];
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
+                            const uint32_t a0 = desc_lo(sp, lbo128), b0 = desc_lo(sp + 16384, lbo128), b1 = desc_lo(sp + 32768, lbo128);
 #pragma unroll
                             for (int k = 0; k < kKB / 16; ++k) {
-                                const uint64_t ad = smem_desc(sp + 2u * k * lbo128, lbo128, sbo);
-                                umma_f16_w(d, ad, smem_desc(sp + 16384 + 2u * k * lbo128, lbo128, sbo), id1, (kb | k) ? 1u : 0u);
-                                umma_f16_w(d, ad, smem_desc(sp + 32768 + 2u * k * lbo128, lbo128, sbo), id1, 1u);
+                                umma_f16_lo(d, a0 + k * ks128, b0 + k * ks128, id1, (kb | k) ? 1u : 0u);
+                                umma_f16_lo(d, a0 + k * ks128, b1 + k * ks128, id1, 1u);
                             }
                             umma_commit_w(empty + stage);
                             next();
@@ -472,12 +493,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
                             const uint32_t a_hi = act_u + (uint32_t)j * 16384, a_lo = act_u + 32768 + (uint32_t)j * 16384;
+                            const uint32_t ah0 = desc_lo(a_hi, lbo128), al0 = desc_lo(a_lo, lbo128), bh0 = desc_lo(sp, lbo2), bl0 = desc_lo(sp + 32768, lbo2);
 #pragma unroll
                             for (int k = 0; k < kKB / 16; ++k) {
-                                const uint64_t ah = smem_desc(a_hi + 2u * k * lbo128, lbo128, sbo), bh = smem_desc(sp + 2u * k * lbo2, lbo2, sbo);
-                                umma_f16_w(d, ah, bh, id2, (c > 1 || j || k) ? 1u : 0u);
-                                umma_f16_w(d, ah, smem_desc(sp + 32768 + 2u * k * lbo2, lbo2, sbo), id2, 1u);
-                                umma_f16_w(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id2, 1u);
+                                umma_f16_lo(d, ah0 + k * ks128, bh0 + k * ks2, id2, (c > 1 || j || k) ? 1u : 0u);
+                                umma_f16_lo(d, ah0 + k * ks128, bl0 + k * ks2, id2, 1u);
+                                umma_f16_lo(d, al0 + k * ks128, bh0 + k * ks2, id2, 1u);
                             }
                             umma_commit_w(empty + stage);
                             umma_commit_w(act_empty + j);              // this K block may be rewritten once these products have read it
@@ -500,12 +521,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                             tc_fence_after();
                             const uint32_t sp = smem_u32(ring + stage * kRingStage);
                             const uint32_t a_hi = act_u + (uint32_t)j * 16384, a_lo = act_u + 32768 + (uint32_t)j * 16384;
+                            const uint32_t ah0 = desc_lo(a_hi, lbo128), al0 = desc_lo(a_lo, lbo128), bh0 = desc_lo(sp, lbo3), bl0 = desc_lo(sp + 32768, lbo3);
 #pragma unroll
                             for (int k = 0; k < kKB / 16; ++k) {
-                                const uint64_t ah = smem_desc(a_hi + 2u * k * lbo128, lbo128, sbo), bh = smem_desc(sp + 2u * k * lbo3, lbo3, sbo);
-                                umma_f16_w(d, ah, bh, id3, (h || j || k) ? 1u : 0u);
-                                umma_f16_w(d, ah, smem_desc(sp + 32768 + 2u * k * lbo3, lbo3, sbo), id3, 1u);
-                                umma_f16_w(d, smem_desc(a_lo + 2u * k * lbo128, lbo128, sbo), bh, id3, 1u);
+                                umma_f16_lo(d, ah0 + k * ks128, bh0 + k * ks3, id3, (h || j || k) ? 1u : 0u);
+                                umma_f16_lo(d, ah0 + k * ks128, bl0 + k * ks3, id3, 1u);
+                                umma_f16_lo(d, al0 + k * ks128, bh0 + k * ks3, id3, 1u);
                             }
                             umma_commit_w(empty + stage);
                             umma_commit_w(act_empty + j);
@@ -522,38 +543,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
         }
     } else if (warp >= 10) {
         // ===== observation-tile producers: follow the loader's stage sequence; for every layer-1 stage write rows' 64 entries of K block kb =====
-        const int t = threadIdx.x - 320;                 // 0..63: rows t and t + 64
+        const int row = threadIdx.x - 320;               // 0..127
         uint32_t stage = 0, phase = 0;
         auto next = [&]() { if (++stage == 2) { stage = 0; phase ^= 1u; } };
+        // the two observation words of K block kb of this thread's row, masked to the entries that exist.  They are requested one stage ahead:
+        // a stage's turn-around (stage free -> tile written) then holds no global-memory latency
+        auto load_words = [&](int mt, int kb, uint32_t (&w)[2]) {
+            const long long grow = (long long)mt * kM + row;
+            uint32_t w0 = 0, w1 = 0;
+            if (grow < a.batch) {
+                const uint32_t* src = a.bits + (size_t)grow * a.obs_words;
+                if (2 * kb < a.obs_words) w0 = __ldg(src + 2 * kb);
+                if (2 * kb + 1 < a.obs_words) w1 = __ldg(src + 2 * kb + 1);
+                const int left = a.obs_size - kb * 64;           // entries of this K block that exist
+                if (left < 32) w0 &= left > 0 ? ((1u << left) - 1u) : 0u;
+                if (left < 64) w1 &= left > 32 ? ((1u << (left - 32)) - 1u) : 0u;
+            }
+            w[0] = w0; w[1] = w1;
+        };
         for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+            uint32_t wn[2];
+            load_words(mt, 0, wn);
             for (int c = 0; c <= a.NC; ++c) {
                 if (c < a.NC) {
                     for (int kb = 0; kb < a.Kb0; ++kb) {
+                        const uint32_t wc[2] = {wn[0], wn[1]};
+                        load_words(mt, kb + 1 < a.Kb0 ? kb + 1 : 0, wn);          // (the next chunk starts over at K block 0)
                         mbar_wait(empty + stage, phase ^ 1u);            // the products that read this stage's previous contents are done
                         uint8_t* const tile = ring + stage * kRingStage;
 #pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            const int row = t + rr * 64;
-                            const long long grow = (long long)mt * kM + row;
-                            uint32_t w0 = 0, w1 = 0;
-                            if (grow < a.batch) {
-                                const uint32_t* src = a.bits + (size_t)grow * a.obs_words;
-                                if (2 * kb < a.obs_words) w0 = src[2 * kb];
-                                if (2 * kb + 1 < a.obs_words) w1 = src[2 * kb + 1];
-                                const int left = a.obs_size - kb * 64;           // entries of this K block that exist
-                                if (left < 32) w0 &= left > 0 ? ((1u << left) - 1u) : 0u;
-                                if (left < 64) w1 &= left > 32 ? ((1u << (left - 32)) - 1u) : 0u;
-                            }
-#pragma unroll
-                            for (int ch = 0; ch < 8; ++ch) {
-                                const uint32_t b = ((ch < 4 ? w0 : w1) >> ((ch & 3) * 8)) & 0xFFu;
-                                uint4 o;
-                                o.x = ((b & 1u) ? 0x3C00u : 0u) | ((b & 2u) ? 0x3C000000u : 0u);
-                                o.y = ((b & 4u) ? 0x3C00u : 0u) | ((b & 8u) ? 0x3C000000u : 0u);
-                                o.z = ((b & 16u) ? 0x3C00u : 0u) | ((b & 32u) ? 0x3C000000u : 0u);
-                                o.w = ((b & 64u) ? 0x3C00u : 0u) | ((b & 128u) ? 0x3C000000u : 0u);
-                                *reinterpret_cast<uint4*>(tile + ((size_t)ch * kM + row) * 16) = o;
-                            }
+                        for (int ch = 0; ch < 8; ++ch) {
+                            // 8 entries as f16 0 / 1.  (A 256-entry shared-memory table instead of these selects was measured: 114 instead of
+                            // 100 us per forward — its loads compete with the tensor core's operand reads for the shared-memory bandwidth.)
+                            const uint32_t b = (wc[ch >> 2] >> ((ch & 3) * 8)) & 0xFFu;
+                            uint4 o;
+                            o.x = ((b & 1u) ? 0x3C00u : 0u) | ((b & 2u) ? 0x3C000000u : 0u);
+                            o.y = ((b & 4u) ? 0x3C00u : 0u) | ((b & 8u) ? 0x3C000000u : 0u);
+                            o.z = ((b & 16u) ? 0x3C00u : 0u) | ((b & 32u) ? 0x3C000000u : 0u);
+                            o.w = ((b & 64u) ? 0x3C00u : 0u) | ((b & 128u) ? 0x3C000000u : 0u);
+                            *reinterpret_cast<uint4*>(tile + ((size_t)ch * kM + row) * 16) = o;
                         }
                         fence_async_smem();
                         __syncwarp();
@@ -705,9 +733,19 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
                     }
                     epilogue8_sync();
                 };
+                // A % 4 == 0: every thread writes its columns of its row straight from registers as float4 (a row is A contiguous floats; the 32
+                // rows of a warp make 32 half-used sectors per store, which L2 merges) — staging tile, two block barriers and the copy loop cost
+                // more than the uncoalesced stores (profiles/r2_v40_tc_probe.json -> r2_v41)
+                auto store_row = [&](float* out, float scale) {
+                    if (grow < a.batch) {
+                        float* drow = out + (size_t)grow * A + col0;
+#pragma unroll
+                        for (int n = 0; n < 64; n += 4) if (n < na) *reinterpret_cast<float4*>(drow + n) = make_float4(x[n] * scale, x[n + 1] * scale, x[n + 2] * scale, x[n + 3] * scale);
+                    }
+                };
                 if (a.logits) {
-                    stage_row(1.0f);
-                    flush(a.logits);
+                    if (vec) store_row(a.logits, 1.0f);
+                    else { stage_row(1.0f); flush(a.logits); }
                 }
                 if (a.probs) {
                     float mx = -INFINITY, sum = 0.0f;
@@ -724,10 +762,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_tc_fused3(const __grid_con
 #endif
                     red_sum[hsel * kM + row] = sum;
                     epilogue8_sync();
-                    stage_row(1.0f / (red_sum[row] + red_sum[kM + row]));
-                    flush(a.probs);
+                    const float inv = 1.0f / (red_sum[row] + red_sum[kM + row]);
+                    if (vec) store_row(a.probs, inv);
+                    else { stage_row(inv); flush(a.probs); }
                 }
-                epilogue8_sync();      // (no warp starts the next tile's first chunk in the buffer while it is the staging tile)
+                if (!vec) epilogue8_sync();      // (no warp starts the next tile's first chunk in the buffer while it is the staging tile)
             }
 #ifdef QG_TC_PROBE
             tce[6] += clock64() - tce_t6;
