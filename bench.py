@@ -36,14 +36,14 @@ STATE_BYTES = {"C1_perm_grid3": 104, "C2_lf8_line": 96, "C3_clifford8_full": 144
 # dram__bytes_read.sum + dram__bytes_write.sum of one replay launch, from the committed ncu --set full capture (profiles/), keyed by
 # (config, envs per GPU, env-steps per launch); None where no capture exists.
 TRAFFIC_BYTES_PER_LAUNCH = {
-    # profiles/r2_v10_<config>_ncu.txt (ncu --set full of one k_step nsteps=128 replay launch per config, 65 536 envs, this round's kernels):
-    # dram__bytes_read.sum + dram__bytes_write.sum.  The launch's last ~0.1-0.2 GB of dirty lines are still in the 126 MB L2 when the counters
-    # stop, hence slightly below the algorithmic bytes: no wasted re-reads.
-    ("C1_perm_grid3", 65536, 128): 38867968 + 2834811000,
-    ("C2_lf8_line", 65536, 128): 38087936 + 2293844000,
-    ("C3_clifford8_full", 65536, 128): 40816640 + 9018149000,
-    ("C4_pauli10_line", 65536, 128): 46079232 + 17496646000,
-    ("C5_perm27_heavyhex", 65536, 128): 44755712 + 24439950000,
+    # profiles/r2_v44_<config>_ncu.txt (ncu --set full of one k_step nsteps=128 replay launch per config, 65 536 envs, this round's final kernels,
+    # one observation slab per step): dram__bytes_read.sum + dram__bytes_write.sum.  Within 1 % of the algorithmic bytes (the launch's last dirty
+    # lines are still in the 126 MB L2 when the counters stop): no wasted re-reads, and nothing absorbed by L2 either.
+    ("C1_perm_grid3", 65536, 128): 38864896 + 2847544000,
+    ("C2_lf8_line", 65536, 128): 38106880 + 2293921000,
+    ("C3_clifford8_full", 65536, 128): 40289792 + 9224168000,
+    ("C4_pauli10_line", 65536, 128): 46339840 + 17687305000,
+    ("C5_perm27_heavyhex", 65536, 128): 44766720 + 24731291000,
 }
 METRIC = "batched env-steps/sec (CliffordGym 8q all-to-all {H,S,CX})"
 UNIT = "env-steps/s"

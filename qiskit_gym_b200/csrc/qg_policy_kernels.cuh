@@ -425,6 +425,14 @@ __device__ __forceinline__ void consume_layer_narrow(const PolicyDev& p, int l, 
     }
 }
 
+#ifdef QG_SEARCH_PROBE       // tools build: cycles thread 0 of CTA 0 spends per part of a decision of the one-launch search (qg_search_debug_read)
+static __device__ long long g_search_prof[16];      // (one copy per translation unit; printed by k_search_fused) [0] observation words, [1 + l] layer l (with its barrier), [9] soft-max, [10] env step, [11] decisions, [12] total
+#define QG_SP_T0() const long long _sp0 = clock64()
+#define QG_SP_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_search_prof[i] += clock64() - _sp0; } while (0)
+#else
+#define QG_SP_T0() do { } while (0)
+#define QG_SP_ADD(i) do { } while (0)
+#endif
 __device__ __forceinline__ void policy_init_barriers(const PolicySmem& ps, int tid) {
     if (tid == 0) {
         for (int s = 0; s < kPolStages; ++s) { mbar_init(ps.full + s, 1); mbar_init(ps.empty + s, kPolConsumers / 32); }
@@ -479,6 +487,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
 
     // ---- 1. consumers: the rows' packed observations into shared memory
     const bool fresh = acc0 == nullptr || pass == 0;
+    { QG_SP_T0();
     if (bits) {
         for (int i = tid; i < kPolRows * p.obs_words; i += kPolConsumers) {
             const int r = i / p.obs_words, w = i - r * p.obs_words;
@@ -487,12 +496,14 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
             rowbits[i] = word;
         }
     }
+    QG_SP_ADD(0); }
 
     // ---- 2. layers
     float* src = act1;
     float* dst = act0;
     for (int l = 0; l < p.num_layers; ++l) {
         const int ni = (p.width[l] + kPolHalf - 1) / kPolHalf;
+        QG_SP_T0();
         if (l == 0) {
             layer0_fixed(p, ps, dst, acc0, fresh, p.num_layers > 1, tid, bits ? nullptr : stream, stream_rows);
         } else if (p.width[l] <= 64) {
@@ -509,11 +520,13 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
             }
         }
         consumers_sync();
+        QG_SP_ADD(1 + l);
         src = dst;
         dst = (dst == act0) ? act1 : act0;
     }
 
     // ---- 3. softmax over the action logits, warp r <-> row r -------------------------------------------------------------
+    QG_SP_T0();
     if (warp < kPolRows) {
         const int64_t row = row0 + warp;
         if (row < B) {
@@ -535,6 +548,7 @@ __device__ __forceinline__ void policy_forward_rows(const PolicyDev& p, const Po
             }
         }
     }
+    QG_SP_ADD(9);
 }
 
 }  // namespace qg

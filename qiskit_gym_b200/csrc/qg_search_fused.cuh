@@ -8,6 +8,7 @@
 // (L2) between decisions and are only updated with the observation entries the step changed (layer0_fixed); since that sum is order
 // independent, the decisions are bit for bit those of the two-kernel path, which sums every set entry afresh.
 #pragma once
+#include <cstdio>
 #include "qg_kernels.cuh"
 #include "qg_policy_kernels.cuh"
 
@@ -35,18 +36,34 @@ __global__ void __launch_bounds__(kPolThreads) k_search_fused(const __grid_const
     if (tid < kPolRows) s_ret[tid] = tid < cnt ? c.ret[row0 + tid] : 0.0f;
     __syncthreads();
     int G = 0, it = 0;
+#ifdef QG_SEARCH_PROBE
+    const long long sp_total0 = clock64();
+#endif
     for (; it < max_decisions; ++it) {
         // decision `it`: the first one reads the packed observations qg_observe_bits left in global memory, the later ones read the
         // step's own bit stream in shared memory; the action weights stay in shared memory; the env records stay in the step's region
         policy_forward_rows(p, ps, it == 0 ? first_bits : nullptr, row0, c.B, s_probs, nullptr, G, it, 0, acc0, obs_stream, cnt);
         __syncthreads();
+        { QG_SP_T0();
         if (warp == 0) {
             const uint32_t en = step_tile<KIND, MODE_SEARCH, 0>(c, a, wbase, nullptr, lane, row0, cnt, it > 0, s_probs, true, s_ret);
             if (lane == 0) s_active = en;
         }
         __syncthreads();                           // next observations in the step's stream, s_active set
+        QG_SP_ADD(10); }
+#ifdef QG_SEARCH_PROBE
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_search_prof[11] += 1;
+#endif
         if (s_active == 0) break;                  // every rollout of this CTA is final
     }
+#ifdef QG_SEARCH_PROBE
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        g_search_prof[12] += clock64() - sp_total0;
+        printf("SEARCHPROF obs %lld l0 %lld l1 %lld l2 %lld l3 %lld softmax %lld step %lld decisions %lld total %lld\n", g_search_prof[0], g_search_prof[1], g_search_prof[2],
+               g_search_prof[3], g_search_prof[4], g_search_prof[9], g_search_prof[10], g_search_prof[11], g_search_prof[12]);
+        for (int i = 0; i < 16; ++i) g_search_prof[i] = 0;
+    }
+#endif
     if (warp == 0) {                               // what stayed in shared memory during the search goes back: records, returns
         tile_writeback(c, wbase, lane, row0, cnt);
         if (lane < cnt) c.ret[row0 + lane] = s_ret[lane];
