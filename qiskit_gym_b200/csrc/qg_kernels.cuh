@@ -808,6 +808,21 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         }
         return en_all;
     }
+    // MODE_SEARCH: the tile's action weights [cnt][A] are contiguous in global memory: the warp copies them into shared memory with coalesced
+    // 4-byte cp.async (row stride A | 1: odd, so the lanes' rows start in different banks) instead of every lane walking its own row with a
+    // 4*A-byte stride between lanes.  All of a lane's ~A copies are in flight at once, under the record load: through registers the loop held
+    // four loads per lane in flight and a 65 536-env collector decision spent ~10 of its 21 us on their latency.
+    const float* staged_wts = nullptr;
+    if (MODE == MODE_SEARCH && !weights_tile && a.sm_wts >= 0) {
+        float* w = reinterpret_cast<float*>(wbase + a.sm_wts);
+        const uint32_t A = (uint32_t)c.A, rs = A | 1u, total = (uint32_t)cnt * A;
+        const float* src = a.weights + (size_t)e0 * A;
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t e = fastdiv40(i, a.magic_A);
+            cp_async_4(reinterpret_cast<uint32_t*>(w + e * rs + (i - e * A)), reinterpret_cast<const uint32_t*>(src + i));
+        }
+        staged_wts = w;
+    }
     uint32_t last_en_bits = 0;
     if (live && !resident) {
         const uint32_t* src = c.rec + (a.src_slot ? (int64_t)a.src_slot[env] : env);
@@ -815,6 +830,7 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         for (int w = 0; w < c.W; ++w, src += c.Bpad) cp_async_4(&R[w], src);       // all W loads in flight at once
         cp_async_wait_all();
     }
+    if (MODE == MODE_SEARCH && staged_wts) { cp_async_wait_all(); __syncwarp(); }     // (lanes without an environment wait here; rows were written by all lanes)
     uint32_t depth = 0, flags = 0, tick = 0;
     PauliRegs pr{};
     if (live) {
@@ -838,18 +854,6 @@ __device__ __forceinline__ uint32_t step_tile(const DevCfg& c, const StepArgs& a
         if (a.coins) next_coin = load_coin((size_t)env);
     }
     uint32_t acc_done = 0, acc_succ = 0;             // lane l: the tile's is_final / success ballots of step (t & ~31) + l (a.done_bits)
-    // MODE_SEARCH: the tile's action weights [cnt][A] are contiguous in global memory: the warp copies them into shared memory with coalesced
-    // loads (row stride A | 1: odd, so the lanes' rows start in different banks) instead of every lane walking its own row with a 4*A-byte
-    // stride between lanes (a 65 536-env collector decision: 43 -> ~10 us for A = 72)
-    const float* staged_wts = nullptr;
-    if (MODE == MODE_SEARCH && !weights_tile && a.sm_wts >= 0) {
-        float* w = reinterpret_cast<float*>(wbase + a.sm_wts);
-        const uint32_t A = (uint32_t)c.A, rs = A | 1u, total = (uint32_t)cnt * A;
-        const float* src = a.weights + (size_t)e0 * A;
-        for (uint32_t i = lane; i < total; i += 32) { const uint32_t e = fastdiv40(i, a.magic_A); w[e * rs + (i - e * A)] = src[i]; }
-        __syncwarp();
-        staged_wts = w;
-    }
     for (int t = 0; t < a.nsteps; ++t) {
         uint32_t* const hand = pair_base + (t & 1) * a.pair_words;       // (role 1) this step's hand-over buffer
         if (role == 1 && t >= 2) pair_wait(pair_bar, 2 + (t & 1), (uint32_t)((t >> 1) - 1) & 1u);   // ... free again: the store warp is done with step t - 2
