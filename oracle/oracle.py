@@ -71,6 +71,8 @@ def lib():
         L.qgo_bench.restype = C.c_double
         L.qgo_bench.argtypes = [C.POINTER(_abi.QgConfig), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.qgo_digest.argtypes = [C.POINTER(_abi.QgConfig), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qgo_philox_draw.restype = C.c_uint32
         L.qgo_philox_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
         L.qgo_gate_kind_from_name.argtypes = [C.c_char_p, C.c_int32]
@@ -254,6 +256,24 @@ def bench(cfg, targets, lens, actions, coins=None, threads=1):
     if sec < 0:
         raise RuntimeError(L.qgo_last_error().decode())
     return sec, cs.value
+
+
+def digest(cfg, targets, lens, actions, wobs, wmask, coins=None, threads=1):
+    """Per-env uint64 digest over every output of every step (see qgo_digest).  wobs uint64[OBS], wmask uint64[A], all < 2^31."""
+    L = lib()
+    targets = np.ascontiguousarray(targets, dtype=np.int64)
+    lens = np.ascontiguousarray(lens, dtype=np.int64)
+    actions = np.ascontiguousarray(actions, dtype=np.int32)
+    wobs = np.ascontiguousarray(wobs, dtype=np.uint64)
+    wmask = np.ascontiguousarray(wmask, dtype=np.uint64)
+    T, B = actions.shape
+    if coins is not None:
+        coins = np.ascontiguousarray(coins, dtype=np.uint8)
+    out = np.zeros(B, np.uint64)
+    rc = L.qgo_digest(C.byref(cfg), B, _ptr(targets), targets.shape[1], _ptr(lens), T, _ptr(actions), _ptr(coins), threads, _ptr(wobs), _ptr(wmask), _ptr(out))
+    if rc < 0:
+        raise RuntimeError(L.qgo_last_error().decode())
+    return out
 
 
 def philox_draw(seed, env, idx, stream):

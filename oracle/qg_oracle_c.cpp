@@ -204,6 +204,53 @@ QG_API double qgo_bench(const qg_config* cfg, int64_t B, const int64_t* targets,
     } catch (const std::exception& ex) { g_err = ex.what(); return -1.0; }
 }
 
+// ---------------------------------------------------------------------------------------
+// Whole-batch digest for parity at BASELINE.json's full sizes (tests/test_full_size.py): one uint64 per environment that folds EVERY output of
+// EVERY step — all set observation entries, all mask entries, the reward's bit pattern, is_final, success — so that a 65 536 x 128 run is
+// compared env by env without storing 2 GB of observations.  Per step  h = sum(wobs[i] : entry i set) + sum(wmask[j] : action j allowed)
+// + reward_bits * 0x9E3779B1 + is_final * 0x85EBCA6B + success * 0xC2B2AE35  and  digest = digest * 0x100000001B3 + h  (mod 2^64; the
+// weights are < 2^31 so that the same sums can be formed in int64 tensor arithmetic on the device side).  Envs are statically
+// partitioned over `threads` threads; the digest of an env does not depend on the partition.
+// ---------------------------------------------------------------------------------------
+QG_API int qgo_digest(const qg_config* cfg, int64_t B, const int64_t* targets, int64_t stride, const int64_t* lens,
+                      int32_t T, const int32_t* actions, const uint8_t* coins, int threads,
+                      const uint64_t* wobs, const uint64_t* wmask, uint64_t* digest) {
+    try {
+        std::unique_ptr<Env> proto(make_env(cfg));
+        if (threads < 1) threads = 1;
+        std::vector<std::string> errs((size_t)threads);
+        std::vector<std::thread> pool;
+        for (int th = 0; th < threads; ++th) {
+            pool.emplace_back([&, th]() {
+                try {
+                    const int64_t lo = B * th / threads, hi = B * (th + 1) / threads;
+                    for (int64_t b = lo; b < hi; ++b) {
+                        std::unique_ptr<Env> e(proto->clone());
+                        e->set_state(std::vector<int64_t>(targets + b * stride, targets + b * stride + lens[b]));
+                        uint64_t d = 0;
+                        for (int t = 0; t < T; ++t) {
+                            const size_t k = (size_t)t * B + b;
+                            if (coins) { OneShotRng r(coins[k] ? 0x80000000u : 0u); e->step((size_t)(int64_t)actions[k], &r); }
+                            else e->step((size_t)(int64_t)actions[k], nullptr);
+                            uint64_t h = 0;
+                            for (size_t i : e->observe(nullptr)) h += wobs[i];
+                            const std::vector<bool> m = e->masks();
+                            for (size_t j = 0; j < m.size(); ++j) if (m[j]) h += wmask[j];
+                            const float r = e->reward(); uint32_t rb; std::memcpy(&rb, &r, 4);
+                            h += (uint64_t)rb * 0x9E3779B1ull + (e->is_final() ? 0x85EBCA6Bull : 0ull) + (e->success() ? 0xC2B2AE35ull : 0ull);
+                            d = d * 0x100000001B3ull + h;
+                        }
+                        digest[b] = d;
+                    }
+                } catch (const std::exception& ex) { errs[(size_t)th] = ex.what(); }
+            });
+        }
+        for (auto& t : pool) t.join();
+        for (auto& er : errs) if (!er.empty()) { g_err = er; return -1; }
+        return 0;
+    } catch (const std::exception& ex) { g_err = ex.what(); return -1; }
+}
+
 QG_API int qgo_gate_kind_from_name(const char* name, int32_t n_idx) {
     const int k = parse_gate_name(name ? name : "", (size_t)n_idx);
     return k == -1 ? QG_ERR_INVALID : k == -2 ? QG_ERR_STATE : k;

@@ -126,3 +126,52 @@ def test_scattered_sample_matches_oracle_and_small_batch_full_size(name):
     obs_s = torch.empty((1, S, osz), dtype=torch.float32, device=dev)
     small.replay(torch.from_numpy(sub_a).to(dev), obs=obs_s, reward=rew_s)
     assert torch.equal(rew_s.view(torch.int32), rew[:, pk].view(torch.int32)) and torch.equal(obs_s[0], obs[0, pk])
+
+
+def _device_digest(obs_all, mask_all, rew, done, succ, wobs, wmask):
+    """The oracle's per-env digest (oracle/qg_oracle_c.cpp: qgo_digest) formed from the engine's output tensors: int64 arithmetic wraps like uint64."""
+    dev = obs_all.device
+    T, B = rew.shape
+    wo = torch.from_numpy(wobs.astype(np.int64)).to(dev)
+    wm = torch.from_numpy(wmask.astype(np.int64)).to(dev)
+    d = torch.zeros(B, dtype=torch.int64, device=dev)
+    for t in range(T):
+        h = (obs_all[t].to(torch.int64) * wo).sum(1) + (mask_all[t].to(torch.int64) * wm).sum(1)
+        rb = rew[t].view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        h = h + rb * 0x9E3779B1 + done[t].to(torch.int64) * 0x85EBCA6B + succ[t].to(torch.int64) * 0xC2B2AE35
+        d = d * 0x100000001B3 + h
+    return d
+
+
+@pytest.mark.parametrize("name,inverts", [("C1_perm_grid3", False), ("C2_lf8_line", False), ("C3_clifford8_full", False), ("C4_pauli10_line", False),
+                                          ("C5_perm27_heavyhex", False), ("C2_lf8_line", True), ("C3_clifford8_full", True), ("C1_perm_grid3", True)])
+def test_whole_batch_digest_matches_oracle_full_size(name, inverts):
+    """EVERY environment of the full 65 536 x 128 batch against the oracle: every observation entry, mask entry, reward bit pattern and flag of
+    every step, folded into one uint64 per environment on both sides (the oracle runs on all host threads; one observation slab per step is
+    kept on the device, as in bench.py)."""
+    import os
+    env, kind, n, gateset, kw = _env(name, B_FULL, **({"add_inverts": True} if inverts else {}))
+    dev, A = env.device, len(gateset)
+    tarr = _targets(kind, n, gateset, B_FULL, 17, kw)
+    rng = np.random.Generator(np.random.PCG64(123))
+    actions = H.random_actions(rng, T_FULL, B_FULL, A, 0.01)
+    osz = int(np.prod(env.obs_shape()))
+    wobs = rng.integers(1, 2 ** 31, size=osz, dtype=np.uint64)
+    wmask = rng.integers(1, 2 ** 31, size=A, dtype=np.uint64)
+    env.set_state(tarr)
+    env.observe()
+    obs_all = torch.empty((T_FULL, B_FULL, osz), dtype=torch.float32, device=dev)
+    mask_all = torch.empty((T_FULL, B_FULL, A), dtype=torch.bool, device=dev)
+    rew = torch.empty((T_FULL, B_FULL), dtype=torch.float32, device=dev)
+    done = torch.empty((T_FULL, B_FULL), dtype=torch.bool, device=dev)
+    succ = torch.empty((T_FULL, B_FULL), dtype=torch.bool, device=dev)
+    coins = rng.integers(0, 2, size=(T_FULL, B_FULL)).astype(np.uint8) if inverts else None       # the invert coin of every step, injected on both sides
+    env.replay(torch.from_numpy(actions).to(dev), coins=None if coins is None else torch.from_numpy(coins).to(dev), obs=obs_all, mask=mask_all, reward=rew, done=done,
+               success=succ)
+    got = _device_digest(obs_all, mask_all, rew, done, succ, wobs, wmask).cpu().numpy().view(np.uint64)
+    del obs_all, mask_all
+    cfg = H.make_cfg(kind, n, gateset, add_perms=False, **kw)
+    ref = orc.digest(cfg, tarr, H.payload_lengths(kind, n, tarr), actions, wobs, wmask, coins=coins, threads=max(1, min(32, os.cpu_count() or 1)))
+    bad = np.nonzero(got != ref)[0]
+    assert bad.size == 0, f"{name}: {bad.size} of {B_FULL} environments differ from the oracle, first {bad[:8].tolist()}"
+    assert int(env.errors().max().item()) == 0
