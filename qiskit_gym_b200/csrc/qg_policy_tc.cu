@@ -71,18 +71,9 @@ __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t 
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem]^T, f16 inputs, f32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        " setp.ne.b32 p, %4, 0;\n"
-        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies tcgen05.fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-// The same two for a whole converged warp: every lane runs the issue loop with warp-uniform operands and one elected lane (always the same
+// D[tmem] (+)= A[smem] * B[smem]^T, f16 inputs, f32 accumulate (tcgen05.mma), and tcgen05.commit: all MMAs issued so far by the issuing
+// thread arrive on the mbarrier when they have completed (implies tcgen05.fence::before_thread_sync) —
+// for a whole converged warp: every lane runs the issue loop with warp-uniform operands and one elected lane (always the same
 // one for the full mask) issues.  Under `if (lane == 0)` the compiler cannot tell that one lane is active and wraps every tcgen05.mma in a loop
 // that broadcasts its operands into uniform registers (ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY): ~20 instructions and ~115 cycles per MMA in
 // the fused kernel, more than a 64-cycle layer-1 product takes on the tensor pipe (cuobjdump -sass, profiles/r2_v36_tc_probe.json).
@@ -205,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        {   // (the whole warp runs the issue loop, an elected lane issues: see umma_f16_w)
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             const uint32_t idesc = instr_desc(a.NT);
             const uint32_t lbo_a = kM * 16, lbo_b = (uint32_t)a.NT * 16, sbo = 128;
@@ -222,14 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_layer(const __grid_constant_
                     for (int k = 0; k < kKB / 16; ++k) {            // one MMA covers K = 16: two 8-wide chunks, lbo apart
                         const uint64_t a_hi = smem_desc(sa0 + 2u * k * lbo_a, lbo_a, sbo), b_hi = smem_desc(sb0 + 2u * k * lbo_b, lbo_b, sbo);
                         const uint64_t b_lo = smem_desc(sb1 + 2u * k * lbo_b, lbo_b, sbo);
-                        umma_f16(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
-                        umma_f16(d, a_hi, b_lo, idesc, 1u);
-                        if (a.a_terms == 2) umma_f16(d, smem_desc(sa1 + 2u * k * lbo_a, lbo_a, sbo), b_hi, idesc, 1u);
+                        umma_f16_w(d, a_hi, b_hi, idesc, (kb | k) ? 1u : 0u);
+                        umma_f16_w(d, a_hi, b_lo, idesc, 1u);
+                        if (a.a_terms == 2) umma_f16_w(d, smem_desc(sa1 + 2u * k * lbo_a, lbo_a, sbo), b_hi, idesc, 1u);
                     }
-                    umma_commit(empty + stage);                     // the stage is free once these MMAs have read it
+                    umma_commit_w(empty + stage);                     // the stage is free once these MMAs have read it
                     if (++stage == (uint32_t)kNumStages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(acc_full + as);                         // accumulator complete -> epilogue
+                umma_commit_w(acc_full + as);                         // accumulator complete -> epilogue
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }

@@ -175,3 +175,64 @@ def test_whole_batch_digest_matches_oracle_full_size(name, inverts):
     bad = np.nonzero(got != ref)[0]
     assert bad.size == 0, f"{name}: {bad.size} of {B_FULL} environments differ from the oracle, first {bad[:8].tolist()}"
     assert int(env.errors().max().item()) == 0
+
+
+def _digest_case(name, seed):
+    import os
+    env, kind, n, gateset, kw = _env(name, B_FULL)
+    A = len(gateset)
+    tarr = _targets(kind, n, gateset, B_FULL, seed, kw)
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    actions = H.random_actions(rng, T_FULL, B_FULL, A, 0.01)
+    osz = int(np.prod(env.obs_shape()))
+    wobs = rng.integers(1, 2 ** 31, size=osz, dtype=np.uint64)
+    wmask = rng.integers(1, 2 ** 31, size=A, dtype=np.uint64)
+    cfg = H.make_cfg(kind, n, gateset, add_perms=False, **kw)
+    ref = orc.digest(cfg, tarr, H.payload_lengths(kind, n, tarr), actions, wobs, wmask, threads=max(1, min(32, os.cpu_count() or 1)))
+    return env, tarr, actions, osz, A, wobs, wmask, ref
+
+
+@pytest.mark.parametrize("name", ["C1_perm_grid3", "C4_pauli10_line", "C5_perm27_heavyhex"])
+def test_whole_batch_digest_single_step_launches_full_size(name):
+    """The same whole-batch comparison through 128 single-step launches (qg_step: the policy-in-the-loop granularity; 16-env warp tiles for the
+    large observations of C4 / C5)."""
+    env, tarr, actions, osz, A, wobs, wmask, ref = _digest_case(name, 19)
+    dev = env.device
+    env.set_state(tarr)
+    env.observe()
+    a_dev = torch.from_numpy(actions).to(dev)
+    obs_t = torch.empty((B_FULL, osz), dtype=torch.float32, device=dev)
+    mask_t = torch.empty((B_FULL, A), dtype=torch.bool, device=dev)
+    wo = torch.from_numpy(wobs.astype(np.int64)).to(dev)
+    wm = torch.from_numpy(wmask.astype(np.int64)).to(dev)
+    d = torch.zeros(B_FULL, dtype=torch.int64, device=dev)
+    for t in range(T_FULL):
+        env.step(a_dev[t], obs=obs_t, mask=mask_t)
+        d = _device_digest(obs_t[None], mask_t[None], env.reward[None], env.done[None], env.success[None], wobs, wmask) + d * 0x100000001B3
+    got = d.cpu().numpy().view(np.uint64)
+    bad = np.nonzero(got != ref)[0]
+    assert bad.size == 0, f"{name}: {bad.size} of {B_FULL} environments differ from the oracle, first {bad[:8].tolist()}"
+
+
+@pytest.mark.parametrize("name", ["C3_clifford8_full", "C4_pauli10_line", "C1_perm_grid3"])
+def test_whole_batch_digest_packed_observations_full_size(name):
+    """... and through the packed-bit observation path (qg_replay_bits: what the fused policy kernels read), bits unpacked on the device."""
+    env, tarr, actions, osz, A, wobs, wmask, ref = _digest_case(name, 23)
+    dev = env.device
+    env.set_state(tarr)
+    env.observe()
+    W = env.obs_words()
+    bits = torch.empty((T_FULL, B_FULL, W), dtype=torch.int32, device=dev)
+    mask_all = torch.empty((T_FULL, B_FULL, A), dtype=torch.bool, device=dev)
+    rew = torch.empty((T_FULL, B_FULL), dtype=torch.float32, device=dev)
+    done = torch.empty((T_FULL, B_FULL), dtype=torch.bool, device=dev)
+    succ = torch.empty((T_FULL, B_FULL), dtype=torch.bool, device=dev)
+    env.replay_bits(torch.from_numpy(actions).to(dev), obs_bits=bits, mask=mask_all, reward=rew, done=done, success=succ)
+    sh = torch.arange(32, dtype=torch.int32, device=dev)
+    d = torch.zeros(B_FULL, dtype=torch.int64, device=dev)
+    for t in range(T_FULL):
+        dense = ((bits[t][:, :, None] >> sh) & 1).reshape(B_FULL, W * 32)[:, :osz].to(torch.float32)
+        d = _device_digest(dense[None], mask_all[t][None], rew[t][None], done[t][None], succ[t][None], wobs, wmask) + d * 0x100000001B3
+    got = d.cpu().numpy().view(np.uint64)
+    bad = np.nonzero(got != ref)[0]
+    assert bad.size == 0, f"{name}: {bad.size} of {B_FULL} environments differ from the oracle, first {bad[:8].tolist()}"
