@@ -695,10 +695,6 @@ __device__ __forceinline__ void pair_wait(uint64_t* bars, int idx, uint32_t pari
 }
 #else
 // (immediate barrier numbers 0..3: with the number in a register ptxas reserves all 16 barriers for the CTA and the SM holds 4 CTAs instead of 16)
-#ifdef QG_PAIR_DYNBAR        // (tools A/B build)
-__device__ __forceinline__ void pair_arrive(uint64_t*, int idx, int) { asm volatile("bar.arrive %0, 64;\n" ::"r"(idx + 1) : "memory"); }
-__device__ __forceinline__ void pair_wait(uint64_t*, int idx, uint32_t) { asm volatile("bar.sync %0, 64;\n" ::"r"(idx + 1) : "memory"); }
-#else
 __device__ __forceinline__ void pair_arrive(uint64_t*, int idx, int) {
     switch (idx) {
         case 0: asm volatile("bar.arrive 0, 64;\n" ::: "memory"); break;
@@ -715,7 +711,6 @@ __device__ __forceinline__ void pair_wait(uint64_t*, int idx, uint32_t) {
         default: asm volatile("bar.sync 3, 64;\n" ::: "memory"); break;
     }
 }
-#endif
 #endif
 
 // Rows of the action / coin streams that the copy engine is still bringing from the host (qg_replay_host_packed): the warp that is about to read
@@ -1145,11 +1140,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, INV == 32 ? 8 : 16) k_step(
 #endif
         // (which warp of the CTA steps alternates with the CTA index, so that the issue-heavy step warps do not all sit on the same
         // scheduler if warps are assigned to the SM's sub-partitions by their index within the CTA)
-#ifdef QG_PAIR_NOALT
-        const bool steps = warp == 0;
-#else
         const bool steps = warp == (int)(blockIdx.x & 1u);
-#endif
         if (steps) step_tile<KIND, MODE, INV, EPW, 1>(c, a, wbase, lut, lane, e0, cnt);
         else step_tile<KIND, MODE, INV, EPW, 2>(c, a, wbase, lut, lane, e0, cnt);
     } else {

@@ -1,7 +1,9 @@
 #!/bin/bash
 # Replay A/B of the warp-pair variants (tools builds) over two observation-ring sizes: ring 0 = the bench's automatic ring (5 slabs for C3: a tile
 # rewrites a slab every 5 steps), ring 128 = one slab per step (every byte of a launch has to reach DRAM).
-# knobs = product kernels (named barriers, immediate numbers), knobs_dyn = barrier number in a register, knobs_mb = mbarriers + relaxed arrive.
+# knobs = product kernels (named barriers, immediate numbers; make EXTRA=-DQG_TOOLS_KNOBS), knobs_mb = mbarriers + relaxed arrive (EXTRA="-DQG_TOOLS_KNOBS
+# -DQG_PAIR_MBARRIER"), knobs_dyn = the first pair kernel: barrier number in a register, which made ptxas reserve 16 barriers per CTA (4 CTAs per SM) — that
+# variant was removed from the tree after this experiment (profiles/r2_v26_pair_ab.txt); QG_REPLAY_CTAS=4 with the product kernels is its equivalent.
 TAG=${1:-r2_v26}
 O=gpurun_out
 F="--steps 20 --warmup 3 --no-cpu-baseline --no-synth --no-collector --no-e2e --no-per-step --no-packed"
