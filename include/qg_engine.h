@@ -222,7 +222,8 @@ QG_API int qg_replay_host_packed(qg_engine* e, int32_t num_steps, const uint8_t*
                                  uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream);
 /* The same call without the final synchronisation: returns once everything is queued on `stream`; the host buffers are the call's until the
  * stream (or an event recorded on it after the call) has been waited for.  A collector keeps two episodes in flight — queue episode k + 1 (its
- * own output buffers), then wait for episode k and read its rewards / flags — so the device never idles across the host's turn-around. */
+ * own output buffers), then wait for episode k and read its rewards / flags — so the device never idles across the host's turn-around.
+ * Neither form can be captured into a CUDA graph (the staged inputs use a second, engine-owned stream). */
 QG_API int qg_replay_host_packed_async(qg_engine* e, int32_t num_steps, const uint8_t* actions8_host, const uint8_t* coins_host,
                                        float* obs_dev, uint8_t* mask_dev, int32_t ring, float* reward_host, float* reward_dev,
                                        uint32_t* done_bits_host, uint32_t* success_bits_host, qg_stream stream);
