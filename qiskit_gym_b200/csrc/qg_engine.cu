@@ -156,7 +156,12 @@ int qg::launch_step(qg_engine* e, int mode, StepArgs a, cudaStream_t st, int64_t
     LaunchGeom g{(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), ((size_t)kLutWords + (size_t)a.sm_warp_words * kWarpsPerCta) * 4, a.pdl_mode ? 1 : 0, epw};
     if (a.pair) { g.grid = (unsigned)tiles; g.smem_bytes = ((size_t)kLutWords + (size_t)a.sm_warp_words) * 4; }
     // the bound: the request is padded to 1 / resident of the SM's shared memory
-    if (mode == MODE_STEP && a.nsteps >= 8 && a.obs && resident >= 2) {
+    int resident_step = 0;           // (tools builds: QG_STEP_CTAS bounds single-step launches the same way)
+#ifdef QG_TOOLS_KNOBS
+    if (mode == MODE_STEP && a.nsteps < 8 && a.obs) resident_step = e->step_ctas;
+#endif
+    if (resident_step >= 2) resident = resident_step;
+    if (mode == MODE_STEP && (a.nsteps >= 8 || resident_step >= 2) && a.obs && resident >= 2) {
         const size_t cap = (kSmSharedBytes / (size_t)resident - 1024) & ~(size_t)127;
         if (cap > g.smem_bytes) g.smem_bytes = cap;
     }
@@ -307,6 +312,7 @@ int qg_create(const qg_config* cfg, int32_t device, int64_t batch, void* workspa
     if (const char* v = std::getenv("QG_STAGGER_NS")) e->stagger_ns = std::atoi(v);
     if (const char* v = std::getenv("QG_EPW")) e->epw_forced = std::atoi(v);
     if (const char* v = std::getenv("QG_REPLAY_CTAS")) e->replay_ctas = std::atoi(v);
+    if (const char* v = std::getenv("QG_STEP_CTAS")) e->step_ctas = std::atoi(v);
     if (const char* v = std::getenv("QG_PAIR")) e->pair_forced = std::atoi(v) > 0 ? 1 : -1;      // 0: single-warp tiles in replay launches too
 #endif
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) e->num_sms = v; }

@@ -31,6 +31,7 @@ struct qg_engine {
     int cat_words = 0;               // words of a 32-env tile's concatenated observation stream (0: this config does not use expand_cat)
     int epw_forced = 0;              // (tools builds only: 16 / 32 forces the tile size)
     int replay_ctas = 0;             // (tools builds only, QG_REPLAY_CTAS: CTAs an SM may hold in replay launches, -1 = whatever fits; 0 = launch_step's rule)
+    int step_ctas = 0;               // (tools builds only, QG_STEP_CTAS: the same bound for single-step launches)
     int pair_forced = 0;             // (tools builds only, QG_PAIR=0 -> -1: no warp pairs in replay launches)
     uint64_t magic_obs = 0, magic_A = 0; uint32_t magic_vpe = 0, magic_a4 = 0;
     int nperms = 0;
