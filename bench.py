@@ -470,7 +470,8 @@ def run_ours(args):
                "note": ("qg_replay_host_packed_async, pinned NUMA-local host buffers, two episodes in flight (episode i + 1 is queued, with its own output buffers, "
                         "before the host waits for episode i and reads its rewards / flags): every episode's uint8 actions [T][B] are copied from pinned host memory "
                         "by the copy engine in flagged chunks while the kernel plays; f32 reward [T][B] and the is_final / success bit planes uint32[B/32][T] are "
-                        "written by the kernel to host memory and read by the host; one launch per episode, obs + mask stay on the device.  sync_value: "
+                        "written by the kernel to host memory and read by the host; one launch per episode, obs + mask stay on the device (it can exceed the device-resident "
+                        "`value`, whose launch also writes int32-action-stream-sized reward / done / success tensors to HBM: here those streams leave over PCIe).  sync_value: "
                         "qg_replay_host_packed, one episode at a time (the call returns when the stream is synchronised)") if e2e_packed else "qg_replay_host (int32 actions; f32 reward, u8 done, u8 success)",
                "steps": Ke,
                "sync_value": e2e_packed["sync_value"] if e2e_packed else wide,             # one episode at a time, synchronous call
